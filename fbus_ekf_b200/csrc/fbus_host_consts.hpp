@@ -1,0 +1,122 @@
+// fbus_host_consts.hpp -- host-side derivation of the per-run constants (DevConsts) from fbus_config,
+// and the default configuration of the reference's bundled logs.  Plain C++ (no CUDA).
+//
+// Mirrors what FILTER::FILTER (C++/include/filter.hpp:63-137), the per-call prologues of
+// filter.cpp:369-372/411-414/629-632, main.cpp:192-203 (marker rotation -> quaternion) and
+// vision.cpp:476-481 compute from the YAML values.
+#pragma once
+
+#include <string.h>
+
+#include "../../include/fbus_ekf.h"
+#include "fbus_math.cuh"
+
+namespace fbus {
+
+inline void host_quat_left(const double* q, double* m) {  // matrix_math.hpp:38-62
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double t[16] = {w, -x, -y, -z, x, w, -z, y, y, z, w, -x, z, -y, x, w};
+    memcpy(m, t, sizeof t);
+}
+inline void host_quat_right(const double* q, double* m) {  // matrix_math.hpp:64-88
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double t[16] = {w, -x, -y, -z, x, w, z, -y, y, -z, w, x, z, y, -x, w};
+    memcpy(m, t, sizeof t);
+}
+
+inline int make_dev_consts(const fbus_config* c, DevConsts* k) {
+    if (c->n_markers < 0 || c->n_markers > MAXM) return FBUS_E_BADARG;
+    memset(k, 0, sizeof *k);
+    const double flip[3] = {-1.0, -1.0, 1.0};  // T_C_I, filter.hpp:67-69
+    double P_LI[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) k->R_IL[i * 3 + j] = flip[i] * c->tsc_left[i * 4 + j];
+        P_LI[i] = flip[i] * c->tsc_left[i * 4 + 3];
+    }
+    R2q(k->R_IL, k->Q_IL);  // Quaterniond(R_I_L), NOT normalised (filter.cpp:370)
+    for (int i = 0; i < 3; ++i)  // P_I_L = -R_I_L^T * P_L_I (filter.cpp:372)
+        k->P_IL[i] = -(k->R_IL[i] * P_LI[0] + k->R_IL[3 + i] * P_LI[1] + k->R_IL[6 + i] * P_LI[2]);
+    k->Qd[0] = c->accel_n_cov; k->Qd[1] = c->gyro_n_cov; k->Qd[2] = c->accel_b_cov; k->Qd[3] = c->gyro_b_cov;
+    k->Rp = c->pos_n_cov; k->Rq = c->quat_n_cov;
+    k->max_dist = c->marker_max_dist; k->switch_thres = c->marker_switch_thres; k->reset_gap = c->reset_gap;
+    // vision view (raw T_SC): R_R_L = R_I_L R_I_R^T ; P_L_R = P_L_I - R_R_L P_R_I (vision.cpp:476-481)
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int x = 0; x < 3; ++x) s += c->tsc_left[i * 4 + x] * c->tsc_right[j * 4 + x];
+            k->R_RL[i * 3 + j] = s;
+        }
+    for (int i = 0; i < 3; ++i) {
+        const double t = k->R_RL[i * 3] * c->tsc_right[3] + k->R_RL[i * 3 + 1] * c->tsc_right[7] + k->R_RL[i * 3 + 2] * c->tsc_right[11];
+        k->P_LR[i] = c->tsc_left[i * 4 + 3] - t;
+    }
+    k->a0 = c->n_air / c->n_glass;
+    k->a1 = c->n_glass / c->n_water;
+    k->air_lt_glass = c->n_air < c->n_glass;      // vision.cpp:511
+    k->glass_gt_water = c->n_glass > c->n_water;  // vision.cpp:531
+    k->d_air = c->d_air; k->d_glass = c->d_glass;
+    for (int i = 0; i < 3; ++i) k->normal[i] = c->normal[i];
+    k->dect_thres = c->marker_dect_dist_thres;
+    k->n_markers = c->n_markers;
+    k->flags = c->flags;
+    double Lil[16];
+    host_quat_left(k->Q_IL, Lil);
+    for (int m = 0; m < c->n_markers; ++m) {
+        MarkerConst& mk = k->mk[m];
+        mk.id = c->marker_id[m];
+        for (int i = 0; i < 3; ++i) mk.p[i] = c->marker_pos[m * 3 + i];
+        R2q(&c->marker_rot[m * 9], mk.q);  // main.cpp:201
+        double Rq[16], A1[16];
+        host_quat_right(mk.q, Rq);
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double s = 0.0;
+                for (int x = 0; x < 4; ++x) s += Rq[i * 4 + x] * Lil[x * 4 + j];
+                A1[i * 4 + j] = s;
+            }
+        for (int i = 0; i < 4; ++i)  // * L2 = diag(1,-1,-1,-1)
+            for (int j = 0; j < 4; ++j) mk.CM[i * 4 + j] = (j == 0) ? A1[i * 4 + j] : -A1[i * 4 + j];
+    }
+    return FBUS_OK;
+}
+
+inline void config_default(fbus_config* c) {
+    memset(c, 0, sizeof *c);
+    // C++/config/camerainfo1.yml (== matlab/config/camerainfo.yml): the calibration of the bundled logs
+    const double tl[16] = {-0.999862, 0.015685, -0.00548, 0.059967, -0.015639, -0.999843, -0.00827, 0.000127837,
+                           -0.005609, -0.008183, 0.999951, -0.002, 0, 0, 0, 1};
+    const double tr[16] = {-0.999826, 0.00929485, -0.0161445, -0.0601272, -0.00937869, -0.999942, 0.00514829, 0.000124714,
+                           -0.0160959, 0.00529897, 0.999857, -0.002, 0, 0, 0, 1};
+    memcpy(c->tsc_left, tl, sizeof tl);
+    memcpy(c->tsc_right, tr, sizeof tr);
+    // C++/config/paramconfig.yml:44-57
+    c->accel_n_cov = 0.001; c->gyro_n_cov = 0.0001; c->accel_b_cov = 0.001; c->gyro_b_cov = 0.0001;
+    c->pos_n_cov = 0.001; c->quat_n_cov = 0.001;
+    c->marker_max_dist = 2.0; c->marker_switch_thres = 0.5;
+    // filter.hpp:29-34
+    const double p0[6] = {0.0001, 0.01, 0.0001, 1e-2, 1e-2, 100.0};
+    memcpy(c->p0_diag, p0, sizeof p0);
+    c->reset_gap = 0.1;  // filter.cpp:462
+    // paramconfig.yml:30-42
+    c->n_air = 1.00; c->n_water = 1.32; c->n_glass = 1.49; c->d_air = 0.002; c->d_glass = 0.02;
+    c->normal[0] = 0; c->normal[1] = 0; c->normal[2] = 1;
+    c->marker_dect_dist_thres = 2.0;  // paramconfig.yml:27
+    // C++/config/markersetup.yml
+    static const int ids[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 16, 17, 18};
+    static const double pos[12][3] = {{0, 0, 0}, {0, 0.61, 0.285}, {0, 0.61, 1.185}, {0, 0.61, 2.085}, {0, 0.61, 2.985},
+                                      {0, 0.265, 4.12}, {0, -0.635, 4.12}, {0, -1.535, 4.12}, {0, -2.435, 4.12},
+                                      {0, -2.7, 0}, {0, -1.8, 0}, {0, -0.9, 0}};
+    static const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    static const double Rx90[9] = {1, 0, 0, 0, 0, -1, 0, 1, 0};
+    static const double Rx180[9] = {1, 0, 0, 0, -1, 0, 0, 0, -1};
+    c->n_markers = 12;
+    for (int m = 0; m < 12; ++m) {
+        c->marker_id[m] = ids[m];
+        for (int i = 0; i < 3; ++i) c->marker_pos[m * 3 + i] = pos[m][i];
+        const double* R = (m == 0 || m >= 9) ? I3 : (m <= 4 ? Rx90 : Rx180);
+        memcpy(&c->marker_rot[m * 9], R, sizeof I3);
+    }
+    c->flags = 0;
+}
+
+}  // namespace fbus

@@ -1,0 +1,721 @@
+// fbus_math.cuh -- per-filter math of the batched FBUS-EKF hot path (device inlines).
+//
+// One CUDA thread owns one filter.  The 18x18 covariance is kept PACKED-SYMMETRIC (171 doubles) in
+// shared memory, laid out [element][thread] so that a warp touches 32 consecutive doubles per access;
+// the nominal state (29 doubles) lives in registers.  All loops are compile-time unrolled: every
+// shared-memory address is an immediate offset from one base register.
+//
+// The arithmetic exploits the structure the reference multiplies out densely:
+//   F = I + N has six small non-zero blocks (filter.cpp:598-604); Gamma*Q*Gamma^T is diagonal
+//   (filter.hpp:108-125); H has two non-zero block columns (filter.cpp:690-694).
+// Results agree with the dense reference evaluation to rounding (~1e-16 relative), far inside the
+// 1e-9 parity tolerance; see DESIGN.md for the derivations and tests/ for the parity checks.
+//
+// The header also compiles for the host (FBUS_HD expands to nothing without nvcc) -- used only by
+// tests/host_math_harness.cpp to debug the math against the oracle on machines without a GPU.  The
+// product never runs this code on the CPU.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define FBUS_HD __host__ __device__ __forceinline__
+#define FBUS_UNROLL _Pragma("unroll")
+#else
+#define FBUS_HD inline
+#define FBUS_UNROLL
+#endif
+
+namespace fbus {
+
+constexpr int NX = 18;
+constexpr int NPK = 171;
+constexpr int MAXM = 16;  // marker-map capacity (FBUS_MAX_MARKERS)
+
+// packed upper-triangular index of P(i,j)
+FBUS_HD constexpr int pidx_u(int i, int j) { return i * NX - (i * (i - 1)) / 2 + (j - i); }
+FBUS_HD constexpr int pidx(int i, int j) { return i <= j ? pidx_u(i, j) : pidx_u(j, i); }
+
+// per-run constants (derived on the host from fbus_config; passed by value as a kernel parameter)
+struct MarkerConst {
+    double p[3];    // positionAtG
+    double q[4];    // quaternionM2G = Quaterniond(rotation), main.cpp:201
+    double CM[16];  // R(Q_M) * L(Q_IL) * L2   (constant factor of H[3:7,6:9], filter.cpp:693-694)
+    int32_t id;
+    int32_t pad;
+};
+struct DevConsts {
+    double R_IL[9], Q_IL[4], P_IL[3];  // filter view: T_C_I * T_SC_left (filter.hpp:67-69)
+    double Qd[4];                      // accel_n, gyro_n, accel_b, gyro_b covariances
+    double Rp, Rq;                     // pos / quat measurement covariances
+    double max_dist, switch_thres, reset_gap;
+    double R_RL[9], P_LR[3];           // vision view: raw T_SC (vision.cpp:476-481)
+    double a0, a1;                     // n_air/n_glass, n_glass/n_water
+    double d_air, d_glass, normal[3], dect_thres;
+    int32_t air_lt_glass, glass_gt_water;
+    int32_t n_markers, flags;
+    MarkerConst mk[MAXM];
+};
+
+// nominal state held in registers (NominalState, common.hpp:205-225)
+struct Nominal {
+    double t, q[4], R[9], p[3], v[3], ba[3], bg[3], g[3];
+};
+
+// ------------------------------------------------------------------------------------------------
+// quaternion / rotation device inlines (matrix_math.hpp + the Eigen rules of SURVEY A.1)
+// ------------------------------------------------------------------------------------------------
+FBUS_HD void qmul(const double* a, const double* b, double* o) {
+    const double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    const double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    const double y = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+    const double z = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+    o[0] = w; o[1] = x; o[2] = y; o[3] = z;
+}
+FBUS_HD void qmul_conjb(const double* a, const double* b, double* o) {  // a * conj(b)
+    const double bb[4] = {b[0], -b[1], -b[2], -b[3]};
+    qmul(a, bb, o);
+}
+FBUS_HD void qnormalize(double* q) {
+    const double inv = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+FBUS_HD void q2R(const double* q, double* R) {  // Eigen toRotationMatrix, literal also for non-unit q
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+FBUS_HD void R2q(const double* m, double* q) {  // Eigen Quaterniond(Matrix3d), not normalised
+    double t = m[0] + m[4] + m[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q[0] = 0.5 * t;
+        t = 0.5 / t;
+        q[1] = (m[7] - m[5]) * t;
+        q[2] = (m[2] - m[6]) * t;
+        q[3] = (m[3] - m[1]) * t;
+    } else {
+        // branch-per-case keeps every index static (no local-memory arrays on the device)
+        if (m[0] >= m[4] && m[0] >= m[8]) {  // i=0,j=1,k=2   (ties -> lowest index, as Eigen)
+            t = sqrt(m[0] - m[4] - m[8] + 1.0);
+            q[1] = 0.5 * t; t = 0.5 / t;
+            q[0] = (m[7] - m[5]) * t; q[2] = (m[3] + m[1]) * t; q[3] = (m[6] + m[2]) * t;
+        } else if (m[4] > m[0] && m[4] >= m[8]) {  // i=1,j=2,k=0
+            t = sqrt(m[4] - m[8] - m[0] + 1.0);
+            q[2] = 0.5 * t; t = 0.5 / t;
+            q[0] = (m[2] - m[6]) * t; q[3] = (m[7] + m[5]) * t; q[1] = (m[1] + m[3]) * t;
+        } else {  // i=2,j=0,k=1
+            t = sqrt(m[8] - m[0] - m[4] + 1.0);
+            q[3] = 0.5 * t; t = 0.5 / t;
+            q[0] = (m[3] - m[1]) * t; q[1] = (m[2] + m[6]) * t; q[2] = (m[5] + m[7]) * t;
+        }
+    }
+}
+FBUS_HD void mat3_vec(const double* M, const double* v, double* o) {
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) o[i] = M[i * 3] * v[0] + M[i * 3 + 1] * v[1] + M[i * 3 + 2] * v[2];
+}
+FBUS_HD void mat3t_vec(const double* M, const double* v, double* o) {  // M^T v
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) o[i] = M[i] * v[0] + M[3 + i] * v[1] + M[6 + i] * v[2];
+}
+FBUS_HD double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+// ------------------------------------------------------------------------------------------------
+// covariance accessor: packed symmetric storage with element stride S (S = block size in shared
+// memory on the device, 1 on the host harness)
+// ------------------------------------------------------------------------------------------------
+template <int S>
+struct Cov {
+    double* s;
+    FBUS_HD double ld(int i, int j) const { return s[pidx(i, j) * S]; }
+    FBUS_HD void st(int i, int j, double v) const { s[pidx(i, j) * S] = v; }
+    // X[r*3+c] = P[3bi+r][3bj+c]  (off-diagonal block, any order of bi,bj)
+    FBUS_HD void ldblk(int bi, int bj, double* X) const {
+        FBUS_UNROLL
+        for (int r = 0; r < 3; ++r)
+            FBUS_UNROLL
+            for (int c = 0; c < 3; ++c) X[r * 3 + c] = ld(3 * bi + r, 3 * bj + c);
+    }
+    // diagonal block expanded to a full symmetric 3x3 (6 loads)
+    FBUS_HD void lddiag(int b, double* X) const {
+        FBUS_UNROLL
+        for (int r = 0; r < 3; ++r)
+            FBUS_UNROLL
+            for (int c = r; c < 3; ++c) {
+                const double v = ld(3 * b + r, 3 * b + c);
+                X[r * 3 + c] = v;
+                X[c * 3 + r] = v;
+            }
+    }
+    FBUS_HD void ldany(int bi, int bj, double* X) const {
+        if (bi == bj) lddiag(bi, X);
+        else ldblk(bi, bj, X);
+    }
+    FBUS_HD void stblk(int bi, int bj, const double* X) const {  // bi < bj
+        FBUS_UNROLL
+        for (int r = 0; r < 3; ++r)
+            FBUS_UNROLL
+            for (int c = 0; c < 3; ++c) st(3 * bi + r, 3 * bj + c, X[r * 3 + c]);
+    }
+    FBUS_HD void stdiag(int b, const double* X) const {  // upper 6 of X
+        FBUS_UNROLL
+        for (int r = 0; r < 3; ++r)
+            FBUS_UNROLL
+            for (int c = r; c < 3; ++c) st(3 * b + r, 3 * b + c, X[r * 3 + c]);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// F1: covariance propagation  P <- F P F^T + diag(Qbar)   (FILTER::UpdateCovariance, filter.cpp:588-616)
+//
+// F = E2*E1*E0 with block-row operations
+//   row0 += dt*row1 ;  row1 += A*row2 + B*row3 + dt*row5 ;  row2 <- (I+Wm)*row2 - dt*row4
+//   A = -R*[a]x*dt,  B = -R*dt,  Wm = -[w]x*dt     (R = CARRIED rotmatI2G, a/w bias-corrected)
+// Only the 126 entries of block rows 0..2 change; rows 3..5 (b_a, b_g, g) only receive Qbar.
+// Evaluation: (1) top-left 3x3 blocks from OLD values, (2) block columns 4,3,5 of rows 0..2, folding
+// their contribution into the top-left accumulators.  ~650 FMA instead of the 2*18^3 dense product.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, const double* w, double dt,
+                           const double* Qd) {
+    const double a = dt;
+    const double ndt = -dt;
+    double A[9], B[9];
+    {
+        const double s0 = acc[0] * ndt, s1 = acc[1] * ndt, s2 = acc[2] * ndt;  // -dt * a
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            // (R * [v]x)[i][:] = (R[i][1]v2 - R[i][2]v1, R[i][2]v0 - R[i][0]v2, R[i][0]v1 - R[i][1]v0)
+            A[i * 3 + 0] = R[i * 3 + 1] * s2 - R[i * 3 + 2] * s1;
+            A[i * 3 + 1] = R[i * 3 + 2] * s0 - R[i * 3 + 0] * s2;
+            A[i * 3 + 2] = R[i * 3 + 0] * s1 - R[i * 3 + 1] * s0;
+            FBUS_UNROLL
+            for (int j = 0; j < 3; ++j) B[i * 3 + j] = R[i * 3 + j] * ndt;
+        }
+    }
+    // Wm = -[w]x dt :  Wm01 = w2 dt, Wm02 = -w1 dt, Wm10 = -w2 dt, Wm12 = w0 dt, Wm20 = w1 dt, Wm21 = -w0 dt
+    const double u0 = w[0] * dt, u1 = w[1] * dt, u2 = w[2] * dt;
+// (Wm X)[i][j] for a 3x3 X (row-major), and (X Wm^T)[i][j] = sum_k X[i][k] Wm[j][k]
+#define FBUS_WX(X, i, j) \
+    ((i) == 0 ? (u2 * X[3 + (j)] - u1 * X[6 + (j)]) : (i) == 1 ? (u0 * X[6 + (j)] - u2 * X[(j)]) : (u1 * X[(j)] - u0 * X[3 + (j)]))
+#define FBUS_XWT(X, i, j) \
+    ((j) == 0 ? (u2 * X[(i)*3 + 1] - u1 * X[(i)*3 + 2]) : (j) == 1 ? (u0 * X[(i)*3 + 2] - u2 * X[(i)*3]) : (u1 * X[(i)*3] - u0 * X[(i)*3 + 1]))
+
+    // ---------------- phase 1: top-left blocks from old values -------------------------------
+    {
+        double P01[9], P02[9], P11[9], P12[9], M01[9], M02[9], M12[9];
+        double acc00[9], acc11[9];
+        P.ldblk(0, 1, P01);
+        P.lddiag(1, P11);
+        P.ldblk(0, 2, P02);
+        P.ldblk(1, 2, P12);
+        {
+            double P00[9];
+            P.lddiag(0, P00);
+            // M00 = P00 + a*P01^T (upper), acc00 = M00 + a*M01 ; M01 = P01 + a*P11
+            FBUS_UNROLL
+            for (int e = 0; e < 9; ++e) M01[e] = P01[e] + a * P11[e];
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = i; j < 3; ++j) acc00[i * 3 + j] = (P00[i * 3 + j] + a * P01[j * 3 + i]) + a * M01[i * 3 + j];
+            P.stdiag(0, acc00);
+        }
+        FBUS_UNROLL
+        for (int e = 0; e < 9; ++e) M02[e] = P02[e] + a * P12[e];
+        // N11 (upper) = P11 + A*P12^T + B*P13^T + a*P15^T
+        {
+            double P13[9], P15[9];
+            P.ldblk(1, 3, P13);
+            P.ldblk(1, 5, P15);
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = i; j < 3; ++j) {
+                    double s = P11[i * 3 + j] + a * P15[j * 3 + i];
+                    FBUS_UNROLL
+                    for (int k = 0; k < 3; ++k) s += A[i * 3 + k] * P12[j * 3 + k] + B[i * 3 + k] * P13[j * 3 + k];
+                    acc11[i * 3 + j] = s;
+                }
+        }
+        // M12 = P12 + A*P22 + B*P23^T + a*P25^T ; U22 = (I+Wm)*P22 - a*P24^T
+        double U22[9];
+        {
+            double P22[9], P23[9], P25[9], P24[9];
+            P.lddiag(2, P22);
+            P.ldblk(2, 3, P23);
+            P.ldblk(2, 5, P25);
+            P.ldblk(2, 4, P24);
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = 0; j < 3; ++j) {
+                    double s = P12[i * 3 + j] + a * P25[j * 3 + i];
+                    FBUS_UNROLL
+                    for (int k = 0; k < 3; ++k) s += A[i * 3 + k] * P22[k * 3 + j] + B[i * 3 + k] * P23[j * 3 + k];
+                    M12[i * 3 + j] = s;
+                    U22[i * 3 + j] = (P22[i * 3 + j] - a * P24[j * 3 + i]) + FBUS_WX(P22, i, j);
+                }
+        }
+        // column operations inside the top-left part
+        {
+            double acc01[9], acc02[9], acc12[9], acc22[9];
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = 0; j < 3; ++j) {
+                    double s = M01[i * 3 + j];
+                    FBUS_UNROLL
+                    for (int k = 0; k < 3; ++k) s += M02[i * 3 + k] * A[j * 3 + k];
+                    acc01[i * 3 + j] = s;
+                    acc02[i * 3 + j] = M02[i * 3 + j] + FBUS_XWT(M02, i, j);
+                    acc12[i * 3 + j] = M12[i * 3 + j] + FBUS_XWT(M12, i, j);
+                    if (j >= i) {
+                        double s1 = acc11[i * 3 + j];
+                        FBUS_UNROLL
+                        for (int k = 0; k < 3; ++k) s1 += M12[i * 3 + k] * A[j * 3 + k];
+                        acc11[i * 3 + j] = s1 + (i == j ? Qd[0] : 0.0);                       // + accel noise on v
+                        acc22[i * 3 + j] = (U22[i * 3 + j] + FBUS_XWT(U22, i, j)) + (i == j ? Qd[1] : 0.0);  // + gyro noise on theta
+                    }
+                }
+            P.stblk(0, 1, acc01);
+            P.stblk(0, 2, acc02);
+            P.stdiag(1, acc11);
+            P.stblk(1, 2, acc12);
+            P.stdiag(2, acc22);
+        }
+    }
+    // ---------------- phase 2: block columns 4, 3, 5 of rows 0..2 -----------------------------
+    double d01[9], d11[9];
+    FBUS_UNROLL
+    for (int kk = 0; kk < 3; ++kk) {
+        const int k = (kk == 0) ? 4 : (kk == 1) ? 3 : 5;
+        double X0[9], X1[9], X2[9], X3[9], X4[9], X5[9];
+        P.ldblk(0, k, X0);
+        P.ldblk(1, k, X1);
+        P.ldblk(2, k, X2);
+        P.ldany(3, k, X3);
+        P.ldany(4, k, X4);
+        P.ldany(5, k, X5);
+        double M0[9], M1[9], M2[9];
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                M0[i * 3 + j] = X0[i * 3 + j] + a * X1[i * 3 + j];
+                double s = X1[i * 3 + j] + a * X5[i * 3 + j];
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) s += A[i * 3 + c] * X2[c * 3 + j] + B[i * 3 + c] * X3[c * 3 + j];
+                M1[i * 3 + j] = s;
+                M2[i * 3 + j] = (X2[i * 3 + j] - a * X4[i * 3 + j]) + FBUS_WX(X2, i, j);
+            }
+        P.stblk(0, k, M0);
+        P.stblk(1, k, M1);
+        P.stblk(2, k, M2);
+        if (k == 4) {
+            // P'02 -= a*M04 ; P'12 -= a*M14 ; P'22 -= a*M24 (upper)
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = 0; j < 3; ++j) {
+                    P.st(i, 6 + j, P.ld(i, 6 + j) - a * M0[i * 3 + j]);
+                    P.st(3 + i, 6 + j, P.ld(3 + i, 6 + j) - a * M1[i * 3 + j]);
+                    if (j >= i) P.st(6 + i, 6 + j, P.ld(6 + i, 6 + j) - a * M2[i * 3 + j]);
+                }
+            // process noise on the gyro-bias block diagonal (k == 4 block row 4)
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i) P.st(12 + i, 12 + i, X4[i * 3 + i] + Qd[3]);
+        } else if (k == 3) {
+            // d01 = M03*B^T ; d11 = M13*B^T (upper)
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = 0; j < 3; ++j) {
+                    double s = 0.0, s1 = 0.0;
+                    FBUS_UNROLL
+                    for (int c = 0; c < 3; ++c) {
+                        s += M0[i * 3 + c] * B[j * 3 + c];
+                        s1 += M1[i * 3 + c] * B[j * 3 + c];
+                    }
+                    d01[i * 3 + j] = s;
+                    d11[i * 3 + j] = s1;
+                }
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i) P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);  // accel-bias noise
+        } else {
+            // k == 5:  P'01 += d01 + a*M05 ; P'11 += d11 + a*M15 (upper)
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = 0; j < 3; ++j) {
+                    P.st(i, 3 + j, P.ld(i, 3 + j) + (d01[i * 3 + j] + a * M0[i * 3 + j]));
+                    if (j >= i) P.st(3 + i, 3 + j, P.ld(3 + i, 3 + j) + (d11[i * 3 + j] + a * M1[i * 3 + j]));
+                }
+        }
+    }
+#undef FBUS_WX
+#undef FBUS_XWT
+}
+
+// ------------------------------------------------------------------------------------------------
+// F2: nominal state propagation (FILTER::UpdateNominalState, filter.cpp:533-582)
+// ------------------------------------------------------------------------------------------------
+FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const double* gyro) {
+    double w[3];
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) w[i] = gyro[i] - n.bg[i];
+    const double wn = norm3(w);
+    double R0[9], qh[4], qn[4];
+    q2R(n.q, R0);
+    if (wn > 10e-5) {
+        const double inv = 1.0 / wn;
+        const double ax[3] = {w[0] * inv, w[1] * inv, w[2] * inv};
+        double sh, ch, sf, cf;
+        sincos(wn * dt / 2 / 2, &sh, &ch);
+        sincos(wn * dt / 2, &sf, &cf);
+        const double dqh[4] = {ch, sh * ax[0], sh * ax[1], sh * ax[2]};
+        const double dq[4] = {cf, sf * ax[0], sf * ax[1], sf * ax[2]};
+        qmul(n.q, dqh, qh);
+        qmul(n.q, dq, qn);
+    } else {
+        const double dqh[4] = {1.0, 0.5 * dt * w[0] / 2, 0.5 * dt * w[1] / 2, 0.5 * dt * w[2] / 2};
+        const double dq[4] = {1.0, 0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
+        qmul(n.q, dqh, qh);
+        qmul(n.q, dq, qn);
+    }
+    qnormalize(qh);
+    qnormalize(qn);
+    FBUS_UNROLL
+    for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
+    double Rh[9];
+    q2R(qh, Rh);
+    q2R(n.q, n.R);
+    double a[3], k1[3], k2[3], k4[3];
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) a[i] = accel[i] - n.ba[i];
+    mat3_vec(R0, a, k1);
+    mat3_vec(Rh, a, k2);
+    mat3_vec(n.R, a, k4);
+    const double dt6 = dt / 6, dt2 = dt / 2;
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const double kv1 = k1[i] + n.g[i], kv2 = k2[i] + n.g[i], kv4 = k4[i] + n.g[i];
+        const double v0 = n.v[i];
+        n.v[i] = v0 + dt6 * (kv1 + 2 * kv2 + 2 * kv2 + kv4);
+        const double kp2 = v0 + kv1 * dt2, kp3 = v0 + kv2 * dt2;
+        n.p[i] = n.p[i] + dt6 * (v0 + 2 * kp2 + 2 * kp3 + kp3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// marker-map lookup (std::map::find on markerPoseServer_, filter.cpp:353,442,671)
+// ------------------------------------------------------------------------------------------------
+FBUS_HD int find_marker(const DevConsts& k, int id) {
+    int m = -1;
+    for (int i = 0; i < k.n_markers; ++i)
+        if (k.mk[i].id == id) m = (m < 0) ? i : m;
+    return m;
+}
+
+// vision-only pose (shared by InitializePose filter.cpp:379-384 and ResetSystemState :454-459):
+//   q = Q_M * conj(Q_ML) * Q_IL ;  Rq = R(q) ;  p = P_M - Rq*P_IL - Rq*R_IL^T*P_ML
+FBUS_HD void vision_pose(const DevConsts& k, const MarkerConst& mk, const double* pml, const double* qml, double* q,
+                         double* Rq, double* p) {
+    double t1[4];
+    qmul_conjb(mk.q, qml, t1);
+    qmul(t1, k.Q_IL, q);
+    q2R(q, Rq);
+    double u[3], r1[3], r2[3];
+    mat3t_vec(k.R_IL, pml, u);  // R_IL^T * P_ML
+    mat3_vec(Rq, k.P_IL, r1);
+    mat3_vec(Rq, u, r2);
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) p[i] = (mk.p[i] - r1[i]) - r2[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// F4: measurement update (FILTER::ObservationUpdate, filter.cpp:677-739) for the chosen detection.
+//
+// H = [Hp0 0 Hp2 0 0 0 ; 0 0 Hq 0 0 0] only touches block rows/cols 0 (p) and 2 (theta):
+//   with G = P[{0,1,2,6,7,8}, :] (6x18), Hs = [Hp0 Hp2; 0 Hq] (7x6), P6 = G[:, {0,1,2,6,7,8}]
+//   S = Hs P6 Hs^T + R ;  K = G^T Hs^T S^-1 ;  dx = G^T u, u = Hs^T S^-1 r ;
+//   (I-KH)P = P - G^T C G,  C = Hs^T S^-1 Hs = Lc Lc^T  ->  P' = P - Z^T Z,  Z = Lc^T G.
+// Z is applied in two half-rank sweeps (rows 0..2 then 3..5) so that only 54 doubles are live;
+// G's theta rows are rebuilt between the sweeps (see DESIGN.md "update without scratch").
+// S is SPD with cond <= ~13 on the reference's logs, so Cholesky replaces the reference's LDLT
+// (filter.cpp:711) to ~1e-15.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+                                const double* yQ) {
+    // ---- predicted measurement and Hs ------------------------------------------------------
+    double Hp0[9], Hp2[9], Hq[12], r[7];
+    {
+        double dp[3], rtdp[3], RP[3], d2[3], rt2[3], hP[3];
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i) dp[i] = mk.p[i] - n.p[i];
+        mat3t_vec(n.R, dp, rtdp);  // R^T (P_M - p)
+        mat3_vec(n.R, k.P_IL, RP);
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i) d2[i] = dp[i] - RP[i];
+        mat3t_vec(n.R, d2, rt2);
+        mat3_vec(k.R_IL, rt2, hP);  // hP = R_IL R^T (P_M - p - R P_IL)
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i) r[i] = yP[i] - hP[i];
+        // Hp0 = -R_IL R^T ; Hp2 = R_IL [R^T(P_M - p)]x
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                double s = 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) s += k.R_IL[i * 3 + c] * n.R[j * 3 + c];
+                Hp0[i * 3 + j] = -s;
+            }
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            const double a0 = k.R_IL[i * 3], a1 = k.R_IL[i * 3 + 1], a2 = k.R_IL[i * 3 + 2];
+            Hp2[i * 3 + 0] = a1 * rtdp[2] - a2 * rtdp[1];
+            Hp2[i * 3 + 1] = a2 * rtdp[0] - a0 * rtdp[2];
+            Hp2[i * 3 + 2] = a0 * rtdp[1] - a1 * rtdp[0];
+        }
+        // hQ = Q_IL * conj(q) * Q_M ; Hq = CM * (L(q) L1),  L(q) L1 = 0.5*[[-x,-y,-z],[w,-z,y],[z,w,-x],[-y,x,w]]
+        double t1[4], hQ[4];
+        qmul_conjb(k.Q_IL, n.q, t1);
+        qmul(t1, mk.q, hQ);
+        const double w = 0.5 * n.q[0], x = 0.5 * n.q[1], y = 0.5 * n.q[2], z = 0.5 * n.q[3];
+        const double LL[12] = {-x, -y, -z, w, -z, y, z, w, -x, -y, x, w};
+        FBUS_UNROLL
+        for (int i = 0; i < 4; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                double s = 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 4; ++c) s += mk.CM[i * 4 + c] * LL[c * 3 + j];
+                Hq[i * 3 + j] = s;
+            }
+        double k1 = 0.0, k2 = 0.0;
+        FBUS_UNROLL
+        for (int i = 0; i < 4; ++i) {
+            k1 += (yQ[i] - hQ[i]) * (yQ[i] - hQ[i]);
+            k2 += (yQ[i] + hQ[i]) * (yQ[i] + hQ[i]);
+        }
+        const double sg = (k1 > k2) ? -1.0 : 1.0;  // filter.cpp:702-706 (strict >)
+        FBUS_UNROLL
+        for (int i = 0; i < 12; ++i) Hq[i] *= sg;
+        FBUS_UNROLL
+        for (int i = 0; i < 4; ++i) r[3 + i] = yQ[i] - sg * hQ[i];
+    }
+    // ---- S = Hs P6 Hs^T + R (lower triangle in Sm) -------------------------------------------
+    double L[28];  // lower-triangular factor of S, row-major packed: L[i*(i+1)/2 + j]
+#define FBUS_L(i, j) L[(i) * ((i) + 1) / 2 + (j)]
+    {
+        double P00[9], P02[9], P22[9];
+        P.lddiag(0, P00);
+        P.ldblk(0, 2, P02);
+        P.lddiag(2, P22);
+        double Ep[18], Eq[24];  // Ep = [Hp0 Hp2] P6 (3x6) ; Eq = Hq [P20 P22] (4x6)
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                double s0 = 0.0, s1 = 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    s0 += Hp0[i * 3 + c] * P00[c * 3 + j] + Hp2[i * 3 + c] * P02[j * 3 + c];
+                    s1 += Hp0[i * 3 + c] * P02[c * 3 + j] + Hp2[i * 3 + c] * P22[c * 3 + j];
+                }
+                Ep[i * 6 + j] = s0;
+                Ep[i * 6 + 3 + j] = s1;
+            }
+        FBUS_UNROLL
+        for (int i = 0; i < 4; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                double s0 = 0.0, s1 = 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    s0 += Hq[i * 3 + c] * P02[j * 3 + c];
+                    s1 += Hq[i * 3 + c] * P22[c * 3 + j];
+                }
+                Eq[i * 6 + j] = s0;
+                Eq[i * 6 + 3 + j] = s1;
+            }
+        // S lower triangle
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j <= i; ++j) {
+                double s = (i == j) ? k.Rp : 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) s += Ep[i * 6 + c] * Hp0[j * 3 + c] + Ep[i * 6 + 3 + c] * Hp2[j * 3 + c];
+                FBUS_L(i, j) = s;
+            }
+        FBUS_UNROLL
+        for (int i = 0; i < 4; ++i) {
+            FBUS_UNROLL
+            for (int j = 0; j < 3; ++j) {  // S[3+i][j] = Eq[i][0:3] Hp0[j]^T + Eq[i][3:6] Hp2[j]^T
+                double s = 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) s += Eq[i * 6 + c] * Hp0[j * 3 + c] + Eq[i * 6 + 3 + c] * Hp2[j * 3 + c];
+                FBUS_L(3 + i, j) = s;
+            }
+            FBUS_UNROLL
+            for (int j = 0; j <= i; ++j) {
+                double s = (i == j) ? k.Rq : 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) s += Eq[i * 6 + 3 + c] * Hq[j * 3 + c];
+                FBUS_L(3 + i, 3 + j) = s;
+            }
+        }
+    }
+    // ---- Cholesky S = L L^T (in place), keep reciprocal diagonal -----------------------------
+    double Li[7];
+    FBUS_UNROLL
+    for (int j = 0; j < 7; ++j) {
+        double s = FBUS_L(j, j);
+        FBUS_UNROLL
+        for (int c = 0; c < j; ++c) s -= FBUS_L(j, c) * FBUS_L(j, c);
+        const double d = sqrt(s);
+        Li[j] = 1.0 / d;
+        FBUS_L(j, j) = d;
+        FBUS_UNROLL
+        for (int i = j + 1; i < 7; ++i) {
+            double s2 = FBUS_L(i, j);
+            FBUS_UNROLL
+            for (int c = 0; c < j; ++c) s2 -= FBUS_L(i, c) * FBUS_L(j, c);
+            FBUS_L(i, j) = s2 * Li[j];
+        }
+    }
+    // ---- X = L^-1 Hs (7x6), z = L^-1 r ; C = X^T X ; u = X^T z -------------------------------
+    double Cm[21], u[6];  // C lower packed: Cm[i*(i+1)/2+j]
+#define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
+    {
+        double X[42], z[7];
+        FBUS_UNROLL
+        for (int i = 0; i < 7; ++i) {
+            FBUS_UNROLL
+            for (int c = 0; c < 6; ++c) {
+                double s = (i < 3) ? ((c < 3) ? Hp0[i * 3 + c] : Hp2[i * 3 + (c - 3)]) : ((c < 3) ? 0.0 : Hq[(i - 3) * 3 + (c - 3)]);
+                FBUS_UNROLL
+                for (int j = 0; j < i; ++j) s -= FBUS_L(i, j) * X[j * 6 + c];
+                X[i * 6 + c] = s * Li[i];
+            }
+            double s = r[i];
+            FBUS_UNROLL
+            for (int j = 0; j < i; ++j) s -= FBUS_L(i, j) * z[j];
+            z[i] = s * Li[i];
+        }
+        FBUS_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            FBUS_UNROLL
+            for (int j = 0; j <= i; ++j) {
+                double s = 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 7; ++c) s += X[c * 6 + i] * X[c * 6 + j];
+                FBUS_C(i, j) = s;
+            }
+            double s = 0.0;
+            FBUS_UNROLL
+            for (int c = 0; c < 7; ++c) s += X[c * 6 + i] * z[c];
+            u[i] = s;
+        }
+    }
+#undef FBUS_L
+    // ---- Cholesky C = Lc Lc^T (in place in Cm) -----------------------------------------------
+    FBUS_UNROLL
+    for (int j = 0; j < 6; ++j) {
+        double s = FBUS_C(j, j);
+        FBUS_UNROLL
+        for (int c = 0; c < j; ++c) s -= FBUS_C(j, c) * FBUS_C(j, c);
+        const double d = sqrt(s);
+        const double di = 1.0 / d;
+        FBUS_C(j, j) = d;
+        FBUS_UNROLL
+        for (int i = j + 1; i < 6; ++i) {
+            double s2 = FBUS_C(i, j);
+            FBUS_UNROLL
+            for (int c = 0; c < j; ++c) s2 -= FBUS_C(i, c) * FBUS_C(j, c);
+            FBUS_C(i, j) = s2 * di;
+        }
+    }
+    // ---- stream G (rows 0..2 and 6..8 of P): dx = G^T u ; Za = rows 0..2 of Lc^T G -------------
+    double dx[18];
+    double Z[54];  // 3 x 18
+    {
+        FBUS_UNROLL
+        for (int c = 0; c < 18; ++c) {
+            dx[c] = 0.0;
+            Z[c] = 0.0; Z[18 + c] = 0.0; Z[36 + c] = 0.0;
+        }
+        FBUS_UNROLL
+        for (int m = 0; m < 6; ++m) {
+            const int row = (m < 3) ? m : (3 + m);  // 0,1,2,6,7,8
+            FBUS_UNROLL
+            for (int c = 0; c < 18; ++c) {
+                const double g = P.ld(row, c);
+                dx[c] += u[m] * g;
+                FBUS_UNROLL
+                for (int kz = 0; kz < 3; ++kz)
+                    if (m >= kz) Z[kz * 18 + c] += FBUS_C(m, kz) * g;
+            }
+        }
+    }
+    // ---- sweep 1: P -= Za^T Za -----------------------------------------------------------------
+    FBUS_UNROLL
+    for (int i = 0; i < 18; ++i)
+        FBUS_UNROLL
+        for (int j = i; j < 18; ++j)
+            P.st(i, j, P.ld(i, j) - (Z[i] * Z[j] + Z[18 + i] * Z[18 + j] + Z[36 + i] * Z[36 + j]));
+    // ---- rebuild G_b = P_old[6..8,:] = P1[6..8,:] + Za[:,6..8]^T Za, then Zb = Lbb^T G_b in place ----
+    {
+        const double z06 = Z[6], z07 = Z[7], z08 = Z[8], z16 = Z[18 + 6], z17 = Z[18 + 7], z18 = Z[18 + 8], z26 = Z[36 + 6],
+                     z27 = Z[36 + 7], z28 = Z[36 + 8];
+        FBUS_UNROLL
+        for (int c = 0; c < 18; ++c) {
+            const double za0 = Z[c], za1 = Z[18 + c], za2 = Z[36 + c];
+            const double g3 = P.ld(6, c) + (z06 * za0 + z16 * za1 + z26 * za2);
+            const double g4 = P.ld(7, c) + (z07 * za0 + z17 * za1 + z27 * za2);
+            const double g5 = P.ld(8, c) + (z08 * za0 + z18 * za1 + z28 * za2);
+            Z[c] = FBUS_C(3, 3) * g3 + FBUS_C(4, 3) * g4 + FBUS_C(5, 3) * g5;
+            Z[18 + c] = FBUS_C(4, 4) * g4 + FBUS_C(5, 4) * g5;
+            Z[36 + c] = FBUS_C(5, 5) * g5;
+        }
+    }
+#undef FBUS_C
+    // ---- sweep 2: P -= Zb^T Zb -----------------------------------------------------------------
+    FBUS_UNROLL
+    for (int i = 0; i < 18; ++i)
+        FBUS_UNROLL
+        for (int j = i; j < 18; ++j)
+            P.st(i, j, P.ld(i, j) - (Z[i] * Z[j] + Z[18 + i] * Z[18 + j] + Z[36 + i] * Z[36 + j]));
+    // ---- inject the error state (filter.cpp:726-733); rotmatI2G deliberately NOT refreshed ------
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        n.p[i] += dx[i];
+        n.v[i] += dx[3 + i];
+        n.ba[i] += dx[9 + i];
+        n.bg[i] += dx[12 + i];
+        n.g[i] += dx[15 + i];
+    }
+    {   // VectorToQuaterniond (matrix_math.hpp:90-99): v/|v| * sin(|v|/2); NaN at exactly zero, as the reference
+        const double vn = norm3(dx + 6);
+        double sh, ch;
+        sincos(vn / 2, &sh, &ch);
+        const double dq[4] = {ch, dx[6] / vn * sh, dx[7] / vn * sh, dx[8] / vn * sh};
+        double qn[4];
+        qmul(n.q, dq, qn);
+        qnormalize(qn);
+        FBUS_UNROLL
+        for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
+    }
+}
+
+}  // namespace fbus

@@ -1,0 +1,51 @@
+// tests/host_math_harness.cpp -- TEST-ONLY: compiles the device math header for the host so the
+// structured kernels' arithmetic can be compared with the oracle on a machine without a GPU.
+// Not part of the product; the product has no CPU path.
+#include "../fbus_ekf_b200/csrc/fbus_host_consts.hpp"
+
+using namespace fbus;
+
+static void nom_from(const double* a, Nominal& n) {
+    n.t = a[0];
+    for (int i = 0; i < 4; ++i) n.q[i] = a[1 + i];
+    for (int i = 0; i < 9; ++i) n.R[i] = a[5 + i];
+    for (int i = 0; i < 3; ++i) { n.p[i] = a[14 + i]; n.v[i] = a[17 + i]; n.ba[i] = a[20 + i]; n.bg[i] = a[23 + i]; n.g[i] = a[26 + i]; }
+}
+static void nom_to(const Nominal& n, double* a) {
+    a[0] = n.t;
+    for (int i = 0; i < 4; ++i) a[1 + i] = n.q[i];
+    for (int i = 0; i < 9; ++i) a[5 + i] = n.R[i];
+    for (int i = 0; i < 3; ++i) { a[14 + i] = n.p[i]; a[17 + i] = n.v[i]; a[20 + i] = n.ba[i]; a[23 + i] = n.bg[i]; a[26 + i] = n.g[i]; }
+}
+
+extern "C" {
+void hm_config_default(fbus_config* c) { config_default(c); }
+
+int hm_propagate(const fbus_config* cfg, double* P171, double* nom, const double* accel, const double* gyro, double dt) {
+    DevConsts k;
+    if (make_dev_consts(cfg, &k)) return -1;
+    Nominal n;
+    nom_from(nom, n);
+    double w[3], a[3];
+    for (int i = 0; i < 3; ++i) { w[i] = gyro[i] - n.bg[i]; a[i] = accel[i] - n.ba[i]; }
+    Cov<1> P{P171};
+    propagate_cov<1>(P, n.R, a, w, dt, k.Qd);
+    propagate_nominal(n, dt, accel, gyro);
+    n.t += dt;
+    nom_to(n, nom);
+    return 0;
+}
+
+int hm_update(const fbus_config* cfg, double* P171, double* nom, int marker_id, const double* yP, const double* yQ) {
+    DevConsts k;
+    if (make_dev_consts(cfg, &k)) return -1;
+    const int m = find_marker(k, marker_id);
+    if (m < 0) return -2;
+    Nominal n;
+    nom_from(nom, n);
+    Cov<1> P{P171};
+    measurement_update<1>(P, n, k, k.mk[m], yP, yQ);
+    nom_to(n, nom);
+    return 0;
+}
+}
