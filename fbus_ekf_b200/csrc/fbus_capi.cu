@@ -1,0 +1,513 @@
+// fbus_capi.cu -- implementation of the C ABI declared in include/fbus_ekf.h.
+//
+// Host side: handle, device buffers, staging of caller-owned host arrays, kernel launches on the
+// handle's stream.  There is no CPU compute path: every entry point that does arithmetic launches a
+// kernel from fbus_kernels.cuh, and fbus_create fails when no CUDA device is usable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fbus_ekf.h"
+#include "fbus_host_consts.hpp"
+#include "fbus_kernels.cuh"
+
+using namespace fbus;
+
+namespace {
+
+constexpr int WIN_BS = 32;  // filters per CTA of the window kernel (one warp; 171*32*8 B = 42.75 KB smem)
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct fbus_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    size_t B = 0;
+    fbus_config cfg;
+    DevConsts k;
+    MarkerTable tab;
+    MarkerTable* d_tab = nullptr;
+    double* d_nom = nullptr;
+    double* d_P = nullptr;
+    int32_t* d_prev = nullptr;
+    int32_t* d_init = nullptr;
+    int32_t* d_status = nullptr;
+    DevBuf imu_t, det_t, win_off, imu_data, det_id, det_pose, trace, scratch_in, scratch_out, scratch_aux, stats_partial, stats_out;
+    std::string err;
+};
+
+namespace {
+
+int fail(fbus_handle* h, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (h) h->err = msg;
+    return code;
+}
+#define CUDA_TRY(h, expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(h, FBUS_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+// stage a caller array on the device if it lives on the host; returns the device pointer to use
+template <class T>
+int stage(fbus_handle* h, DevBuf& buf, const T* src, size_t count, int mem, const T** out) {
+    if (mem == FBUS_MEM_DEVICE) {
+        *out = src;
+        return FBUS_OK;
+    }
+    CUDA_TRY(h, buf.reserve(count * sizeof(T)));
+    CUDA_TRY(h, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *out = (const T*)buf.p;
+    return FBUS_OK;
+}
+
+int launch_window(fbus_handle* h, WinParams& prm) {
+    prm.nom = h->d_nom;
+    prm.P = h->d_P;
+    prm.prev_id = h->d_prev;
+    prm.init = h->d_init;
+    prm.status = h->d_status;
+    prm.B = h->B;
+    prm.tab = h->d_tab;
+    const size_t smem = (size_t)NPK * WIN_BS * sizeof(double);
+    const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
+    ekf_window_kernel<WIN_BS><<<grid, WIN_BS, smem, h->stream>>>(prm, h->k);
+    CUDA_TRY(h, cudaGetLastError());
+    return FBUS_OK;
+}
+
+int stage_det(fbus_handle* h, const fbus_det_frames* det, size_t w0, size_t w1, WinParams& prm) {
+    if (!det || det->batch != h->B || w1 > det->n_frames || w0 > w1 || det->max_markers == 0 || !det->t || !det->id || !det->pose)
+        return fail(h, FBUS_E_BADARG, "bad detection frames");
+    const size_t m = det->max_markers, B = h->B, nw = w1 - w0;
+    // timestamps are always host memory; stage only the frames of this call, re-based to index 0
+    const double* dt;
+    int rc = stage(h, h->det_t, det->t + w0, nw, FBUS_MEM_HOST, &dt);
+    if (rc) return rc;
+    const int32_t* did;
+    const double* dpose;
+    rc = stage(h, h->det_id, det->id + w0 * m * B, nw * m * B, det->mem, &did);
+    if (rc) return rc;
+    rc = stage(h, h->det_pose, det->pose + w0 * m * 7 * B, nw * m * 7 * B, det->mem, &dpose);
+    if (rc) return rc;
+    prm.det_t = dt;
+    prm.det_id = did;
+    prm.det_pose = dpose;
+    prm.m = (int32_t)m;
+    prm.w0 = 0;
+    prm.w1 = (uint32_t)nw;
+    return FBUS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fbus_abi_version(void) { return FBUS_ABI_VERSION; }
+
+int fbus_config_default(fbus_config* cfg) {
+    if (!cfg) return FBUS_E_BADARG;
+    config_default(cfg);
+    return FBUS_OK;
+}
+
+void fbus_quat_from_rotmat(const double R[9], double q[4]) { R2q(R, q); }
+
+const char* fbus_last_error(const fbus_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t batch) {
+    if (!out || !cfg || batch == 0) return fail(nullptr, FBUS_E_BADARG, "fbus_create: bad argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, FBUS_E_CUDA, std::string("fbus_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                                              "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, FBUS_E_BADARG, "fbus_create: bad device index");
+    fbus_handle* h = new fbus_handle;
+    h->device = device;
+    h->B = batch;
+    h->cfg = *cfg;
+    if (make_dev_consts(cfg, &h->k, &h->tab) != FBUS_OK) {
+        delete h;
+        return fail(nullptr, FBUS_E_BADARG, "fbus_create: bad config (n_markers)");
+    }
+    auto bail = [&](const char* what, cudaError_t ce) {
+        std::string msg = std::string("fbus_create: ") + what + ": " + cudaGetErrorString(ce);
+        fbus_destroy(h);
+        return fail(nullptr, ce == cudaErrorMemoryAllocation ? FBUS_E_NOMEM : FBUS_E_CUDA, msg);
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&h->d_nom, sizeof(double) * NOM_FIELDS * batch)) != cudaSuccess) return bail("cudaMalloc nom", e);
+    if ((e = cudaMalloc(&h->d_P, sizeof(double) * NPK * batch)) != cudaSuccess) return bail("cudaMalloc P", e);
+    if ((e = cudaMalloc(&h->d_prev, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc prev", e);
+    if ((e = cudaMalloc(&h->d_init, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc init", e);
+    if ((e = cudaMalloc(&h->d_status, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc status", e);
+    if ((e = cudaMalloc(&h->d_tab, sizeof(MarkerTable))) != cudaSuccess) return bail("cudaMalloc marker table", e);
+    if ((e = cudaMemcpy(h->d_tab, &h->tab, sizeof(MarkerTable), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("marker table copy", e);
+    if ((e = cudaFuncSetAttribute(ekf_window_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(NPK * WIN_BS * sizeof(double)))) != cudaSuccess)
+        return bail("cudaFuncSetAttribute", e);
+    const unsigned grid = (unsigned)((batch + 127) / 128);
+    ctor_kernel<<<grid, 128, 0, h->stream>>>(h->d_nom, h->d_P, h->d_prev, h->d_init, h->d_status, batch, cfg->p0_diag[0],
+                                             cfg->p0_diag[1], cfg->p0_diag[2], cfg->p0_diag[3], cfg->p0_diag[4], cfg->p0_diag[5]);
+    if ((e = cudaGetLastError()) != cudaSuccess) return bail("ctor_kernel", e);
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("ctor sync", e);
+    *out = h;
+    return FBUS_OK;
+}
+
+int fbus_destroy(fbus_handle* h) {
+    if (!h) return FBUS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_nom); cudaFree(h->d_P); cudaFree(h->d_prev); cudaFree(h->d_init); cudaFree(h->d_status); cudaFree(h->d_tab);
+    DevBuf* bufs[] = {&h->imu_t, &h->det_t, &h->win_off, &h->imu_data, &h->det_id, &h->det_pose, &h->trace,
+                      &h->scratch_in, &h->scratch_out, &h->scratch_aux, &h->stats_partial, &h->stats_out};
+    for (DevBuf* b : bufs) b->release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return FBUS_OK;
+}
+
+int fbus_synchronize(fbus_handle* h) {
+    if (!h) return FBUS_E_BADARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return FBUS_OK;
+}
+size_t fbus_batch(const fbus_handle* h) { return h ? h->B : 0; }
+void* fbus_stream(fbus_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int fbus_init_gravity_gyrobias(fbus_handle* h, const fbus_imu_stream* imu, size_t first, size_t count) {
+    if (!h || !imu || imu->batch != h->B || first + count > imu->n_samples || !imu->data) return fail(h, FBUS_E_BADARG, "bad imu stream");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (count == 0) return FBUS_OK;
+    const double* d;
+    int rc = stage(h, h->imu_data, imu->data + first * 6 * h->B, count * 6 * h->B, imu->mem, &d);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((h->B + 127) / 128);
+    init_gravity_kernel<<<grid, 128, 0, h->stream>>>(h->d_nom, h->B, d, 0u, (uint32_t)count);
+    CUDA_TRY(h, cudaGetLastError());
+    return FBUS_OK;
+}
+
+int fbus_init_position_quaternion(fbus_handle* h, const fbus_det_frames* det, size_t frame, size_t n_imu_before) {
+    if (!h) return FBUS_E_BADARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    WinParams prm;
+    memset(&prm, 0, sizeof prm);
+    int rc = stage_det(h, det, frame, frame + 1, prm);
+    if (rc) return rc;
+    prm.mode = M_INIT;
+    prm.n_imu_before = (uint32_t)n_imu_before;
+    return launch_window(h, prm);
+}
+
+int fbus_propagate(fbus_handle* h, const fbus_imu_stream* imu, size_t first, size_t count, double t_end) {
+    if (!h || !imu || imu->batch != h->B || first + count > imu->n_samples || !imu->t || !imu->data)
+        return fail(h, FBUS_E_BADARG, "bad imu stream");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (count == 0) return FBUS_OK;
+    WinParams prm;
+    memset(&prm, 0, sizeof prm);
+    const double* dt;
+    const double* dd;
+    int rc = stage(h, h->imu_t, imu->t + first, count, FBUS_MEM_HOST, &dt);
+    if (rc) return rc;
+    rc = stage(h, h->imu_data, imu->data + first * 6 * h->B, count * 6 * h->B, imu->mem, &dd);
+    if (rc) return rc;
+    prm.imu_t = dt;
+    prm.imu = dd;
+    prm.mode = M_PROP;
+    prm.prop_first = 0;
+    prm.prop_count = (uint32_t)count;
+    prm.prop_t_end = t_end;
+    prm.w0 = 0;
+    prm.w1 = 1;
+    return launch_window(h, prm);
+}
+
+int fbus_reset_state(fbus_handle* h, const fbus_det_frames* det, size_t frame) {
+    if (!h) return FBUS_E_BADARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    WinParams prm;
+    memset(&prm, 0, sizeof prm);
+    int rc = stage_det(h, det, frame, frame + 1, prm);
+    if (rc) return rc;
+    prm.mode = M_RESET;
+    return launch_window(h, prm);
+}
+
+int fbus_update(fbus_handle* h, const fbus_det_frames* det, size_t frame) {
+    if (!h) return FBUS_E_BADARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    WinParams prm;
+    memset(&prm, 0, sizeof prm);
+    int rc = stage_det(h, det, frame, frame + 1, prm);
+    if (rc) return rc;
+    prm.mode = M_UPDATE;
+    return launch_window(h, prm);
+}
+
+int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det_frames* det, const uint32_t* win_off,
+                      size_t w0, size_t w1, double* trace, int32_t trace_mem) {
+    if (!h || !imu || !det || !win_off || imu->batch != h->B || !imu->t || !imu->data)
+        return fail(h, FBUS_E_BADARG, "fbus_step_windows: bad argument");
+    if (w0 >= w1) return (w0 == w1) ? FBUS_OK : fail(h, FBUS_E_BADARG, "fbus_step_windows: w0 > w1");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t B = h->B, nw = w1 - w0;
+    const size_t s0 = win_off[w0], s1 = win_off[w1];
+    for (size_t w = w0; w < w1; ++w)
+        if (win_off[w + 1] < win_off[w]) return fail(h, FBUS_E_BADARG, "fbus_step_windows: win_off must be non-decreasing");
+    if (s1 > imu->n_samples) return fail(h, FBUS_E_BADARG, "fbus_step_windows: win_off beyond the IMU stream");
+    WinParams prm;
+    memset(&prm, 0, sizeof prm);
+    int rc = stage_det(h, det, w0, w1, prm);
+    if (rc) return rc;
+    // IMU samples of this call, re-based to index 0
+    const double* dt;
+    const double* dd;
+    const size_t ns = s1 - s0;
+    rc = stage(h, h->imu_t, imu->t + s0, ns ? ns : 1, FBUS_MEM_HOST, &dt);
+    if (rc) return rc;
+    if (imu->mem == FBUS_MEM_HOST && ns == 0) dd = nullptr;
+    else {
+        rc = stage(h, h->imu_data, imu->data + s0 * 6 * B, ns * 6 * B, imu->mem, &dd);
+        if (rc) return rc;
+    }
+    std::vector<uint32_t> off(nw + 1);
+    for (size_t w = 0; w <= nw; ++w) off[w] = (uint32_t)(win_off[w0 + w] - s0);
+    const uint32_t* doff;
+    rc = stage(h, h->win_off, off.data(), nw + 1, FBUS_MEM_HOST, &doff);
+    if (rc) return rc;
+    // `off` is pageable host memory: cudaMemcpyAsync has staged it before returning
+    prm.imu_t = dt;
+    prm.imu = dd;
+    prm.win_off = doff;
+    prm.mode = M_FUSED;
+    double* dtrace = nullptr;
+    if (trace) {
+        if (trace_mem == FBUS_MEM_DEVICE) dtrace = trace;
+        else {
+            CUDA_TRY(h, h->trace.reserve(nw * 17 * B * sizeof(double)));
+            dtrace = (double*)h->trace.p;
+        }
+    }
+    prm.trace = dtrace;
+    rc = launch_window(h, prm);
+    if (rc) return rc;
+    if (trace && trace_mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(trace, dtrace, nw * 17 * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
+int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid, int32_t mem) {
+    if (!h || !corners || !pose) return fail(h, FBUS_E_BADARG, "fbus_refract_solve: bad argument");
+    if (n == 0) return FBUS_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const float* dc;
+    int rc = stage(h, h->scratch_in, corners, 16 * n, mem, &dc);
+    if (rc) return rc;
+    double* dpose = pose;
+    double* dc3 = corners3d;
+    int32_t* dvalid = valid;
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, h->scratch_out.reserve((7 + 12) * n * sizeof(double)));
+        CUDA_TRY(h, h->scratch_aux.reserve(n * sizeof(int32_t)));
+        dpose = (double*)h->scratch_out.p;
+        dc3 = dpose + 7 * n;
+        dvalid = (int32_t*)h->scratch_aux.p;
+    }
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    refract_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc, n, dpose, dc3, dvalid);
+    CUDA_TRY(h, cudaGetLastError());
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(pose, dpose, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (corners3d) CUDA_TRY(h, cudaMemcpyAsync(corners3d, dc3, 12 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (valid) CUDA_TRY(h, cudaMemcpyAsync(valid, dvalid, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
+int fbus_marker_pose(fbus_handle* h, const double* corners3d, size_t n, double* pose, int32_t mem) {
+    if (!h || !corners3d || !pose) return fail(h, FBUS_E_BADARG, "fbus_marker_pose: bad argument");
+    if (n == 0) return FBUS_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const double* dc;
+    int rc = stage(h, h->scratch_in, corners3d, 12 * n, mem, &dc);
+    if (rc) return rc;
+    double* dpose = pose;
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, h->scratch_out.reserve(7 * n * sizeof(double)));
+        dpose = (double*)h->scratch_out.p;
+    }
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    marker_pose_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc, n, dpose);
+    CUDA_TRY(h, cudaGetLastError());
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(pose, dpose, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
+int fbus_get_state(fbus_handle* h, fbus_state_soa* out) {
+    if (!h || !out || out->batch != h->B) return fail(h, FBUS_E_BADARG, "fbus_get_state: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t B = h->B;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    struct { double* dst; int field; int n; } f[] = {{out->t, F_T, 1}, {out->q, F_Q, 4}, {out->R, F_R, 9}, {out->p, F_P, 3},
+                                                     {out->v, F_V, 3}, {out->ba, F_BA, 3}, {out->bg, F_BG, 3}, {out->g, F_G, 3},
+                                                     {out->pv, F_PV, 3}, {out->qv, F_QV, 4}};
+    for (auto& x : f)
+        if (x.dst) CUDA_TRY(h, cudaMemcpy(x.dst, h->d_nom + (size_t)x.field * B, sizeof(double) * x.n * B, cudaMemcpyDeviceToHost));
+    if (out->prev_marker_id) CUDA_TRY(h, cudaMemcpy(out->prev_marker_id, h->d_prev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
+    if (out->initialised) CUDA_TRY(h, cudaMemcpy(out->initialised, h->d_init, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
+    if (out->status) CUDA_TRY(h, cudaMemcpy(out->status, h->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
+    if (out->P) {
+        std::vector<double> pk((size_t)NPK * B);
+        CUDA_TRY(h, cudaMemcpy(pk.data(), h->d_P, sizeof(double) * NPK * B, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < NX; ++i)
+            for (int j = 0; j < NX; ++j) memcpy(out->P + (size_t)(i * NX + j) * B, pk.data() + (size_t)pidx(i, j) * B, sizeof(double) * B);
+    }
+    return FBUS_OK;
+}
+
+int fbus_set_state(fbus_handle* h, const fbus_state_soa* in) {
+    if (!h || !in || in->batch != h->B) return fail(h, FBUS_E_BADARG, "fbus_set_state: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t B = h->B;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    struct { const double* src; int field; int n; } f[] = {{in->t, F_T, 1}, {in->q, F_Q, 4}, {in->R, F_R, 9}, {in->p, F_P, 3},
+                                                           {in->v, F_V, 3}, {in->ba, F_BA, 3}, {in->bg, F_BG, 3}, {in->g, F_G, 3},
+                                                           {in->pv, F_PV, 3}, {in->qv, F_QV, 4}};
+    for (auto& x : f)
+        if (x.src) CUDA_TRY(h, cudaMemcpy(h->d_nom + (size_t)x.field * B, x.src, sizeof(double) * x.n * B, cudaMemcpyHostToDevice));
+    if (in->prev_marker_id) CUDA_TRY(h, cudaMemcpy(h->d_prev, in->prev_marker_id, sizeof(int32_t) * B, cudaMemcpyHostToDevice));
+    if (in->initialised) CUDA_TRY(h, cudaMemcpy(h->d_init, in->initialised, sizeof(int32_t) * B, cudaMemcpyHostToDevice));
+    if (in->status) CUDA_TRY(h, cudaMemcpy(h->d_status, in->status, sizeof(int32_t) * B, cudaMemcpyHostToDevice));
+    if (in->P) {
+        std::vector<double> pk((size_t)NPK * B);
+        for (int i = 0; i < NX; ++i)
+            for (int j = i; j < NX; ++j) memcpy(pk.data() + (size_t)pidx_u(i, j) * B, in->P + (size_t)(i * NX + j) * B, sizeof(double) * B);
+        CUDA_TRY(h, cudaMemcpy(h->d_P, pk.data(), sizeof(double) * NPK * B, cudaMemcpyHostToDevice));
+    }
+    return FBUS_OK;
+}
+
+int fbus_clear_status(fbus_handle* h) {
+    if (!h) return FBUS_E_BADARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_status, 0, sizeof(int32_t) * h->B, h->stream));
+    return FBUS_OK;
+}
+
+int fbus_stats(fbus_handle* h, const double* truth_p, const double* truth_q, int32_t mem, double* out_host, double* out_dev) {
+    if (!h || !truth_p || !truth_q) return fail(h, FBUS_E_BADARG, "fbus_stats: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t B = h->B;
+    const double* tp;
+    const double* tq;
+    int rc = stage(h, h->scratch_in, truth_p, 3 * B, mem, &tp);
+    if (rc) return rc;
+    rc = stage(h, h->scratch_out, truth_q, 4 * B, mem, &tq);
+    if (rc) return rc;
+    const int grid = (int)((B + STATS_BS - 1) / STATS_BS);
+    CUDA_TRY(h, h->stats_partial.reserve((size_t)grid * 8 * sizeof(double)));
+    CUDA_TRY(h, h->stats_out.reserve(FBUS_NSTATS * sizeof(double)));
+    stats_kernel<<<grid, STATS_BS, 0, h->stream>>>(h->d_nom, h->d_P, B, tp, tq, (double*)h->stats_partial.p);
+    CUDA_TRY(h, cudaGetLastError());
+    double* dout = out_dev ? out_dev : (double*)h->stats_out.p;
+    stats_reduce_kernel<<<1, 256, 0, h->stream>>>((const double*)h->stats_partial.p, grid, dout);
+    CUDA_TRY(h, cudaGetLastError());
+    if (out_host) {
+        CUDA_TRY(h, cudaMemcpyAsync(out_host, dout, FBUS_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
+int fbus_synth_streams(fbus_handle* h, const fbus_synth_spec* spec, double* imu_data, int32_t* det_id, double* det_pose, double* bias_out) {
+    if (!h || !spec || !imu_data || !det_id || !det_pose || !spec->base_imu || !spec->base_pose)
+        return fail(h, FBUS_E_BADARG, "fbus_synth_streams: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SynthParams sp;
+    memset(&sp, 0, sizeof sp);
+    const double* bi;
+    const double* bp;
+    int rc = stage(h, h->scratch_in, spec->base_imu, spec->n_samples * 6, FBUS_MEM_HOST, &bi);
+    if (rc) return rc;
+    rc = stage(h, h->scratch_out, spec->base_pose, spec->n_frames * 7, FBUS_MEM_HOST, &bp);
+    if (rc) return rc;
+    sp.B = h->B; sp.N = spec->n_samples; sp.W = spec->n_frames;
+    sp.base_imu = bi; sp.base_pose = bp;
+    sp.imu = imu_data; sp.det_id = det_id; sp.det_pose = det_pose; sp.bias_out = bias_out;
+    sp.s_acc = spec->sigma_acc; sp.s_gyro = spec->sigma_gyro; sp.s_ba = spec->sigma_ba; sp.s_bg = spec->sigma_bg;
+    sp.s_pos = spec->sigma_pos; sp.s_quat = spec->sigma_quat;
+    sp.seed = spec->seed; sp.filter_offset = spec->filter_offset; sp.marker_id = spec->marker_id;
+    const unsigned grid = (unsigned)((h->B + 127) / 128);
+    synth_kernel<<<grid, 128, 0, h->stream>>>(sp);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // base arrays staged from caller memory: make reuse safe
+    return FBUS_OK;
+}
+
+int fbus_measure_fp64_peak(fbus_handle* h, double* flops) {
+    if (!h || !flops) return fail(h, FBUS_E_BADARG, "fbus_measure_fp64_peak: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    CUDA_TRY(h, h->scratch_aux.reserve((size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(h, cudaEventCreate(&e0));
+    CUDA_TRY(h, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CUDA_TRY(h, cudaEventRecord(e0, h->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>((double*)h->scratch_aux.p, iters, 1.0 + rep);
+        CUDA_TRY(h, cudaEventRecord(e1, h->stream));
+        CUDA_TRY(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 64.0 * (double)iters * (double)blocks * threads / (ms * 1e-3);
+        if (rep > 0 && fl > best) best = fl;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_TRY(h, cudaGetLastError());
+    *flops = best;
+    return FBUS_OK;
+}
+
+}  // extern "C"

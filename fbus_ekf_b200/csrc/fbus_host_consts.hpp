@@ -24,9 +24,10 @@ inline void host_quat_right(const double* q, double* m) {  // matrix_math.hpp:64
     memcpy(m, t, sizeof t);
 }
 
-inline int make_dev_consts(const fbus_config* c, DevConsts* k) {
+inline int make_dev_consts(const fbus_config* c, DevConsts* k, MarkerTable* tab) {
     if (c->n_markers < 0 || c->n_markers > MAXM) return FBUS_E_BADARG;
     memset(k, 0, sizeof *k);
+    memset(tab, 0, sizeof *tab);
     const double flip[3] = {-1.0, -1.0, 1.0};  // T_C_I, filter.hpp:67-69
     double P_LI[3];
     for (int i = 0; i < 3; ++i) {
@@ -57,12 +58,14 @@ inline int make_dev_consts(const fbus_config* c, DevConsts* k) {
     k->d_air = c->d_air; k->d_glass = c->d_glass;
     for (int i = 0; i < 3; ++i) k->normal[i] = c->normal[i];
     k->dect_thres = c->marker_dect_dist_thres;
+    k->rod_s = sin(-3.1415926 / 4);
+    k->rod_c = cos(-3.1415926 / 4);
     k->n_markers = c->n_markers;
     k->flags = c->flags;
     double Lil[16];
     host_quat_left(k->Q_IL, Lil);
     for (int m = 0; m < c->n_markers; ++m) {
-        MarkerConst& mk = k->mk[m];
+        MarkerConst& mk = tab->mk[m];
         mk.id = c->marker_id[m];
         for (int i = 0; i < 3; ++i) mk.p[i] = c->marker_pos[m * 3 + i];
         R2q(&c->marker_rot[m * 9], mk.q);  // main.cpp:201

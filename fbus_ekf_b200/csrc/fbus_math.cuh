@@ -22,7 +22,13 @@
 #ifdef __CUDACC__
 #define FBUS_HD __host__ __device__ __forceinline__
 #define FBUS_UNROLL _Pragma("unroll")
+#ifdef __CUDA_ARCH__
+#define FBUS_FENCE asm volatile("" ::: "memory")
 #else
+#define FBUS_FENCE ((void)0)
+#endif
+#else
+#define FBUS_FENCE ((void)0)
 #define FBUS_HD inline
 #define FBUS_UNROLL
 #endif
@@ -53,8 +59,13 @@ struct DevConsts {
     double R_RL[9], P_LR[3];           // vision view: raw T_SC (vision.cpp:476-481)
     double a0, a1;                     // n_air/n_glass, n_glass/n_water
     double d_air, d_glass, normal[3], dect_thres;
+    double rod_s, rod_c;               // sin/cos of -3.1415926/4 (common.hpp:14, vision.cpp:740)
     int32_t air_lt_glass, glass_gt_water;
     int32_t n_markers, flags;
+};
+// marker map: lives in device global memory (dynamic indexing of kernel parameters would force a
+// local-memory copy of the whole table)
+struct MarkerTable {
     MarkerConst mk[MAXM];
 };
 
@@ -185,6 +196,7 @@ struct Cov {
 template <int S>
 FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, const double* w, double dt,
                            const double* Qd) {
+    // Every sum below is written as a chain  s += x*y  so that it compiles to one DFMA per term.
     const double a = dt;
     const double ndt = -dt;
     double A[9], B[9];
@@ -202,166 +214,267 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
     }
     // Wm = -[w]x dt :  Wm01 = w2 dt, Wm02 = -w1 dt, Wm10 = -w2 dt, Wm12 = w0 dt, Wm20 = w1 dt, Wm21 = -w0 dt
     const double u0 = w[0] * dt, u1 = w[1] * dt, u2 = w[2] * dt;
-// (Wm X)[i][j] for a 3x3 X (row-major), and (X Wm^T)[i][j] = sum_k X[i][k] Wm[j][k]
-#define FBUS_WX(X, i, j) \
-    ((i) == 0 ? (u2 * X[3 + (j)] - u1 * X[6 + (j)]) : (i) == 1 ? (u0 * X[6 + (j)] - u2 * X[(j)]) : (u1 * X[(j)] - u0 * X[3 + (j)]))
-#define FBUS_XWT(X, i, j) \
-    ((j) == 0 ? (u2 * X[(i)*3 + 1] - u1 * X[(i)*3 + 2]) : (j) == 1 ? (u0 * X[(i)*3 + 2] - u2 * X[(i)*3]) : (u1 * X[(i)*3] - u0 * X[(i)*3 + 1]))
+// s += (Wm X)[i][j]  and  s += (X Wm^T)[i][j] = sum_k X[i][k] Wm[j][k]   (two DFMA each)
+#define FBUS_WX_ACC(s, X, i, j)                                                \
+    do {                                                                       \
+        if ((i) == 0) { s += u2 * X[3 + (j)]; s -= u1 * X[6 + (j)]; }          \
+        else if ((i) == 1) { s += u0 * X[6 + (j)]; s -= u2 * X[(j)]; }         \
+        else { s += u1 * X[(j)]; s -= u0 * X[3 + (j)]; }                       \
+    } while (0)
+#define FBUS_XWT_ACC(s, X, i, j)                                               \
+    do {                                                                       \
+        if ((j) == 0) { s += u2 * X[(i)*3 + 1]; s -= u1 * X[(i)*3 + 2]; }      \
+        else if ((j) == 1) { s += u0 * X[(i)*3 + 2]; s -= u2 * X[(i)*3]; }     \
+        else { s += u1 * X[(i)*3]; s -= u0 * X[(i)*3 + 1]; }                   \
+    } while (0)
 
     // ---------------- phase 1: top-left blocks from old values -------------------------------
+    // Staged so that few blocks are live at a time (FBUS_FENCE stops the scheduler hoisting every
+    // shared-memory load to the top, which would blow the 255-register budget).
     {
-        double P01[9], P02[9], P11[9], P12[9], M01[9], M02[9], M12[9];
-        double acc00[9], acc11[9];
-        P.ldblk(0, 1, P01);
-        P.lddiag(1, P11);
-        P.ldblk(0, 2, P02);
+        double P11[9], P12[9];
         P.ldblk(1, 2, P12);
-        {
-            double P00[9];
-            P.lddiag(0, P00);
-            // M00 = P00 + a*P01^T (upper), acc00 = M00 + a*M01 ; M01 = P01 + a*P11
-            FBUS_UNROLL
-            for (int e = 0; e < 9; ++e) M01[e] = P01[e] + a * P11[e];
-            FBUS_UNROLL
-            for (int i = 0; i < 3; ++i)
-                FBUS_UNROLL
-                for (int j = i; j < 3; ++j) acc00[i * 3 + j] = (P00[i * 3 + j] + a * P01[j * 3 + i]) + a * M01[i * 3 + j];
-            P.stdiag(0, acc00);
-        }
-        FBUS_UNROLL
-        for (int e = 0; e < 9; ++e) M02[e] = P02[e] + a * P12[e];
-        // N11 (upper) = P11 + A*P12^T + B*P13^T + a*P15^T
-        {
-            double P13[9], P15[9];
-            P.ldblk(1, 3, P13);
-            P.ldblk(1, 5, P15);
-            FBUS_UNROLL
-            for (int i = 0; i < 3; ++i)
-                FBUS_UNROLL
-                for (int j = i; j < 3; ++j) {
-                    double s = P11[i * 3 + j] + a * P15[j * 3 + i];
-                    FBUS_UNROLL
-                    for (int k = 0; k < 3; ++k) s += A[i * 3 + k] * P12[j * 3 + k] + B[i * 3 + k] * P13[j * 3 + k];
-                    acc11[i * 3 + j] = s;
-                }
-        }
-        // M12 = P12 + A*P22 + B*P23^T + a*P25^T ; U22 = (I+Wm)*P22 - a*P24^T
-        double U22[9];
-        {
-            double P22[9], P23[9], P25[9], P24[9];
+        double M12[9];
+        {   // 1c: P'22 (without the -a*M24 term) ; M12 = P12 + A*P22 (+ more below)
+            double P22[9], P24[9], U22[9], acc22[9];
             P.lddiag(2, P22);
-            P.ldblk(2, 3, P23);
-            P.ldblk(2, 5, P25);
             P.ldblk(2, 4, P24);
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
                 for (int j = 0; j < 3; ++j) {
-                    double s = P12[i * 3 + j] + a * P25[j * 3 + i];
+                    double s = P12[i * 3 + j];
                     FBUS_UNROLL
-                    for (int k = 0; k < 3; ++k) s += A[i * 3 + k] * P22[k * 3 + j] + B[i * 3 + k] * P23[j * 3 + k];
+                    for (int k = 0; k < 3; ++k) s += A[i * 3 + k] * P22[k * 3 + j];
                     M12[i * 3 + j] = s;
-                    U22[i * 3 + j] = (P22[i * 3 + j] - a * P24[j * 3 + i]) + FBUS_WX(P22, i, j);
+                    double t = P22[i * 3 + j];
+                    t -= a * P24[j * 3 + i];
+                    FBUS_WX_ACC(t, P22, i, j);
+                    U22[i * 3 + j] = t;
                 }
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = i; j < 3; ++j) {
+                    double t = U22[i * 3 + j];
+                    if (i == j) t += Qd[1];  // + gyro noise on theta
+                    FBUS_XWT_ACC(t, U22, i, j);
+                    acc22[i * 3 + j] = t;
+                }
+            P.stdiag(2, acc22);
         }
-        // column operations inside the top-left part
-        {
-            double acc01[9], acc02[9], acc12[9], acc22[9];
+        FBUS_FENCE;
+        {   // M12 += B*P23^T + a*P25^T
+            double P23[9], P25[9];
+            P.ldblk(2, 3, P23);
+            P.ldblk(2, 5, P25);
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
                 for (int j = 0; j < 3; ++j) {
-                    double s = M01[i * 3 + j];
+                    double s = M12[i * 3 + j];
+                    s += a * P25[j * 3 + i];
                     FBUS_UNROLL
-                    for (int k = 0; k < 3; ++k) s += M02[i * 3 + k] * A[j * 3 + k];
-                    acc01[i * 3 + j] = s;
-                    acc02[i * 3 + j] = M02[i * 3 + j] + FBUS_XWT(M02, i, j);
-                    acc12[i * 3 + j] = M12[i * 3 + j] + FBUS_XWT(M12, i, j);
+                    for (int k = 0; k < 3; ++k) s += B[i * 3 + k] * P23[j * 3 + k];
+                    M12[i * 3 + j] = s;
+                }
+        }
+        FBUS_FENCE;
+        {   // 1b: P'11 (without the M13*B^T + a*M15 term), P'12 (without -a*M14)
+            double P13[9], P15[9], acc11[9], acc12[9];
+            P.lddiag(1, P11);
+            P.ldblk(1, 3, P13);
+            P.ldblk(1, 5, P15);
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = 0; j < 3; ++j) {
+                    double t = M12[i * 3 + j];
+                    FBUS_XWT_ACC(t, M12, i, j);
+                    acc12[i * 3 + j] = t;
                     if (j >= i) {
-                        double s1 = acc11[i * 3 + j];
+                        double s = P11[i * 3 + j];
+                        if (i == j) s += Qd[0];  // + accel noise on v
+                        s += a * P15[j * 3 + i];
                         FBUS_UNROLL
-                        for (int k = 0; k < 3; ++k) s1 += M12[i * 3 + k] * A[j * 3 + k];
-                        acc11[i * 3 + j] = s1 + (i == j ? Qd[0] : 0.0);                       // + accel noise on v
-                        acc22[i * 3 + j] = (U22[i * 3 + j] + FBUS_XWT(U22, i, j)) + (i == j ? Qd[1] : 0.0);  // + gyro noise on theta
+                        for (int k = 0; k < 3; ++k) {
+                            s += A[i * 3 + k] * P12[j * 3 + k];
+                            s += B[i * 3 + k] * P13[j * 3 + k];
+                            s += M12[i * 3 + k] * A[j * 3 + k];
+                        }
+                        acc11[i * 3 + j] = s;
                     }
                 }
-            P.stblk(0, 1, acc01);
-            P.stblk(0, 2, acc02);
             P.stdiag(1, acc11);
             P.stblk(1, 2, acc12);
-            P.stdiag(2, acc22);
+        }
+        FBUS_FENCE;
+        {   // 1a: P'00, P'01 (without M03*B^T + a*M05), P'02 (without -a*M04); uses OLD P11, P12 kept in registers
+            double P00[9], P01[9], P02[9], acc00[9], acc01[9], acc02[9];
+            P.lddiag(0, P00);
+            P.ldblk(0, 1, P01);
+            P.ldblk(0, 2, P02);
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = i; j < 3; ++j) {
+                    double m01 = P01[i * 3 + j];
+                    m01 += a * P11[i * 3 + j];  // M01[i][j]
+                    double t = P00[i * 3 + j];
+                    t += a * P01[j * 3 + i];    // M00[i][j]
+                    t += a * m01;
+                    acc00[i * 3 + j] = t;
+                }
+            FBUS_UNROLL
+            for (int e = 0; e < 9; ++e) {
+                P01[e] += a * P11[e];  // M01
+                P02[e] += a * P12[e];  // M02
+            }
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = 0; j < 3; ++j) {
+                    double s = P01[i * 3 + j];
+                    FBUS_UNROLL
+                    for (int k = 0; k < 3; ++k) s += P02[i * 3 + k] * A[j * 3 + k];
+                    acc01[i * 3 + j] = s;
+                    double t = P02[i * 3 + j];
+                    FBUS_XWT_ACC(t, P02, i, j);
+                    acc02[i * 3 + j] = t;
+                }
+            P.stdiag(0, acc00);
+            P.stblk(0, 1, acc01);
+            P.stblk(0, 2, acc02);
         }
     }
+    FBUS_FENCE;
     // ---------------- phase 2: block columns 4, 3, 5 of rows 0..2 -----------------------------
     double d01[9], d11[9];
     FBUS_UNROLL
     for (int kk = 0; kk < 3; ++kk) {
         const int k = (kk == 0) ? 4 : (kk == 1) ? 3 : 5;
-        double X0[9], X1[9], X2[9], X3[9], X4[9], X5[9];
-        P.ldblk(0, k, X0);
+        double X1[9];
         P.ldblk(1, k, X1);
-        P.ldblk(2, k, X2);
-        P.ldany(3, k, X3);
-        P.ldany(4, k, X4);
-        P.ldany(5, k, X5);
-        double M0[9], M1[9], M2[9];
-        FBUS_UNROLL
-        for (int i = 0; i < 3; ++i)
+        {   // row 0: M0 = P0k + a*P1k
+            double M0[9];
+            P.ldblk(0, k, M0);
             FBUS_UNROLL
-            for (int j = 0; j < 3; ++j) {
-                M0[i * 3 + j] = X0[i * 3 + j] + a * X1[i * 3 + j];
-                double s = X1[i * 3 + j] + a * X5[i * 3 + j];
+            for (int e = 0; e < 9; ++e) M0[e] += a * X1[e];
+            P.stblk(0, k, M0);
+            if (k == 4) {  // P'02 -= a*M04
                 FBUS_UNROLL
-                for (int c = 0; c < 3; ++c) s += A[i * 3 + c] * X2[c * 3 + j] + B[i * 3 + c] * X3[c * 3 + j];
-                M1[i * 3 + j] = s;
-                M2[i * 3 + j] = (X2[i * 3 + j] - a * X4[i * 3 + j]) + FBUS_WX(X2, i, j);
+                for (int i = 0; i < 3; ++i)
+                    FBUS_UNROLL
+                    for (int j = 0; j < 3; ++j) {
+                        double t = P.ld(i, 6 + j);
+                        t -= a * M0[i * 3 + j];
+                        P.st(i, 6 + j, t);
+                    }
+            } else if (k == 3) {  // d01 = M03*B^T
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i)
+                    FBUS_UNROLL
+                    for (int j = 0; j < 3; ++j) {
+                        double s = M0[i * 3] * B[j * 3];
+                        s += M0[i * 3 + 1] * B[j * 3 + 1];
+                        s += M0[i * 3 + 2] * B[j * 3 + 2];
+                        d01[i * 3 + j] = s;
+                    }
+            } else {  // P'01 += d01 + a*M05
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i)
+                    FBUS_UNROLL
+                    for (int j = 0; j < 3; ++j) {
+                        double t = P.ld(i, 3 + j) + d01[i * 3 + j];
+                        t += a * M0[i * 3 + j];
+                        P.st(i, 3 + j, t);
+                    }
             }
-        P.stblk(0, k, M0);
-        P.stblk(1, k, M1);
-        P.stblk(2, k, M2);
-        if (k == 4) {
-            // P'02 -= a*M04 ; P'12 -= a*M14 ; P'22 -= a*M24 (upper)
+        }
+        FBUS_FENCE;
+        double X2[9];
+        P.ldblk(2, k, X2);
+        {   // row 1: M1 = P1k + A*P2k + B*P3k + a*P5k
+            double X3[9], X5[9];
+            P.ldany(3, k, X3);
+            P.ldany(5, k, X5);
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
                 for (int j = 0; j < 3; ++j) {
-                    P.st(i, 6 + j, P.ld(i, 6 + j) - a * M0[i * 3 + j]);
-                    P.st(3 + i, 6 + j, P.ld(3 + i, 6 + j) - a * M1[i * 3 + j]);
-                    if (j >= i) P.st(6 + i, 6 + j, P.ld(6 + i, 6 + j) - a * M2[i * 3 + j]);
-                }
-            // process noise on the gyro-bias block diagonal (k == 4 block row 4)
-            FBUS_UNROLL
-            for (int i = 0; i < 3; ++i) P.st(12 + i, 12 + i, X4[i * 3 + i] + Qd[3]);
-        } else if (k == 3) {
-            // d01 = M03*B^T ; d11 = M13*B^T (upper)
-            FBUS_UNROLL
-            for (int i = 0; i < 3; ++i)
-                FBUS_UNROLL
-                for (int j = 0; j < 3; ++j) {
-                    double s = 0.0, s1 = 0.0;
+                    double s = X1[i * 3 + j];
+                    s += a * X5[i * 3 + j];
                     FBUS_UNROLL
                     for (int c = 0; c < 3; ++c) {
-                        s += M0[i * 3 + c] * B[j * 3 + c];
-                        s1 += M1[i * 3 + c] * B[j * 3 + c];
+                        s += A[i * 3 + c] * X2[c * 3 + j];
+                        s += B[i * 3 + c] * X3[c * 3 + j];
                     }
-                    d01[i * 3 + j] = s;
-                    d11[i * 3 + j] = s1;
+                    X1[i * 3 + j] = s;  // M1 in place (X1[i][j] is not read again)
                 }
-            FBUS_UNROLL
-            for (int i = 0; i < 3; ++i) P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);  // accel-bias noise
-        } else {
-            // k == 5:  P'01 += d01 + a*M05 ; P'11 += d11 + a*M15 (upper)
+            P.stblk(1, k, X1);
+            if (k == 4) {  // P'12 -= a*M14
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i)
+                    FBUS_UNROLL
+                    for (int j = 0; j < 3; ++j) {
+                        double t = P.ld(3 + i, 6 + j);
+                        t -= a * X1[i * 3 + j];
+                        P.st(3 + i, 6 + j, t);
+                    }
+            } else if (k == 3) {  // d11 = M13*B^T (upper) ; accel-bias process noise on P33's diagonal
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i)
+                    FBUS_UNROLL
+                    for (int j = i; j < 3; ++j) {
+                        double s = X1[i * 3] * B[j * 3];
+                        s += X1[i * 3 + 1] * B[j * 3 + 1];
+                        s += X1[i * 3 + 2] * B[j * 3 + 2];
+                        d11[i * 3 + j] = s;
+                    }
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i) P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);
+            } else {  // P'11 += d11 + a*M15 (upper)
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i)
+                    FBUS_UNROLL
+                    for (int j = i; j < 3; ++j) {
+                        double t = P.ld(3 + i, 3 + j) + d11[i * 3 + j];
+                        t += a * X1[i * 3 + j];
+                        P.st(3 + i, 3 + j, t);
+                    }
+            }
+        }
+        FBUS_FENCE;
+        {   // row 2: M2 = (I+Wm)*P2k - a*P4k
+            double X4[9], M2[9];
+            P.ldany(4, k, X4);
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
                 for (int j = 0; j < 3; ++j) {
-                    P.st(i, 3 + j, P.ld(i, 3 + j) + (d01[i * 3 + j] + a * M0[i * 3 + j]));
-                    if (j >= i) P.st(3 + i, 3 + j, P.ld(3 + i, 3 + j) + (d11[i * 3 + j] + a * M1[i * 3 + j]));
+                    double t = X2[i * 3 + j];
+                    t -= a * X4[i * 3 + j];
+                    FBUS_WX_ACC(t, X2, i, j);
+                    M2[i * 3 + j] = t;
                 }
+            P.stblk(2, k, M2);
+            if (k == 4) {  // P'22 -= a*M24 (upper) ; gyro-bias process noise on P44's diagonal
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i)
+                    FBUS_UNROLL
+                    for (int j = i; j < 3; ++j) {
+                        double t = P.ld(6 + i, 6 + j);
+                        t -= a * M2[i * 3 + j];
+                        P.st(6 + i, 6 + j, t);
+                    }
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i) P.st(12 + i, 12 + i, X4[i * 3 + i] + Qd[3]);
+            }
         }
+        FBUS_FENCE;
     }
-#undef FBUS_WX
-#undef FBUS_XWT
+#undef FBUS_WX_ACC
+#undef FBUS_XWT_ACC
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,10 +530,10 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
 // ------------------------------------------------------------------------------------------------
 // marker-map lookup (std::map::find on markerPoseServer_, filter.cpp:353,442,671)
 // ------------------------------------------------------------------------------------------------
-FBUS_HD int find_marker(const DevConsts& k, int id) {
+FBUS_HD int find_marker(const DevConsts& k, const MarkerTable* tab, int id) {
     int m = -1;
     for (int i = 0; i < k.n_markers; ++i)
-        if (k.mk[i].id == id) m = (m < 0) ? i : m;
+        if (tab->mk[i].id == id) m = (m < 0) ? i : m;
     return m;
 }
 
@@ -452,6 +565,35 @@ FBUS_HD void vision_pose(const DevConsts& k, const MarkerConst& mk, const double
 // S is SPD with cond <= ~13 on the reference's logs, so Cholesky replaces the reference's LDLT
 // (filter.cpp:711) to ~1e-15.
 // ------------------------------------------------------------------------------------------------
+// In-place Cholesky of a packed lower-triangular matrix (row-major packed: L[i*(i+1)/2 + j]); also returns the
+// reciprocal diagonal.  Template recursion instead of a loop over columns: nvcc does not fully unroll the
+// column loop (it contains sqrt/division slow paths), and a rolled loop would index L dynamically and push
+// it to local memory.
+template <int N, int J>
+struct CholStep {
+    static FBUS_HD void run(double* L, double* Li) {
+        double s = L[J * (J + 1) / 2 + J];
+        FBUS_UNROLL
+        for (int c = 0; c < J; ++c) s -= L[J * (J + 1) / 2 + c] * L[J * (J + 1) / 2 + c];
+        const double d = sqrt(s);
+        const double di = 1.0 / d;
+        L[J * (J + 1) / 2 + J] = d;
+        Li[J] = di;
+        FBUS_UNROLL
+        for (int i = J + 1; i < N; ++i) {
+            double s2 = L[i * (i + 1) / 2 + J];
+            FBUS_UNROLL
+            for (int c = 0; c < J; ++c) s2 -= L[i * (i + 1) / 2 + c] * L[J * (J + 1) / 2 + c];
+            L[i * (i + 1) / 2 + J] = s2 * di;
+        }
+        CholStep<N, J + 1>::run(L, Li);
+    }
+};
+template <int N>
+struct CholStep<N, N> {
+    static FBUS_HD void run(double*, double*) {}
+};
+
 template <int S>
 FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
                                 const double* yQ) {
@@ -474,9 +616,9 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
         for (int i = 0; i < 3; ++i)
             FBUS_UNROLL
             for (int j = 0; j < 3; ++j) {
-                double s = 0.0;
-                FBUS_UNROLL
-                for (int c = 0; c < 3; ++c) s += k.R_IL[i * 3 + c] * n.R[j * 3 + c];
+                double s = k.R_IL[i * 3] * n.R[j * 3];
+                s += k.R_IL[i * 3 + 1] * n.R[j * 3 + 1];
+                s += k.R_IL[i * 3 + 2] * n.R[j * 3 + 2];
                 Hp0[i * 3 + j] = -s;
             }
         FBUS_UNROLL
@@ -490,31 +632,30 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
         double t1[4], hQ[4];
         qmul_conjb(k.Q_IL, n.q, t1);
         qmul(t1, mk.q, hQ);
-        const double w = 0.5 * n.q[0], x = 0.5 * n.q[1], y = 0.5 * n.q[2], z = 0.5 * n.q[3];
-        const double LL[12] = {-x, -y, -z, w, -z, y, z, w, -x, -y, x, w};
-        FBUS_UNROLL
-        for (int i = 0; i < 4; ++i)
-            FBUS_UNROLL
-            for (int j = 0; j < 3; ++j) {
-                double s = 0.0;
-                FBUS_UNROLL
-                for (int c = 0; c < 4; ++c) s += mk.CM[i * 4 + c] * LL[c * 3 + j];
-                Hq[i * 3 + j] = s;
-            }
         double k1 = 0.0, k2 = 0.0;
         FBUS_UNROLL
         for (int i = 0; i < 4; ++i) {
             k1 += (yQ[i] - hQ[i]) * (yQ[i] - hQ[i]);
             k2 += (yQ[i] + hQ[i]) * (yQ[i] + hQ[i]);
         }
-        const double sg = (k1 > k2) ? -1.0 : 1.0;  // filter.cpp:702-706 (strict >)
+        const double sg = (k1 > k2) ? -1.0 : 1.0;  // filter.cpp:702-706 (strict >): flips hQ and H[3:7,6:9]
+        const double hs = 0.5 * sg;
+        const double w = hs * n.q[0], x = hs * n.q[1], y = hs * n.q[2], z = hs * n.q[3];
+        const double LL[12] = {-x, -y, -z, w, -z, y, z, w, -x, -y, x, w};
         FBUS_UNROLL
-        for (int i = 0; i < 12; ++i) Hq[i] *= sg;
+        for (int i = 0; i < 4; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                double s = mk.CM[i * 4] * LL[j];
+                FBUS_UNROLL
+                for (int c = 1; c < 4; ++c) s += mk.CM[i * 4 + c] * LL[c * 3 + j];
+                Hq[i * 3 + j] = s;
+            }
         FBUS_UNROLL
         for (int i = 0; i < 4; ++i) r[3 + i] = yQ[i] - sg * hQ[i];
     }
-    // ---- S = Hs P6 Hs^T + R (lower triangle in Sm) -------------------------------------------
-    double L[28];  // lower-triangular factor of S, row-major packed: L[i*(i+1)/2 + j]
+    // ---- S = Hs P6 Hs^T + R (lower triangle, packed in L) --------------------------------------
+    double L[28];  // row-major packed lower triangle: L[i*(i+1)/2 + j]
 #define FBUS_L(i, j) L[(i) * ((i) + 1) / 2 + (j)]
     {
         double P00[9], P02[9], P22[9];
@@ -526,11 +667,16 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
         for (int i = 0; i < 3; ++i)
             FBUS_UNROLL
             for (int j = 0; j < 3; ++j) {
-                double s0 = 0.0, s1 = 0.0;
+                double s0 = Hp0[i * 3] * P00[j], s1 = Hp0[i * 3] * P02[j];
+                FBUS_UNROLL
+                for (int c = 1; c < 3; ++c) {
+                    s0 += Hp0[i * 3 + c] * P00[c * 3 + j];
+                    s1 += Hp0[i * 3 + c] * P02[c * 3 + j];
+                }
                 FBUS_UNROLL
                 for (int c = 0; c < 3; ++c) {
-                    s0 += Hp0[i * 3 + c] * P00[c * 3 + j] + Hp2[i * 3 + c] * P02[j * 3 + c];
-                    s1 += Hp0[i * 3 + c] * P02[c * 3 + j] + Hp2[i * 3 + c] * P22[c * 3 + j];
+                    s0 += Hp2[i * 3 + c] * P02[j * 3 + c];
+                    s1 += Hp2[i * 3 + c] * P22[c * 3 + j];
                 }
                 Ep[i * 6 + j] = s0;
                 Ep[i * 6 + 3 + j] = s1;
@@ -539,32 +685,36 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
         for (int i = 0; i < 4; ++i)
             FBUS_UNROLL
             for (int j = 0; j < 3; ++j) {
-                double s0 = 0.0, s1 = 0.0;
+                double s0 = Hq[i * 3] * P02[j * 3], s1 = Hq[i * 3] * P22[j];
                 FBUS_UNROLL
-                for (int c = 0; c < 3; ++c) {
+                for (int c = 1; c < 3; ++c) {
                     s0 += Hq[i * 3 + c] * P02[j * 3 + c];
                     s1 += Hq[i * 3 + c] * P22[c * 3 + j];
                 }
                 Eq[i * 6 + j] = s0;
                 Eq[i * 6 + 3 + j] = s1;
             }
-        // S lower triangle
         FBUS_UNROLL
         for (int i = 0; i < 3; ++i)
             FBUS_UNROLL
             for (int j = 0; j <= i; ++j) {
                 double s = (i == j) ? k.Rp : 0.0;
                 FBUS_UNROLL
-                for (int c = 0; c < 3; ++c) s += Ep[i * 6 + c] * Hp0[j * 3 + c] + Ep[i * 6 + 3 + c] * Hp2[j * 3 + c];
+                for (int c = 0; c < 3; ++c) {
+                    s += Ep[i * 6 + c] * Hp0[j * 3 + c];
+                    s += Ep[i * 6 + 3 + c] * Hp2[j * 3 + c];
+                }
                 FBUS_L(i, j) = s;
             }
         FBUS_UNROLL
         for (int i = 0; i < 4; ++i) {
             FBUS_UNROLL
             for (int j = 0; j < 3; ++j) {  // S[3+i][j] = Eq[i][0:3] Hp0[j]^T + Eq[i][3:6] Hp2[j]^T
-                double s = 0.0;
+                double s = Eq[i * 6] * Hp0[j * 3];
                 FBUS_UNROLL
-                for (int c = 0; c < 3; ++c) s += Eq[i * 6 + c] * Hp0[j * 3 + c] + Eq[i * 6 + 3 + c] * Hp2[j * 3 + c];
+                for (int c = 1; c < 3; ++c) s += Eq[i * 6 + c] * Hp0[j * 3 + c];
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) s += Eq[i * 6 + 3 + c] * Hp2[j * 3 + c];
                 FBUS_L(3 + i, j) = s;
             }
             FBUS_UNROLL
@@ -576,24 +726,9 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
             }
         }
     }
-    // ---- Cholesky S = L L^T (in place), keep reciprocal diagonal -----------------------------
+    // ---- Cholesky S = L L^T (in place), reciprocal diagonal in Li -------------------------------
     double Li[7];
-    FBUS_UNROLL
-    for (int j = 0; j < 7; ++j) {
-        double s = FBUS_L(j, j);
-        FBUS_UNROLL
-        for (int c = 0; c < j; ++c) s -= FBUS_L(j, c) * FBUS_L(j, c);
-        const double d = sqrt(s);
-        Li[j] = 1.0 / d;
-        FBUS_L(j, j) = d;
-        FBUS_UNROLL
-        for (int i = j + 1; i < 7; ++i) {
-            double s2 = FBUS_L(i, j);
-            FBUS_UNROLL
-            for (int c = 0; c < j; ++c) s2 -= FBUS_L(i, c) * FBUS_L(j, c);
-            FBUS_L(i, j) = s2 * Li[j];
-        }
-    }
+    CholStep<7, 0>::run(L, Li);
     // ---- X = L^-1 Hs (7x6), z = L^-1 r ; C = X^T X ; u = X^T z -------------------------------
     double Cm[21], u[6];  // C lower packed: Cm[i*(i+1)/2+j]
 #define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
@@ -617,63 +752,81 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
         for (int i = 0; i < 6; ++i) {
             FBUS_UNROLL
             for (int j = 0; j <= i; ++j) {
-                double s = 0.0;
+                double s = X[i] * X[j];
                 FBUS_UNROLL
-                for (int c = 0; c < 7; ++c) s += X[c * 6 + i] * X[c * 6 + j];
+                for (int c = 1; c < 7; ++c) s += X[c * 6 + i] * X[c * 6 + j];
                 FBUS_C(i, j) = s;
             }
-            double s = 0.0;
+            double s = X[i] * z[0];
             FBUS_UNROLL
-            for (int c = 0; c < 7; ++c) s += X[c * 6 + i] * z[c];
+            for (int c = 1; c < 7; ++c) s += X[c * 6 + i] * z[c];
             u[i] = s;
         }
     }
 #undef FBUS_L
-    // ---- Cholesky C = Lc Lc^T (in place in Cm) -----------------------------------------------
-    FBUS_UNROLL
-    for (int j = 0; j < 6; ++j) {
-        double s = FBUS_C(j, j);
+    // ---- Cholesky C = Lc Lc^T (in place in Cm) ; y = Lc^-1 u -------------------------------------
+    // dx = K r = G^T u = Z^T y = Za^T y[0:3] + Zb^T y[3:6]
+    double y[6];
+    {
+        double Lci[6];
+        CholStep<6, 0>::run(Cm, Lci);
         FBUS_UNROLL
-        for (int c = 0; c < j; ++c) s -= FBUS_C(j, c) * FBUS_C(j, c);
-        const double d = sqrt(s);
-        const double di = 1.0 / d;
-        FBUS_C(j, j) = d;
-        FBUS_UNROLL
-        for (int i = j + 1; i < 6; ++i) {
-            double s2 = FBUS_C(i, j);
+        for (int i = 0; i < 6; ++i) {
+            double s = u[i];
             FBUS_UNROLL
-            for (int c = 0; c < j; ++c) s2 -= FBUS_C(i, c) * FBUS_C(j, c);
-            FBUS_C(i, j) = s2 * di;
+            for (int j = 0; j < i; ++j) s -= FBUS_C(i, j) * y[j];
+            y[i] = s * Lci[i];
         }
     }
-    // ---- stream G (rows 0..2 and 6..8 of P): dx = G^T u ; Za = rows 0..2 of Lc^T G -------------
-    double dx[18];
-    double Z[54];  // 3 x 18
-    {
+    double dth[3];  // attitude part of dx (needed whole before the quaternion injection)
+    double Z[54];   // 3 x 18
+    // ---- stream G (rows 0..2 and 6..8 of P): Za = rows 0..2 of Lc^T G -----------------------------
+    FBUS_UNROLL
+    for (int m = 0; m < 6; ++m) {
+        const int row = (m < 3) ? m : (3 + m);  // 0,1,2,6,7,8
         FBUS_UNROLL
         for (int c = 0; c < 18; ++c) {
-            dx[c] = 0.0;
-            Z[c] = 0.0; Z[18 + c] = 0.0; Z[36 + c] = 0.0;
-        }
-        FBUS_UNROLL
-        for (int m = 0; m < 6; ++m) {
-            const int row = (m < 3) ? m : (3 + m);  // 0,1,2,6,7,8
+            const double g = P.ld(row, c);
             FBUS_UNROLL
-            for (int c = 0; c < 18; ++c) {
-                const double g = P.ld(row, c);
-                dx[c] += u[m] * g;
-                FBUS_UNROLL
-                for (int kz = 0; kz < 3; ++kz)
-                    if (m >= kz) Z[kz * 18 + c] += FBUS_C(m, kz) * g;
+            for (int kz = 0; kz < 3; ++kz) {
+                if (m == kz) Z[kz * 18 + c] = FBUS_C(m, kz) * g;
+                else if (m > kz) Z[kz * 18 + c] += FBUS_C(m, kz) * g;
             }
         }
     }
+    // error-state injection, first half (filter.cpp:726-733); rotmatI2G deliberately NOT refreshed
+#define FBUS_DX_ACC(dst, c)       \
+    do {                          \
+        dst += y0 * Z[c];         \
+        dst += y1 * Z[18 + (c)];  \
+        dst += y2 * Z[36 + (c)];  \
+    } while (0)
+    {
+        const double y0 = y[0], y1 = y[1], y2 = y[2];
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            FBUS_DX_ACC(n.p[i], i);
+            FBUS_DX_ACC(n.v[i], 3 + i);
+            dth[i] = 0.0;
+            FBUS_DX_ACC(dth[i], 6 + i);
+            FBUS_DX_ACC(n.ba[i], 9 + i);
+            FBUS_DX_ACC(n.bg[i], 12 + i);
+            FBUS_DX_ACC(n.g[i], 15 + i);
+        }
+    }
+    FBUS_FENCE;
     // ---- sweep 1: P -= Za^T Za -----------------------------------------------------------------
     FBUS_UNROLL
     for (int i = 0; i < 18; ++i)
         FBUS_UNROLL
-        for (int j = i; j < 18; ++j)
-            P.st(i, j, P.ld(i, j) - (Z[i] * Z[j] + Z[18 + i] * Z[18 + j] + Z[36 + i] * Z[36 + j]));
+        for (int j = i; j < 18; ++j) {
+            double v = P.ld(i, j);
+            v -= Z[i] * Z[j];
+            v -= Z[18 + i] * Z[18 + j];
+            v -= Z[36 + i] * Z[36 + j];
+            P.st(i, j, v);
+        }
+    FBUS_FENCE;
     // ---- rebuild G_b = P_old[6..8,:] = P1[6..8,:] + Za[:,6..8]^T Za, then Zb = Lbb^T G_b in place ----
     {
         const double z06 = Z[6], z07 = Z[7], z08 = Z[8], z16 = Z[18 + 6], z17 = Z[18 + 7], z18 = Z[18 + 8], z26 = Z[36 + 6],
@@ -681,35 +834,51 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
         FBUS_UNROLL
         for (int c = 0; c < 18; ++c) {
             const double za0 = Z[c], za1 = Z[18 + c], za2 = Z[36 + c];
-            const double g3 = P.ld(6, c) + (z06 * za0 + z16 * za1 + z26 * za2);
-            const double g4 = P.ld(7, c) + (z07 * za0 + z17 * za1 + z27 * za2);
-            const double g5 = P.ld(8, c) + (z08 * za0 + z18 * za1 + z28 * za2);
-            Z[c] = FBUS_C(3, 3) * g3 + FBUS_C(4, 3) * g4 + FBUS_C(5, 3) * g5;
-            Z[18 + c] = FBUS_C(4, 4) * g4 + FBUS_C(5, 4) * g5;
+            double g3 = P.ld(6, c), g4 = P.ld(7, c), g5 = P.ld(8, c);
+            g3 += z06 * za0; g3 += z16 * za1; g3 += z26 * za2;
+            g4 += z07 * za0; g4 += z17 * za1; g4 += z27 * za2;
+            g5 += z08 * za0; g5 += z18 * za1; g5 += z28 * za2;
+            double t3 = FBUS_C(3, 3) * g3;
+            t3 += FBUS_C(4, 3) * g4;
+            t3 += FBUS_C(5, 3) * g5;
+            double t4 = FBUS_C(4, 4) * g4;
+            t4 += FBUS_C(5, 4) * g5;
+            Z[c] = t3;
+            Z[18 + c] = t4;
             Z[36 + c] = FBUS_C(5, 5) * g5;
         }
     }
 #undef FBUS_C
+    {   // injection, second half
+        const double y0 = y[3], y1 = y[4], y2 = y[5];
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            FBUS_DX_ACC(n.p[i], i);
+            FBUS_DX_ACC(n.v[i], 3 + i);
+            FBUS_DX_ACC(dth[i], 6 + i);
+            FBUS_DX_ACC(n.ba[i], 9 + i);
+            FBUS_DX_ACC(n.bg[i], 12 + i);
+            FBUS_DX_ACC(n.g[i], 15 + i);
+        }
+    }
+#undef FBUS_DX_ACC
+    FBUS_FENCE;
     // ---- sweep 2: P -= Zb^T Zb -----------------------------------------------------------------
     FBUS_UNROLL
     for (int i = 0; i < 18; ++i)
         FBUS_UNROLL
-        for (int j = i; j < 18; ++j)
-            P.st(i, j, P.ld(i, j) - (Z[i] * Z[j] + Z[18 + i] * Z[18 + j] + Z[36 + i] * Z[36 + j]));
-    // ---- inject the error state (filter.cpp:726-733); rotmatI2G deliberately NOT refreshed ------
-    FBUS_UNROLL
-    for (int i = 0; i < 3; ++i) {
-        n.p[i] += dx[i];
-        n.v[i] += dx[3 + i];
-        n.ba[i] += dx[9 + i];
-        n.bg[i] += dx[12 + i];
-        n.g[i] += dx[15 + i];
-    }
+        for (int j = i; j < 18; ++j) {
+            double v = P.ld(i, j);
+            v -= Z[i] * Z[j];
+            v -= Z[18 + i] * Z[18 + j];
+            v -= Z[36 + i] * Z[36 + j];
+            P.st(i, j, v);
+        }
     {   // VectorToQuaterniond (matrix_math.hpp:90-99): v/|v| * sin(|v|/2); NaN at exactly zero, as the reference
-        const double vn = norm3(dx + 6);
+        const double vn = norm3(dth);
         double sh, ch;
         sincos(vn / 2, &sh, &ch);
-        const double dq[4] = {ch, dx[6] / vn * sh, dx[7] / vn * sh, dx[8] / vn * sh};
+        const double dq[4] = {ch, dth[0] / vn * sh, dth[1] / vn * sh, dth[2] / vn * sh};
         double qn[4];
         qmul(n.q, dq, qn);
         qnormalize(qn);

@@ -406,12 +406,14 @@ void UpdateNominalState(Filter* f, double dt, const double* accel, const double*
 }
 
 // filter.cpp:483-531 over an explicit candidate range
-void BatchImuProcessing(const Consts& k, Filter* f, const double* t, const double* data, size_t B, size_t b,
-                        size_t first, size_t count, double t_end) {
+size_t BatchImuProcessing(const Consts& k, Filter* f, const double* t, const double* data, size_t B, size_t b,
+                          size_t first, size_t count, double t_end) {
     const double start = f->t;
+    size_t imuCnt = 0;  // samples erased afterwards (filter.cpp:492-503,520)
     for (size_t i = first; i < first + count; ++i) {
-        if (t[i] < start) continue;
+        if (t[i] < start) { imuCnt++; continue; }
         if (t[i] > t_end) break;
+        imuCnt++;
         double accel[3], gyro[3];
         for (int c = 0; c < 3; ++c) { accel[c] = data[(i * 6 + c) * B + b]; gyro[c] = data[(i * 6 + 3 + c) * B + b]; }
         const double dt = t[i] - f->t;
@@ -419,6 +421,7 @@ void BatchImuProcessing(const Consts& k, Filter* f, const double* t, const doubl
         UpdateNominalState(f, dt, accel, gyro);
         f->t = t[i];
     }
+    return imuCnt;
 }
 
 // nearest-marker scan shared by filter.cpp:329-341, 418-430, 639-658
@@ -847,8 +850,7 @@ int orc_step_windows(orc_handle* h, const fbus_imu_stream* imu, const fbus_det_f
                     if (InitializePose(h->k, &f, d.data(), n, t_det, cnt)) { f.initialised = 1; cursor = win_off[w + 1]; }
                 } else {
                     ResetSystemState(h->k, &f, d.data(), n, t_det);
-                    BatchImuProcessing(h->k, &f, imu->t, imu->data, B, b, first, count, t_det);
-                    cursor = win_off[w + 1];
+                    cursor = first + BatchImuProcessing(h->k, &f, imu->t, imu->data, B, b, first, count, t_det);
                     ObservationUpdate(h->k, &f, d.data(), n);
                 }
                 if (trace) {

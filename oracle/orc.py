@@ -4,9 +4,9 @@ It reuses the product's ctypes struct definitions (the oracle takes the same C s
 from __future__ import annotations
 
 import ctypes as C
-import importlib.util
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -15,14 +15,9 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "_build", "libfbus_oracle.so")
 
 
-def _capi():
-    spec = importlib.util.spec_from_file_location("fbus_ekf_b200_capi_for_oracle", os.path.join(ROOT, "fbus_ekf_b200", "capi.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
-
-
-capi = _capi()
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from fbus_ekf_b200 import capi  # noqa: E402  (struct definitions only; the oracle never calls the product library)
 _lib = None
 
 

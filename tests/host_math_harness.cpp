@@ -23,7 +23,8 @@ void hm_config_default(fbus_config* c) { config_default(c); }
 
 int hm_propagate(const fbus_config* cfg, double* P171, double* nom, const double* accel, const double* gyro, double dt) {
     DevConsts k;
-    if (make_dev_consts(cfg, &k)) return -1;
+    MarkerTable tab;
+    if (make_dev_consts(cfg, &k, &tab)) return -1;
     Nominal n;
     nom_from(nom, n);
     double w[3], a[3];
@@ -38,14 +39,39 @@ int hm_propagate(const fbus_config* cfg, double* P171, double* nom, const double
 
 int hm_update(const fbus_config* cfg, double* P171, double* nom, int marker_id, const double* yP, const double* yQ) {
     DevConsts k;
-    if (make_dev_consts(cfg, &k)) return -1;
-    const int m = find_marker(k, marker_id);
+    MarkerTable tab;
+    if (make_dev_consts(cfg, &k, &tab)) return -1;
+    const int m = find_marker(k, &tab, marker_id);
     if (m < 0) return -2;
     Nominal n;
     nom_from(nom, n);
     Cov<1> P{P171};
-    measurement_update<1>(P, n, k, k.mk[m], yP, yQ);
+    measurement_update<1>(P, n, k, tab.mk[m], yP, yQ);
     nom_to(n, nom);
+    return 0;
+}
+}
+
+#include "../fbus_ekf_b200/csrc/fbus_refract.cuh"
+extern "C" {
+// corners16: Lxy x4, Rxy x4 (float32) -> corners3d[12], pose[7]; returns valid flag
+int hm_refract(const fbus_config* cfg, const float* c16, double* c3d, double* pose) {
+    DevConsts k;
+    MarkerTable tab;
+    if (make_dev_consts(cfg, &k, &tab)) return -1;
+    int ok = 1;
+    for (int i = 0; i < 4; ++i) {
+        const double nrm = triangulate_corner(k, c16[2 * i], c16[2 * i + 1], c16[8 + 2 * i], c16[8 + 2 * i + 1], c3d + 3 * i);
+        if (nrm > k.dect_thres) ok = 0;
+    }
+    marker_pose(c3d, k.rod_s, k.rod_c, pose, pose + 3);
+    return ok;
+}
+int hm_marker_pose(const fbus_config* cfg, const double* c3d, double* pose) {
+    DevConsts k;
+    MarkerTable tab;
+    if (make_dev_consts(cfg, &k, &tab)) return -1;
+    marker_pose(c3d, k.rod_s, k.rod_c, pose, pose + 3);
     return 0;
 }
 }
