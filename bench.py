@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched FBUS-EKF hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on all host cores
+
+Metric (BASELINE.json): filter-steps/sec (batched EKF, FP64).  1 filter-step = one IMU propagate (F1+F2) or one
+marker-pose update (F4 incl. F5) for one filter.  Workload = BASELINE configs[4]: 1,048,576 Monte-Carlo filters per
+GPU on synthetic 200 Hz IMU + 25 Hz marker poses; one bench "step" = one second of stream for every filter
+(200 propagates + 25 updates per filter) through ONE launch of the fused window kernel.  The truth trajectory is
+periodic in that second, so every step replays the same device-resident noisy streams with timestamps advanced by
+one period: the filters keep running, nothing is reset or cached between steps.
+
+One JSON line on stdout (rank 0).  `value` = device-resident inputs; `e2e` = the same call with HOST (pinned)
+buffers, i.e. host->device copies of every step's streams and a device->host read of the step's statistics inside
+the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "filter-steps/sec (batched EKF, FP64)"
+UNIT = "filter-steps/s"
+# algorithmic work model (SURVEY.md 8d / BASELINE.md 3): FMA = 2 flops, structural zeros not counted, full 18x18 P
+FLOP_IMU_STEP = 3050.0
+FLOP_UPDATE = 8700.0
+FLOP_SOLVE = 1900.0
+BYTES_SOLVE = 124.0
+PERIOD = 1.0  # seconds of stream per bench step
+IMU_RATE, FRAME_RATE = 200.0, 25.0
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def shifted(traj, k):
+    """timestamps of bench step k (the trajectory is periodic with PERIOD)"""
+    return traj["t_imu"] + k * PERIOD, traj["t_frames"] + k * PERIOD
+
+
+# ------------------------------------------------------------------------------------------------------- CPU arm
+def cpu_arm(cfg, traj, target_seconds=15.0, threads=None, max_filters=None):
+    """The oracle (scalar port of the reference's filter.cpp, dense 18x18 products) as independent copies on all host
+    cores.  Bounded sample: `B` filters x `passes` seconds of the same synthetic stream."""
+    import orc
+    from fbus_ekf_b200 import capi
+    threads = threads or os.cpu_count() or 1
+    B = 32 * threads
+    if max_filters:
+        B = min(B, max_filters)
+    N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
+    rng = np.random.default_rng(123)
+    imu = np.ascontiguousarray(traj["base_imu"][:, :, None] + rng.normal(size=(N, 6, B)) * np.array([0.015] * 3 + [1e-3] * 3)[None, :, None])
+    ids = np.zeros((W, 1, B), dtype=np.int32)
+    pose = np.repeat(traj["base_pose"][:, None, :, None], B, axis=3) + rng.normal(size=(W, 1, 7, B)) * 2.5e-4
+    pose[:, :, 3:7, :] /= np.linalg.norm(pose[:, :, 3:7, :], axis=2, keepdims=True)
+    pose = np.ascontiguousarray(pose)
+    o = orc.Oracle(cfg, B)
+
+    def one_pass(k):
+        ti, tf = shifted(traj, k)
+        s = capi.make_imu_stream(ti, imu, B)
+        d = capi.make_det_frames(tf, ids, pose, B, 1)
+        o.step_windows(s, d, traj["win_off"], 0, W, None, threads)
+
+    t0 = time.perf_counter()
+    one_pass(0)  # includes the pose initialisation frame; also calibrates the pass time
+    t_pass = time.perf_counter() - t0
+    passes = int(max(2, min(400, round(target_seconds / max(t_pass, 1e-3)))))
+    t0 = time.perf_counter()
+    for k in range(1, passes + 1):
+        one_pass(k)
+    dt = time.perf_counter() - t0
+    steps = B * (N + W) * passes
+    st = o.get_state(with_cov=False)
+    finite = bool(np.isfinite(st["p"]).all())
+    return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{B} filters x {passes} s of the synthetic 200 Hz IMU + 25 Hz marker stream ({steps} filter-steps in {dt:.1f} s), "
+                      f"oracle/fbus_oracle.cpp (dense port of filter.cpp), {threads} threads", "finite": finite,
+            "seconds": dt, "steps_per_pass": B * (N + W)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be built in this
+    image (needs Eigen3/OpenCV/ArUco/yaml-cpp/glog), so this is the oracle port, on every host core, rank 0 only."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    import __graft_entry__ as ge
+    ge.build()
+    from fbus_ekf_b200 import capi, synth
+    cfg = capi.config_default()
+    traj = synth.truth_trajectory(cfg, PERIOD, IMU_RATE, FRAME_RATE, periodic=True)
+    threads = os.cpu_count() or 1
+    k_total = max(1, args.steps)
+    # each "step" = a bounded sample; whole run sized to a few minutes at most
+    per_step_seconds = min(20.0, 120.0 / (k_total + args.warmup))
+    for _ in range(args.warmup):
+        cpu_arm(cfg, traj, target_seconds=min(2.0, per_step_seconds), threads=threads)
+    vals, secs, cb = [], 0.0, None
+    for _ in range(k_total):
+        cb = cpu_arm(cfg, traj, target_seconds=per_step_seconds, threads=threads)
+        vals.append(cb["value"])
+        secs += cb["seconds"]
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / k_total, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(env_int("FBUS_BENCH_BATCH", 1 << 20), max(1, args.gpus)), "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(batch, world):
+    return {"workload": "BASELINE configs[4]: 1,048,576 Monte-Carlo filters per GPU (perturbed noise seeds, Philox keyed by global "
+                        "filter index) on synthetic 200 Hz IMU + 25 Hz marker poses; 1 bench step = 1 s of stream per filter",
+            "filters_per_gpu": batch, "filters_total": batch * world, "imu_steps_per_filter_per_step": int(IMU_RATE * PERIOD),
+            "updates_per_filter_per_step": int(FRAME_RATE * PERIOD), "state": "18-state error-state EKF, 7-row marker-pose update",
+            "parallelism": f"independent filters sharded over {world} GPU(s), no hot-path collective",
+            "l2": "inputs per step (imu+detections) are far larger than the 126 MB L2 at the default batch"}
+
+
+# ------------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        import __graft_entry__ as ge
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from fbus_ekf_b200 import BatchFilter, capi, synth
+
+    B = env_int("FBUS_BENCH_BATCH", 1 << 20)
+    K, Wm = args.steps, args.warmup
+    cfg = capi.config_default()
+    traj = synth.truth_trajectory(cfg, PERIOD, IMU_RATE, FRAME_RATE, periodic=True)
+    N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
+    steps_per_filter = N + W
+
+    f = BatchFilter(cfg, batch=B, device=local)
+    stream = torch.cuda.ExternalStream(f.stream, device=dev)
+    imu_d = torch.empty((N, 6, B), dtype=torch.float64, device=dev)
+    id_d = torch.empty((W, 1, B), dtype=torch.int32, device=dev)
+    pose_d = torch.empty((W, 1, 7, B), dtype=torch.float64, device=dev)
+    f.SynthStreams(synth.make_synth_spec(traj, seed=20260117 + 5, filter_offset=rank * B), imu_d.data_ptr(), id_d.data_ptr(),
+                   pose_d.data_ptr())
+
+    def gpu_step(k):
+        ti, tf = shifted(traj, k)
+        imu = capi.make_imu_stream(ti, imu_d.data_ptr(), B, capi.FBUS_MEM_DEVICE)
+        det = capi.make_det_frames(tf, id_d.data_ptr(), pose_d.data_ptr(), B, 1, capi.FBUS_MEM_DEVICE)
+        f.StepWindows(imu, det, traj["win_off"], 0, W)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    fp64_peak = f.MeasureFp64Peak()  # DFMA microbenchmark on this GPU: the FP64 roofline denominator (burst)
+
+    for k in range(Wm):
+        gpu_step(k)
+    f.Synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record(stream)
+    for k in range(K):
+        gpu_step(Wm + k)
+        ev[k + 1].record(stream)
+    f.Synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev[0].elapsed_time(ev[K])
+    launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total_max = float(tmax.item())
+    value = world * B * steps_per_filter * K / (ms_total_max * 1e-3)
+
+    # ---- final statistics: local sums on the device, one NCCL all-reduce over NVLink (the only collective) ----------
+    k_last = Wm + K - 1
+    tp = torch.tensor(traj["truth_p"][-1], dtype=torch.float64, device=dev).reshape(3, 1).expand(3, B).contiguous()
+    tq = torch.tensor(traj["truth_q"][-1], dtype=torch.float64, device=dev).reshape(4, 1).expand(4, B).contiguous()
+    st_d = torch.zeros(capi.FBUS_NSTATS, dtype=torch.float64, device=dev)
+    f.Stats(tp.data_ptr(), tq.data_ptr(), capi.FBUS_MEM_DEVICE, out_dev_ptr=st_d.data_ptr(), want_host=False)
+    f.Synchronize()
+    sums, mx = st_d[:5].clone(), st_d[5:6].clone()
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sums = sums.cpu().numpy()
+    n_ok = max(sums[3], 1.0)
+    stats = {"rmse_pos_m": float(np.sqrt(sums[0] / n_ok)), "rmse_att_rad": float(np.sqrt(sums[1] / n_ok)),
+             "nees_pose_mean_6dof": float(sums[2] / n_ok), "filters_finite": int(sums[3]), "filters_nonfinite": int(sums[4]),
+             "max_pos_err_m": float(mx.item()), "after_seconds_of_stream": (k_last + 1) * PERIOD,
+             "allreduce": "nccl" if world > 1 else "single rank"}
+
+    # ---- roofline of the dominant kernel (ekf_window_kernel) -------------------------------------------------------
+    flop_launch = B * (N * FLOP_IMU_STEP + W * FLOP_UPDATE)
+    bytes_launch = B * (N * 48.0 + W * 60.0 + 2.0 * (171 + 29) * 8.0 + 12.0)  # streams + state in/out + flags
+    avg_launch_s = float(np.mean(launch_ms)) * 1e-3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
+    except Exception:
+        pass
+    ach_tf = flop_launch / avg_launch_s / 1e12
+    roofline = {"kernel": "ekf_window_kernel<32>", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                "frac": ach_tf / (fp64_peak / 1e12),
+                "peak_source": "DFMA-saturating microbenchmark measured live on this GPU (fbus_measure_fp64_peak, burst); "
+                               "MEASURED_PEAKS.json has no FP64 entry; nominal 37.2 TFLOP/s",
+                "algorithmic_flop_per_launch": flop_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                "traffic": prof.get("ekf_window_dram_bytes_per_launch"),
+                "hbm": {"achieved": bytes_launch / avg_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bytes_launch / avg_launch_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": bytes_launch,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}}
+
+    # ---- refractive solves/sec (second half of the metric): K3+K4 on 524,288 markers per launch ---------------------
+    solves = bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak) if not args.no_solves else None
+
+    # ---- e2e: HOST buffers through the C ABI, H2D of every step's streams + D2H of the step's statistics -------------
+    e2e = bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq) if not args.no_e2e else None
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_baseline = cpu_arm(cfg, traj, target_seconds=12.0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(B, world), "e2e": e2e, "gpu_launches": K,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "stats": stats, "solves": solves,
+                "timing": "CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak):
+    import torch
+    from fbus_ekf_b200 import capi, synth
+    n_unique = 65536
+    rng = np.random.default_rng(99)
+    c = synth.random_marker_corners(cfg, n_unique, rng)
+    n = n_unique * 8  # BASELINE configs[3]: 65,536 filters x 8 markers per frame
+    reps = 32         # distinct corner sets so that successive launches stream new data (32 x 33.5 MB > L2)
+    base = torch.from_numpy(c).to(dev)
+    corners = torch.empty((reps, 16, n), dtype=torch.float32, device=dev)
+    for r in range(reps):
+        corners[r] = base.repeat(1, 8) + (1e-4 * (r + 1)) * torch.randn((16, n), device=dev, dtype=torch.float32)
+    pose = torch.empty((7, n), dtype=torch.float64, device=dev)
+    valid = torch.empty((n,), dtype=torch.int32, device=dev)
+    iters = max(K * 8, 16)
+    for i in range(max(Wm, 3)):
+        f.RefractSolveDevice(corners[i % reps].data_ptr(), n, pose.data_ptr(), None, valid.data_ptr())
+    f.Synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(iters):
+        f.RefractSolveDevice(corners[i % reps].data_ptr(), n, pose.data_ptr(), None, valid.data_ptr())
+    e1.record(stream)
+    f.Synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / iters
+    rate = n / sec
+    # e2e: pinned host corners in, poses + flags out
+    hc = torch.empty((16, n), dtype=torch.float32).pin_memory()
+    hc.copy_(corners[0].cpu())
+    hp = torch.empty((7, n), dtype=torch.float64).pin_memory()
+    hv = torch.empty((n,), dtype=torch.int32).pin_memory()
+    lib = capi.lib()
+
+    def host_call():
+        rc = lib.fbus_refract_solve(f._h, hc.data_ptr(), n, hp.data_ptr(), None, hv.data_ptr(), capi.FBUS_MEM_HOST)
+        assert rc == 0
+    for _ in range(3):
+        host_call()
+    t0 = time.perf_counter()
+    for _ in range(max(K, 4)):
+        host_call()
+    e2e_rate = n * max(K, 4) / (time.perf_counter() - t0)
+    return {"metric": "refractive solves/sec", "value": rate * world, "unit": "solves/s", "markers_per_launch": n,
+            "ms_per_launch": sec * 1e3, "valid_fraction": float(valid.float().mean().item()),
+            "e2e": {"value": e2e_rate * world, "unit": "solves/s", "h2d_bytes_per_step": 64 * n, "d2h_bytes_per_step": 60 * n},
+            "roofline": {"kernel": "refract_kernel", "bound": "fp64", "achieved": rate * FLOP_SOLVE / 1e12, "peak": fp64_peak / 1e12,
+                         "unit": "TFLOP/s", "frac": rate * FLOP_SOLVE / fp64_peak,
+                         "hbm": {"achieved": rate * BYTES_SOLVE / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": rate * BYTES_SOLVE / 1e9 / hbm_peak}}}
+
+
+def bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq):
+    """Same metric through the public API with HOST buffers: every step copies that step's per-filter streams from pinned
+    host memory to the device and reads the step's statistics vector back."""
+    import psutil
+    import torch
+    import torch.distributed as dist
+    from fbus_ekf_b200 import BatchFilter, capi
+    N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
+    per_filter = N * 48 + W * 60
+    local_world = env_int("LOCAL_WORLD_SIZE", world)
+    budget = 0.15 * psutil.virtual_memory().available / max(local_world, 1)
+    Be = B
+    while Be > 4096 and Be * per_filter > budget:
+        Be //= 2
+    Be = env_int("FBUS_BENCH_E2E_BATCH", Be)
+    f2 = BatchFilter(cfg, batch=Be, device=local)
+    h_imu = torch.empty((N, 6, Be), dtype=torch.float64).pin_memory()
+    h_id = torch.empty((W, 1, Be), dtype=torch.int32).pin_memory()
+    h_pose = torch.empty((W, 1, 7, Be), dtype=torch.float64).pin_memory()
+    h_imu.copy_(imu_d[:, :, :Be])
+    h_id.copy_(id_d[:, :, :Be])
+    h_pose.copy_(pose_d[:, :, :, :Be])
+    tpe, tqe = tp[:, :Be].contiguous(), tq[:, :Be].contiguous()
+    lib = capi.lib()
+    import ctypes as C
+    off = np.ascontiguousarray(traj["win_off"], dtype=np.uint32)
+
+    def step(k):
+        ti, tf = shifted(traj, k)
+        imu = capi.make_imu_stream(ti, h_imu.data_ptr(), Be, capi.FBUS_MEM_HOST)
+        det = capi.make_det_frames(tf, h_id.data_ptr(), h_pose.data_ptr(), Be, 1, capi.FBUS_MEM_HOST)
+        rc = lib.fbus_step_windows(f2._h, C.byref(imu), C.byref(det), capi.dptr(off, capi.c_uint32_p), 0, W, None, 0)
+        assert rc == 0
+        return f2.Stats(tpe.data_ptr(), tqe.data_ptr(), capi.FBUS_MEM_DEVICE)  # 64-byte D2H, synchronises
+
+    for k in range(max(Wm, 1)):
+        step(k)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(K):
+        last = step(Wm + k)
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt.item())
+    f2.close()
+    return {"value": world * Be * (N + W) * K / sec, "unit": UNIT, "h2d_bytes_per_step": int(Be * per_filter + (N + 2 * W + 1) * 8),
+            "d2h_bytes_per_step": 64, "filters_per_gpu": Be, "ms_per_step": 1e3 * sec / K,
+            "api": "fbus_step_windows(FBUS_MEM_HOST streams in pinned memory) + fbus_stats -> host",
+            "rmse_pos_m_last_step": float(np.sqrt(last[0] / max(last[3], 1.0)))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-solves", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -28,7 +28,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True)
+    except FileNotFoundError:
+        if os.path.exists(OUT):  # no nvcc on this machine: keep the prebuilt library that travelled with the repo
+            sys.stderr.write("fbus_ekf_b200.build: nvcc not found, using the prebuilt libfbus_ekf.so\n")
+            return OUT
+        raise
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)

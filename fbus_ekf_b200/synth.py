@@ -84,10 +84,12 @@ def stereo_extrinsics(cfg: capi.FbusConfig):
 
 
 def truth_trajectory(cfg: capi.FbusConfig, duration: float, imu_rate: float = 200.0, frame_rate: float = 25.0, marker_id: int = 0,
-                     seed: int = 20260117):
+                     seed: int = 20260117, periodic: bool = False):
     """Smooth trajectory matching the envelope of the reference's logs (position extent < 0.8 m, |v| < 0.4 m/s, a few
     hundredths rad/s of rotation) in front of marker `marker_id`.  Gravity convention of the filter after
-    InitializePose: g = (9.8, 0, 0) (filter.cpp:387), i.e. accel_body = R^T (p'' - g)."""
+    InitializePose: g = (9.8, 0, 0) (filter.cpp:387), i.e. accel_body = R^T (p'' - g).
+    periodic=True makes the motion exactly periodic in `duration` (all sinusoid frequencies are multiples of
+    1/duration), so a stream of one period can be replayed with timestamps advanced by k*duration."""
     rng = np.random.default_rng(seed)
     n_frames = int(round(duration * frame_rate))
     per = int(round(imu_rate / frame_rate))
@@ -103,6 +105,12 @@ def truth_trajectory(cfg: capi.FbusConfig, duration: float, imu_rate: float = 20
     fr = rng.uniform(0.05, 0.35, size=(nf, 3))
     ar = rng.uniform(0.01, 0.03, size=(nf, 3))
     phr = rng.uniform(0, 2 * np.pi, size=(nf, 3))
+    if periodic:
+        harm = np.array([1.0, 1.0, 2.0, 3.0])[:, None] / duration
+        fp = np.repeat(harm, 3, axis=1)
+        fr = np.repeat(harm, 3, axis=1)
+        ap = ap * 0.25 / (harm * duration)
+        ar = ar * 0.5 / (harm * duration)
     p0 = np.array([-0.10, 0.05, 0.50])
     q0 = np.array([-0.0203, -0.7053, 0.7086, -0.0065])
     q0 /= np.linalg.norm(q0)
