@@ -23,6 +23,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+def build_variant(win_bs: int, suffix: str) -> str:
+    """experiment builds: libfbus_ekf_<suffix>.so with a different CTA size for the window kernel"""
+    out = os.path.join(HERE, f"libfbus_ekf_{suffix}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + [f"-DFBUS_WIN_BS={win_bs}", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT

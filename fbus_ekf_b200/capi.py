@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfbus_ekf.so")
+LIB_PATH = os.environ.get("FBUS_EKF_LIB", os.path.join(HERE, "libfbus_ekf.so"))
 
 FBUS_MEM_HOST = 0
 FBUS_MEM_DEVICE = 1

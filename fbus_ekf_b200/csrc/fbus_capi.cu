@@ -18,7 +18,10 @@ using namespace fbus;
 
 namespace {
 
-constexpr int WIN_BS = 32;  // filters per CTA of the window kernel (one warp; 171*32*8 B = 42.75 KB smem)
+#ifndef FBUS_WIN_BS
+#define FBUS_WIN_BS 64
+#endif
+constexpr int WIN_BS = FBUS_WIN_BS;  // filters per CTA of the window kernel (171*WIN_BS*8 B of shared memory)
 
 thread_local std::string g_last_error;
 

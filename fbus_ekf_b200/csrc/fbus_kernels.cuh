@@ -56,8 +56,14 @@ template <int BS>
 __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
     extern __shared__ double smem[];
     const size_t B = prm.B;
-    const size_t b = (size_t)blockIdx.x * BS + threadIdx.x;
-    if (b >= B) return;
+    // CTAs larger than one warp keep their warps in step with __syncthreads (one barrier per IMU sample): the
+    // warps then run the same ~30 KB instruction stream at the same time and share its instruction-cache lines.
+    // Threads past the end of the batch therefore stay alive (they mirror the last filter) but never store.
+    constexpr bool SYNC = BS > 32;
+    __shared__ uint32_t sred[2][(BS + 31) / 32];
+    const size_t b0 = (size_t)blockIdx.x * BS + threadIdx.x;
+    const bool live = b0 < B;
+    const size_t b = live ? b0 : B - 1;
     const Cov<BS> P{smem + threadIdx.x};
 
     // ---- load state --------------------------------------------------------------------------
@@ -194,10 +200,12 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
                 double qv[4], Rv[9], pv[3];
                 const MarkerConst mkc = prm.tab->mk[mk];
                 vision_pose(k, mkc, dp, dq, qv, Rv, pv);
+                if (live) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) prm.nom[(size_t)(F_PV + i) * B + b] = pv[i];
+                    for (int i = 0; i < 3; ++i) prm.nom[(size_t)(F_PV + i) * B + b] = pv[i];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_QV + i) * B + b] = qv[i];
+                    for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_QV + i) * B + b] = qv[i];
+                }
                 if (t_det - n.t > k.reset_gap && inited) {
                     n.t = t_det;
 #pragma unroll
@@ -211,38 +219,59 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
             }
         }
         // ---- F3 BatchImuProcessing (filter.cpp:483-531): F1 then F2 per sample ------------------
-        if (do_prop) {
-            const double start = n.t;
-            uint32_t i = p_first;
-            double s_t = 0.0, s_d[6];
-            if (i < p_end) {
-                s_t = prm.imu_t[i];
+        if (SYNC ? (__syncthreads_or(do_prop ? 1 : 0) != 0) : do_prop) {
+            // block-uniform candidate range [lo, hi) so that the per-sample barrier is reached by every thread
+            uint32_t lo = p_first, hi = p_end;
+            if (SYNC) {
+                const uint32_t vlo = __reduce_min_sync(0xffffffffu, do_prop ? p_first : 0xffffffffu);
+                const uint32_t vhi = __reduce_max_sync(0xffffffffu, do_prop ? p_end : 0u);
+                if ((threadIdx.x & 31) == 0) { sred[0][threadIdx.x >> 5] = vlo; sred[1][threadIdx.x >> 5] = vhi; }
+                __syncthreads();
+                lo = sred[0][0]; hi = sred[1][0];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)i * 6 + c) * B + b];
+                for (int q = 1; q < (BS + 31) / 32; ++q) { lo = min(lo, sred[0][q]); hi = max(hi, sred[1][q]); }
+                __syncthreads();
             }
-            while (i < p_end) {
+            const double start = n.t;
+            bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
+            uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
+            double s_t = 0.0, s_d[6];
+            if (lo < hi) {
+                s_t = prm.imu_t[lo];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)lo * 6 + c) * B + b];
+            }
+            for (uint32_t i = lo; i < hi; ++i) {
+                if (SYNC) __syncthreads();
                 const double ti = s_t;
                 double d[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) d[c] = s_d[c];
-                if (i + 1 < p_end) {  // prefetch the next sample while this one is processed
+                if (i + 1 < hi) {  // prefetch the next sample while this one is processed
                     s_t = prm.imu_t[i + 1];
 #pragma unroll
                     for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)(i + 1) * 6 + c) * B + b];
                 }
-                ++i;
-                if (ti < start) continue;
-                if (ti > t_end) { --i; break; }  // this sample stays buffered
-                const double dt = ti - n.t;
-                double wv[3], av[3];
+                if (open && i >= p_first && i < p_end) {
+                    if (ti < start) {
+                        consumed = i + 1;
+                    } else if (ti > t_end) {
+                        open = false;  // this sample stays buffered
+                    } else {
+                        consumed = i + 1;
+                        const double dt = ti - n.t;
+                        double wv[3], av[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
-                propagate_cov<BS>(P, n.R, av, wv, dt, k.Qd);  // uses the CARRIED rotmatI2G (A.3-2,3)
-                propagate_nominal(n, dt, d, d + 3);
-                n.t = ti;
+                        for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
+                        propagate_cov<BS>(P, n.R, av, wv, dt, k.Qd);  // uses the CARRIED rotmatI2G (A.3-2,3)
+                        propagate_nominal(n, dt, d, d + 3);
+                        n.t = ti;
+                    }
+                }
             }
-            if (fused) cursor = i;  // consumed (processed or skipped) samples erased (filter.cpp:520)
+            if (fused && do_prop) cursor = consumed;
         }
+        if (SYNC) __syncthreads();
         // ---- F4 ObservationUpdate (filter.cpp:622-739) -----------------------------------------
         if (do_update && n_det > 0) {
             load_det(idx_upd);
@@ -256,7 +285,7 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
             }
         }
         // ---- trace row: the data/fusion.txt record (filter.cpp:241-246) -------------------------
-        if (prm.trace) {
+        if (prm.trace && live) {
             double* row = prm.trace + (size_t)(w - prm.w0) * 17 * B + b;
             row[0] = n.t;
 #pragma unroll
@@ -281,6 +310,7 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
         for (int i = 0; i < 3; ++i) fin = fin && isfinite(n.p[i]) && isfinite(n.v[i]);
         if (!fin) status |= FBUS_ST_NONFINITE;
     }
+    if (!live) return;
     for (int e = 0; e < NPK; ++e) prm.P[(size_t)e * B + b] = smem[e * BS + threadIdx.x];
     prm.nom[(size_t)F_T * B + b] = n.t;
 #pragma unroll

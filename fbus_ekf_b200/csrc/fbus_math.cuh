@@ -490,9 +490,11 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
     if (wn > 10e-5) {
         const double inv = 1.0 / wn;
         const double ax[3] = {w[0] * inv, w[1] * inv, w[2] * inv};
-        double sh, ch, sf, cf;
+        // one sincos: the half-interval quaternion needs angle/2 = wn*dt/4, the full one twice that
+        // (double-angle identities; ~1 ulp from evaluating sin/cos of wn*dt/2 directly)
+        double sh, ch;
         sincos(wn * dt / 2 / 2, &sh, &ch);
-        sincos(wn * dt / 2, &sf, &cf);
+        const double sf = 2.0 * sh * ch, cf = 1.0 - 2.0 * sh * sh;
         const double dqh[4] = {ch, sh * ax[0], sh * ax[1], sh * ax[2]};
         const double dq[4] = {cf, sf * ax[0], sf * ax[1], sf * ax[2]};
         qmul(n.q, dqh, qh);
