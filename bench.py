@@ -267,16 +267,10 @@ def run_ours(args):
     st_d = torch.zeros(capi.FBUS_NSTATS, dtype=torch.float64, device=dev)
     f.Stats(tp.data_ptr(), tq.data_ptr(), capi.FBUS_MEM_DEVICE, out_dev_ptr=st_d.data_ptr(), want_host=False)
     f.Synchronize()
-    sums, mx = st_d[:5].clone(), st_d[5:6].clone()
-    if world > 1:
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    sums = sums.cpu().numpy()
-    n_ok = max(sums[3], 1.0)
-    stats = {"rmse_pos_m": float(np.sqrt(sums[0] / n_ok)), "rmse_att_rad": float(np.sqrt(sums[1] / n_ok)),
-             "nees_pose_mean_6dof": float(sums[2] / n_ok), "filters_finite": int(sums[3]), "filters_nonfinite": int(sums[4]),
-             "max_pos_err_m": float(mx.item()), "after_seconds_of_stream": (k_last + 1) * PERIOD,
-             "allreduce": "nccl" if world > 1 else "single rank"}
+    from fbus_ekf_b200 import shard
+    shard.combine_stats(st_d, dist if world > 1 else None)  # SUM of the sums, MAX of the maximum
+    stats = shard.summarize_stats(st_d.cpu().numpy())
+    stats.update({"after_seconds_of_stream": (k_last + 1) * PERIOD, "allreduce": "nccl" if world > 1 else "single rank"})
 
     # ---- roofline of the dominant kernel (ekf_window_kernel) -------------------------------------------------------
     flop_launch = B * (N * FLOP_IMU_STEP + W * FLOP_UPDATE)
