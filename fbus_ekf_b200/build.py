@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfbus_ekf.so")
 SOURCES = ["fbus_capi.cu"]
-DEPS = ["fbus_capi.cu", "fbus_kernels.cuh", "fbus_math.cuh", "fbus_refract.cuh", "fbus_host_consts.hpp",
+DEPS = ["fbus_capi.cu", "fbus_kernels.cuh", "fbus_kernel_split.cuh", "fbus_math.cuh", "fbus_refract.cuh", "fbus_host_consts.hpp",
         os.path.join("..", "..", "include", "fbus_ekf.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-cudart", "static"]
@@ -23,15 +23,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build_variant(win_bs: int, suffix: str) -> str:
-    """experiment builds: libfbus_ekf_<suffix>.so with a different CTA size for the window kernel"""
+def build_variant(win_bs: int, suffix: str, extra=()) -> str:
+    """experiment builds: libfbus_ekf_<suffix>.so with a different CTA size / macros for the window kernel"""
     out = os.path.join(HERE, f"libfbus_ekf_{suffix}.so")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [f"-DFBUS_WIN_BS={win_bs}", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + [f"-DFBUS_WIN_BS={win_bs}"] + list(extra) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed")
+    for line in (res.stdout + res.stderr).splitlines():
+        if "ekf_window" in line or ("spill" in line and "3" in line[:0]):
+            pass
+    import re
+    m = re.search(r"ekf_window_\w*kernel.*?\n.*?\n\s*(\d+ bytes stack frame, \d+ bytes spill stores, \d+ bytes spill loads)", res.stdout + res.stderr, re.S)
+    print(suffix, m.group(1) if m else "")
     return out
 
 

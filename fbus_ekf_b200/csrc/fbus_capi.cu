@@ -13,15 +13,26 @@
 #include "../../include/fbus_ekf.h"
 #include "fbus_host_consts.hpp"
 #include "fbus_kernels.cuh"
+#include "fbus_kernel_split.cuh"
 
 using namespace fbus;
 
 namespace {
 
 #ifndef FBUS_WIN_BS
-#define FBUS_WIN_BS 64
+#define FBUS_WIN_BS 128
 #endif
 constexpr int WIN_BS = FBUS_WIN_BS;  // filters per CTA of the window kernel (171*WIN_BS*8 B of shared memory)
+// 1 (default): warp-specialised window kernel, 2*WIN_BS threads per CTA (covariance warps + nominal warps);
+// 0: one thread per filter does everything (kept for A/B measurements)
+#ifndef FBUS_SPLIT
+#define FBUS_SPLIT 1
+#endif
+#if FBUS_SPLIT
+constexpr size_t WIN_SMEM = (size_t)(NPK + XCH) * WIN_BS * sizeof(double);
+#else
+constexpr size_t WIN_SMEM = (size_t)NPK * WIN_BS * sizeof(double);
+#endif
 
 thread_local std::string g_last_error;
 
@@ -98,9 +109,12 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.status = h->d_status;
     prm.B = h->B;
     prm.tab = h->d_tab;
-    const size_t smem = (size_t)NPK * WIN_BS * sizeof(double);
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
-    ekf_window_kernel<WIN_BS><<<grid, WIN_BS, smem, h->stream>>>(prm, h->k);
+#if FBUS_SPLIT
+    ekf_window_split_kernel<WIN_BS><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
+#else
+    ekf_window_kernel<WIN_BS><<<grid, WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
+#endif
     CUDA_TRY(h, cudaGetLastError());
     return FBUS_OK;
 }
@@ -174,9 +188,12 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     if ((e = cudaMalloc(&h->d_status, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc status", e);
     if ((e = cudaMalloc(&h->d_tab, sizeof(MarkerTable))) != cudaSuccess) return bail("cudaMalloc marker table", e);
     if ((e = cudaMemcpy(h->d_tab, &h->tab, sizeof(MarkerTable), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("marker table copy", e);
-    if ((e = cudaFuncSetAttribute(ekf_window_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(NPK * WIN_BS * sizeof(double)))) != cudaSuccess)
-        return bail("cudaFuncSetAttribute", e);
+#if FBUS_SPLIT
+    e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+#else
+    e = cudaFuncSetAttribute(ekf_window_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+#endif
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute", e);
     const unsigned grid = (unsigned)((batch + 127) / 128);
     ctor_kernel<<<grid, 128, 0, h->stream>>>(h->d_nom, h->d_P, h->d_prev, h->d_init, h->d_status, batch, cfg->p0_diag[0],
                                              cfg->p0_diag[1], cfg->p0_diag[2], cfg->p0_diag[3], cfg->p0_diag[4], cfg->p0_diag[5]);

@@ -1,0 +1,432 @@
+// fbus_kernel_split.cuh -- K12, warp-specialised: the fused window kernel with TWO warps per 32 filters.
+//
+// Why: the packed covariance (171 doubles = 1368 B per filter) caps residency at ~128-160 filters per SM, i.e. one
+// warp per scheduler with one thread per filter.  A lone warp cannot overlap its shared-memory traffic, integer work
+// and the serial sin/cos/sqrt/div chains of the nominal-state integration with the half-rate FP64 pipe (ncu: FP64 pipe
+// ~33 % busy, "wait"/"short scoreboard" stalls, 1.0 warp per scheduler).  Here every group of 32 filters gets
+//   * a COVARIANCE warp: F1 (P <- F P F^T + Q) and the measurement update's covariance work, P in shared memory;
+//   * a NOMINAL warp:    detection scan, F6b init, F5 reset, F2 nominal integration (q,p,v + the carried rotmatI2G),
+//                        the IMU/detection streams, and the error-state injection after an update.
+// so each scheduler holds two warps with complementary instruction mixes.  The nominal warp runs one IMU sample AHEAD
+// and hands the covariance warp the coefficients of F for that sample (A = -R[a]x dt, B = -R dt, w dt, dt: 22 doubles)
+// through a 2-deep ring in shared memory; one __syncthreads per sample orders the ring and also keeps all warps of the
+// CTA on the same instruction-cache lines.  For an update the nominal warp posts (marker, y, q, R, p), the covariance
+// warp runs measurement_update and posts back the injected pose / state increments.
+//
+// Numerically identical to ekf_window_kernel (same device functions, same order of operations per filter).
+#pragma once
+
+#include "fbus_kernels.cuh"
+
+// 1 (default): the covariance warp keeps the top-left 9x9 block of P in registers while it propagates a window
+#ifndef FBUS_TL_REGS
+#define FBUS_TL_REGS 1
+#endif
+
+namespace fbus {
+
+constexpr int XCH = 44;  // doubles of exchange area per filter: ring 2 x 22, reused for the update hand-off (23 in, 19 out)
+
+// CTA-wide named barrier used by both roles (the two roles run different code, so the barrier is issued from
+// different program counters; whole warps take each path, and arrivals are counted per barrier id)
+template <int NT>
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
+struct SplitShared {
+    uint32_t lo_hi[2][8];   // per nominal warp: min first / max end of the candidate IMU range
+    int32_t any_upd[8];     // per nominal warp: some filter requests an update
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// COVARIANCE role: owns P (shared memory; top-left 9x9 in registers while propagating)
+// ------------------------------------------------------------------------------------------------------------------
+template <int BSF>
+__device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh, int32_t (*sflag)[BSF],
+                                         int fl, size_t b, bool live) {
+    constexpr int NT = 2 * BSF, NW = BSF / 32;
+    const size_t B = prm.B;
+    const Cov<BSF> P{smem + fl};
+    double* const X = smem + (size_t)NPK * BSF + fl;
+    for (int e = 0; e < NPK; ++e) smem[e * BSF + fl] = prm.P[(size_t)e * B + b];
+    for (uint32_t w = prm.w0; w < prm.w1; ++w) {
+        cta_bar<NT>();  // (a) the nominal warps have posted their IMU ranges
+        uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
+        if (lo < hi) {
+#if FBUS_TL_REGS
+            double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
+            tl_load<BSF>(P, TL);
+#endif
+            for (uint32_t i = lo; i < hi; ++i) {
+                cta_bar<NT>();  // record (i) is complete; the nominal warp moves on to sample i+1
+                const int slot = (int)((i - lo) & 1u);
+                if (sflag[slot][fl]) {
+                    const double* rec = X + (size_t)slot * 22 * BSF;
+                    double A[9], Bm[9];
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * BSF]; Bm[e] = rec[(size_t)(9 + e) * BSF]; }
+                    const double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
+                    const double dt = rec[(size_t)21 * BSF];
+#if FBUS_TL_REGS
+                    propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, k.Qd, nullptr, TL);
+#else
+                    propagate_cov_core<BSF>(P, A, Bm, u0, u1, u2, dt, k.Qd);
+#endif
+                }
+            }
+#if FBUS_TL_REGS
+            tl_store<BSF>(P, TL);
+#endif
+        }
+        cta_bar<NT>();  // (b) ring consumed: the exchange area is free for the update hand-off
+        cta_bar<NT>();  // (c) update requests posted
+        int any = sh.any_upd[0];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) any |= sh.any_upd[q];
+        if (any) {
+            const int req = sflag[2][fl];
+            if (req) {
+                Nominal t;
+                double yP[3], yQ[4];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) yP[c] = X[(size_t)c * BSF];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { yQ[c] = X[(size_t)(3 + c) * BSF]; t.q[c] = X[(size_t)(7 + c) * BSF]; }
+#pragma unroll
+                for (int c = 0; c < 9; ++c) t.R[c] = X[(size_t)(11 + c) * BSF];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { t.p[c] = X[(size_t)(20 + c) * BSF]; t.v[c] = 0.0; t.ba[c] = 0.0; t.bg[c] = 0.0; t.g[c] = 0.0; }
+                t.t = 0.0;
+                const MarkerConst mkc = prm.tab->mk[req - 1];
+                measurement_update<BSF>(P, t, k, mkc, yP, yQ);
+                // hand back: corrected p, q and the increments of v, b_a, b_g, g
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    X[(size_t)(23 + c) * BSF] = t.p[c];
+                    X[(size_t)(30 + c) * BSF] = t.v[c];
+                    X[(size_t)(33 + c) * BSF] = t.ba[c];
+                    X[(size_t)(36 + c) * BSF] = t.bg[c];
+                    X[(size_t)(39 + c) * BSF] = t.g[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) X[(size_t)(26 + c) * BSF] = t.q[c];
+            }
+            cta_bar<NT>();  // (d) results posted
+            cta_bar<NT>();  // (e) results consumed: the exchange area may be overwritten by the next frame's ring
+        }
+    }
+    if (live)
+        for (int e = 0; e < NPK; ++e) prm.P[(size_t)e * B + b] = smem[e * BSF + fl];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// NOMINAL role: owns the nominal state (registers), the streams, and all per-frame decisions
+// ------------------------------------------------------------------------------------------------------------------
+template <int BSF>
+__device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
+                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
+    constexpr int NT = 2 * BSF, NW = BSF / 32;
+    const size_t B = prm.B;
+    double* const X = smem + (size_t)NPK * BSF + fl;
+    const int mode = prm.mode;
+    const bool fused = (mode & M_FUSED) != 0;
+    const int wq = fl >> 5;  // nominal warp index
+    Nominal n;
+    n.t = prm.nom[(size_t)F_T * B + b];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) n.q[i] = prm.nom[(size_t)(F_Q + i) * B + b];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) n.R[i] = prm.nom[(size_t)(F_R + i) * B + b];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        n.p[i] = prm.nom[(size_t)(F_P + i) * B + b];
+        n.v[i] = prm.nom[(size_t)(F_V + i) * B + b];
+        n.ba[i] = prm.nom[(size_t)(F_BA + i) * B + b];
+        n.bg[i] = prm.nom[(size_t)(F_BG + i) * B + b];
+        n.g[i] = prm.nom[(size_t)(F_G + i) * B + b];
+    }
+    int prev_id = prm.prev_id[b];
+    int inited = prm.init[b];
+    int status = prm.status[b];
+    uint32_t cursor = fused ? prm.win_off[prm.w0] : 0u;
+
+    for (uint32_t w = prm.w0; w < prm.w1; ++w) {
+        bool do_prop = false, do_update = false;
+        uint32_t p_first = 0, p_end = 0;
+        double t_end = 0.0;
+        int n_det = 0, idx_upd = 0;
+        double t_det = 0.0;
+        {
+            // ---- scan this frame's detections (filter.cpp:329-341 / 418-430 / 639-658) ----------------
+            int idx_near = 0, idx_prev = 0;
+            double md = 10.0, prev_dist = 0.0;
+            const bool uses_det = (mode & (M_INIT | M_RESET | M_UPDATE | M_FUSED)) != 0;
+            if (uses_det) {
+                t_det = prm.det_t[w];
+                for (int s = 0; s < prm.m; ++s) {
+                    const size_t slot = (size_t)w * prm.m + s;
+                    const int id = prm.det_id[slot * B + b];
+                    if (id < 0) continue;
+                    const double* pp = prm.det_pose + slot * 7 * B + b;
+                    const double px = pp[0], py = pp[B], pz = pp[2 * B];
+                    const double dist = sqrt(px * px + py * py + pz * pz);
+                    if (n_det == 0) { idx_near = s; idx_prev = s; }  // detectionResult_[0] defaults (min_dist_id = 0)
+                    if (dist < md) { md = dist; idx_near = s; }
+                    if (id == prev_id) { prev_dist = dist; idx_prev = s; }
+                    ++n_det;
+                }
+            }
+            idx_upd = idx_near;  // nearest, or the previously used marker within the switch threshold (filter.cpp:660-664)
+            {
+                const double dd = prev_dist - md;
+                if ((dd < 0 ? -dd : dd) < k.switch_thres && prev_dist != 0) idx_upd = idx_prev;
+            }
+            bool do_init = false, do_reset = false;
+            uint32_t n_before = prm.n_imu_before;
+            if (fused) {
+                if (n_det == 0) {
+                    status |= FBUS_ST_NO_DETECTION;  // filter thread not woken (vision.cpp:136-140)
+                } else if (!inited) {
+                    do_init = true;
+                    n_before = 0;
+                    const uint32_t hi = prm.win_off[w + 1];
+                    for (uint32_t i = cursor; i < hi; ++i) n_before += (prm.imu_t[i] <= t_det) ? 1u : 0u;
+                } else {
+                    do_reset = do_prop = do_update = true;
+                    p_first = cursor;
+                    p_end = prm.win_off[w + 1];
+                    t_end = t_det;
+                }
+            } else {
+                do_init = (mode & M_INIT) != 0;
+                do_reset = (mode & M_RESET) != 0;
+                do_update = (mode & M_UPDATE) != 0;
+                if (mode & M_PROP) {
+                    do_prop = true;
+                    p_first = prm.prop_first;
+                    p_end = prm.prop_first + prm.prop_count;
+                    t_end = prm.prop_t_end;
+                }
+                if ((mode & M_UPDATE) && n_det == 0) status |= FBUS_ST_NO_DETECTION;
+            }
+            // ---- F6b InitializePose (filter.cpp:291-399) / F5 ResetSystemState (filter.cpp:405-477) -------
+            if ((do_init || do_reset) && n_det > 0) {
+                bool ok = !(md > k.max_dist);
+                if (do_init) ok = ok && (n_before > 0);
+                int mk = -1;
+                double dp[3], dq[4];
+                if (ok) {
+                    const size_t slot = (size_t)w * prm.m + idx_near;
+                    const int did = prm.det_id[slot * B + b];
+                    const double* pp = prm.det_pose + slot * 7 * B + b;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) dp[c] = pp[(size_t)c * B];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dq[c] = pp[(size_t)(3 + c) * B];
+                    mk = find_marker(k, prm.tab, did);
+                    ok = mk >= 0;
+                }
+                if (ok) {
+                    double qv[4], Rv[9], pv[3];
+                    const MarkerConst mkc = prm.tab->mk[mk];
+                    vision_pose(k, mkc, dp, dq, qv, Rv, pv);
+                    if (do_init) {
+                        n.t = t_det;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) n.q[i] = qv[i];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) n.R[i] = Rv[i];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) n.p[i] = pv[i];
+                        n.g[0] = 9.8; n.g[1] = 0.0; n.g[2] = 0.0;  // filter.cpp:387
+                        inited = 1;
+                        if (fused) cursor = prm.win_off[w + 1];  // consumed IMU samples erased (filter.cpp:390)
+                    }
+                    if (do_reset) {
+                        if (live) {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) prm.nom[(size_t)(F_PV + i) * B + b] = pv[i];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_QV + i) * B + b] = qv[i];
+                        }
+                        if (t_det - n.t > k.reset_gap && inited) {
+                            n.t = t_det;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) n.q[i] = qv[i];
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) { n.p[i] = pv[i]; n.v[i] = 0.0; n.ba[i] = 0.0; n.bg[i] = 0.0; }
+                            status |= FBUS_ST_RESET_DONE;  // P, g and the carried R stay untouched
+                        }
+                    }
+                } else {
+                    if (do_init) status |= FBUS_ST_INIT_FAILED;
+                    if (do_reset) status |= FBUS_ST_RESET_SKIPPED;
+                }
+            } else if (do_init) {
+                status |= FBUS_ST_INIT_FAILED;
+            }
+        }
+
+        // ---- F3 BatchImuProcessing (filter.cpp:483-531): one sample ahead of the covariance warp -------------
+        {
+            const uint32_t vlo = __reduce_min_sync(0xffffffffu, do_prop ? p_first : 0xffffffffu);
+            const uint32_t vhi = __reduce_max_sync(0xffffffffu, do_prop ? p_end : 0u);
+            if ((fl & 31) == 0) { sh.lo_hi[0][wq] = vlo; sh.lo_hi[1][wq] = vhi; }
+        }
+        cta_bar<NT>();  // (a)
+        uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
+        if (lo < hi) {
+            const double start = n.t;
+            bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
+            uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
+            double s_t = prm.imu_t[lo], s_d[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)lo * 6 + c) * B + b];
+            for (uint32_t i = lo; i < hi; ++i) {
+                const double ti = s_t;
+                double d[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) d[c] = s_d[c];
+                if (i + 1 < hi) {  // prefetch the next sample
+                    s_t = prm.imu_t[i + 1];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)(i + 1) * 6 + c) * B + b];
+                }
+                const int slot = (int)((i - lo) & 1u);
+                int valid = 0;
+                if (open && i >= p_first && i < p_end) {
+                    if (ti < start) {
+                        consumed = i + 1;
+                    } else if (ti > t_end) {
+                        open = false;  // this sample stays buffered
+                    } else {
+                        consumed = i + 1;
+                        valid = 1;
+                        const double dt = ti - n.t;
+                        double wv[3], av[3], A[9], Bm[9], u[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
+                        cov_coeffs(n.R, av, wv, dt, A, Bm, u);  // F1 uses the CARRIED rotmatI2G (A.3-2,3)
+                        double* rec = X + (size_t)slot * 22 * BSF;
+#pragma unroll
+                        for (int e = 0; e < 9; ++e) { rec[(size_t)e * BSF] = A[e]; rec[(size_t)(9 + e) * BSF] = Bm[e]; }
+                        rec[(size_t)18 * BSF] = u[0]; rec[(size_t)19 * BSF] = u[1]; rec[(size_t)20 * BSF] = u[2];
+                        rec[(size_t)21 * BSF] = dt;
+                        propagate_nominal(n, dt, d, d + 3);  // F2 after F1's coefficients were taken (filter.cpp:509-513)
+                        n.t = ti;
+                    }
+                }
+                sflag[slot][fl] = valid;
+                cta_bar<NT>();  // publish record (i); also: the covariance warp has finished sample i-1
+            }
+            if (fused && do_prop) cursor = consumed;
+        }
+        cta_bar<NT>();  // (b) the covariance warp is done with the ring
+
+        // ---- F4 ObservationUpdate (filter.cpp:622-739): post the request, the covariance warp does the algebra ----
+        int req = 0;
+        if (do_update && n_det > 0) {
+            const size_t slot = (size_t)w * prm.m + idx_upd;
+            const int did = prm.det_id[slot * B + b];
+            const int mk = find_marker(k, prm.tab, did);
+            if (mk >= 0) {
+                prev_id = did;
+                req = mk + 1;
+                const double* pp = prm.det_pose + slot * 7 * B + b;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) X[(size_t)c * BSF] = pp[(size_t)c * B];  // yP (3), yQ (4)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) X[(size_t)(7 + c) * BSF] = n.q[c];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) X[(size_t)(11 + c) * BSF] = n.R[c];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) X[(size_t)(20 + c) * BSF] = n.p[c];
+            } else {
+                status |= FBUS_ST_UPDATE_SKIPPED;
+            }
+        }
+        sflag[2][fl] = req;
+        {
+            const int wany = __any_sync(0xffffffffu, req != 0);
+            if ((fl & 31) == 0) sh.any_upd[wq] = wany;
+        }
+        cta_bar<NT>();  // (c)
+        int any = sh.any_upd[0];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) any |= sh.any_upd[q];
+        if (any) {
+            cta_bar<NT>();  // (d) results posted
+            if (req) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    n.p[c] = X[(size_t)(23 + c) * BSF];
+                    n.v[c] += X[(size_t)(30 + c) * BSF];
+                    n.ba[c] += X[(size_t)(33 + c) * BSF];
+                    n.bg[c] += X[(size_t)(36 + c) * BSF];
+                    n.g[c] += X[(size_t)(39 + c) * BSF];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(26 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
+            }
+            cta_bar<NT>();  // (e)
+        }
+        // ---- trace row: the data/fusion.txt record (filter.cpp:241-246) -------------------------
+        if (prm.trace && live) {
+            double* row = prm.trace + (size_t)(w - prm.w0) * 17 * B + b;
+            row[0] = n.t;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) row[(size_t)(1 + c) * B] = n.p[c];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) row[(size_t)(4 + c) * B] = n.q[c];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                row[(size_t)(8 + c) * B] = n.v[c];
+                row[(size_t)(11 + c) * B] = n.ba[c];
+                row[(size_t)(14 + c) * B] = n.bg[c];
+            }
+        }
+    }
+    if (!live) return;
+    bool fin = isfinite(n.t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fin = fin && isfinite(n.q[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fin = fin && isfinite(n.p[i]) && isfinite(n.v[i]);
+    if (!fin) status |= FBUS_ST_NONFINITE;
+    prm.nom[(size_t)F_T * B + b] = n.t;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_Q + i) * B + b] = n.q[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) prm.nom[(size_t)(F_R + i) * B + b] = n.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        prm.nom[(size_t)(F_P + i) * B + b] = n.p[i];
+        prm.nom[(size_t)(F_V + i) * B + b] = n.v[i];
+        prm.nom[(size_t)(F_BA + i) * B + b] = n.ba[i];
+        prm.nom[(size_t)(F_BG + i) * B + b] = n.bg[i];
+        prm.nom[(size_t)(F_G + i) * B + b] = n.g[i];
+    }
+    prm.prev_id[b] = prev_id;
+    prm.init[b] = inited;
+    prm.status[b] = status;
+}
+
+template <int BSF>  // filters per CTA; the CTA has 2*BSF threads: warps [0, BSF/32) covariance, [BSF/32, 2*BSF/32) nominal
+__global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
+    extern __shared__ double smem[];
+    __shared__ SplitShared sh;
+    __shared__ int32_t sflag[3][BSF];  // [0],[1]: ring slot valid ; [2]: update requested (marker index + 1, 0 = none)
+    static_assert(BSF % 32 == 0 && BSF / 32 <= 8, "BSF must be a multiple of the warp size, at most 256");
+    const bool is_cov = threadIdx.x < BSF;
+    const int fl = is_cov ? threadIdx.x : threadIdx.x - BSF;  // filter lane inside the CTA
+    const size_t b0 = (size_t)blockIdx.x * BSF + fl;
+    const bool live = b0 < prm.B;
+    const size_t b = live ? b0 : prm.B - 1;  // threads past the batch mirror the last filter and never store
+    if (is_cov) cov_role<BSF>(prm, k, smem, sh, sflag, fl, b, live);
+    else nominal_role<BSF>(prm, k, smem, sh, sflag, fl, b, live);
+}
+
+}  // namespace fbus

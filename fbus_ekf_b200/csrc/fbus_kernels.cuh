@@ -20,6 +20,11 @@
 #include "fbus_math.cuh"
 #include "fbus_refract.cuh"
 
+// 1 = keep the bottom-right 9x9 covariance block in registers while a window's IMU samples are propagated
+#ifndef FBUS_BR_REGS
+#define FBUS_BR_REGS 0
+#endif
+
 namespace fbus {
 
 constexpr int NOM_FIELDS = 36;  // t q4 R9 p3 v3 ba3 bg3 g3 pv3 qv4
@@ -232,6 +237,10 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
                 for (int q = 1; q < (BS + 31) / 32; ++q) { lo = min(lo, sred[0][q]); hi = max(hi, sred[1][q]); }
                 __syncthreads();
             }
+#if FBUS_BR_REGS
+            double BR[NBR];
+            br_load<BS>(P, BR);
+#endif
             const double start = n.t;
             bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
             uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
@@ -263,13 +272,20 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
                         double wv[3], av[3];
 #pragma unroll
                         for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
+#if FBUS_BR_REGS
+                        propagate_cov<BS, true>(P, n.R, av, wv, dt, k.Qd, BR);  // uses the CARRIED rotmatI2G (A.3-2,3)
+#else
                         propagate_cov<BS>(P, n.R, av, wv, dt, k.Qd);  // uses the CARRIED rotmatI2G (A.3-2,3)
+#endif
                         propagate_nominal(n, dt, d, d + 3);
                         n.t = ti;
                     }
                 }
             }
             if (fused && do_prop) cursor = consumed;
+#if FBUS_BR_REGS
+            br_store_diag<BS>(P, BR);
+#endif
         }
         if (SYNC) __syncthreads();
         // ---- F4 ObservationUpdate (filter.cpp:622-739) -----------------------------------------

@@ -33,6 +33,21 @@
 #define FBUS_UNROLL
 #endif
 
+// scheduling fences inside propagate_cov: level 2 = between every stage, 1 = between phases only, 0 = none
+#ifndef FBUS_COV_FENCES
+#define FBUS_COV_FENCES 2
+#endif
+#if FBUS_COV_FENCES >= 2
+#define FBUS_FENCE_A FBUS_FENCE
+#else
+#define FBUS_FENCE_A ((void)0)
+#endif
+#if FBUS_COV_FENCES >= 1
+#define FBUS_FENCE_B FBUS_FENCE
+#else
+#define FBUS_FENCE_B ((void)0)
+#endif
+
 namespace fbus {
 
 constexpr int NX = 18;
@@ -193,27 +208,90 @@ struct Cov {
 // Evaluation: (1) top-left 3x3 blocks from OLD values, (2) block columns 4,3,5 of rows 0..2, folding
 // their contribution into the top-left accumulators.  ~650 FMA instead of the 2*18^3 dense product.
 // ------------------------------------------------------------------------------------------------
+// packed index inside the bottom-right 9x9 (rows/cols 9..17), used when that block is cached in registers
+FBUS_HD constexpr int bridx(int i, int j) {  // any order; i,j in 9..17
+    return (i <= j) ? ((i - 9) * 9 - ((i - 9) * (i - 10)) / 2 + (j - i)) : ((j - 9) * 9 - ((j - 9) * (j - 10)) / 2 + (i - j));
+}
+constexpr int NBR = 45;
+// packed index inside the top-left 9x9 (rows/cols 0..8)
+FBUS_HD constexpr int tlidx(int i, int j) {
+    return (i <= j) ? (i * 9 - (i * (i - 1)) / 2 + (j - i)) : (j * 9 - (j * (j - 1)) / 2 + (i - j));
+}
+constexpr int NTL = 45;
 template <int S>
-FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, const double* w, double dt,
-                           const double* Qd) {
-    // Every sum below is written as a chain  s += x*y  so that it compiles to one DFMA per term.
-    const double a = dt;
-    const double ndt = -dt;
-    double A[9], B[9];
-    {
-        const double s0 = acc[0] * ndt, s1 = acc[1] * ndt, s2 = acc[2] * ndt;  // -dt * a
+FBUS_HD void tl_load(const Cov<S> P, double* TL) {
+    FBUS_UNROLL
+    for (int i = 0; i < 9; ++i)
         FBUS_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            // (R * [v]x)[i][:] = (R[i][1]v2 - R[i][2]v1, R[i][2]v0 - R[i][0]v2, R[i][0]v1 - R[i][1]v0)
-            A[i * 3 + 0] = R[i * 3 + 1] * s2 - R[i * 3 + 2] * s1;
-            A[i * 3 + 1] = R[i * 3 + 2] * s0 - R[i * 3 + 0] * s2;
-            A[i * 3 + 2] = R[i * 3 + 0] * s1 - R[i * 3 + 1] * s0;
-            FBUS_UNROLL
-            for (int j = 0; j < 3; ++j) B[i * 3 + j] = R[i * 3 + j] * ndt;
-        }
+        for (int j = i; j < 9; ++j) TL[tlidx(i, j)] = P.ld(i, j);
+}
+template <int S>
+FBUS_HD void tl_store(const Cov<S> P, const double* TL) {
+    FBUS_UNROLL
+    for (int i = 0; i < 9; ++i)
+        FBUS_UNROLL
+        for (int j = i; j < 9; ++j) P.st(i, j, TL[tlidx(i, j)]);
+}
+template <int S>
+FBUS_HD void br_load(const Cov<S> P, double* BR) {
+    FBUS_UNROLL
+    for (int i = 9; i < 18; ++i)
+        FBUS_UNROLL
+        for (int j = i; j < 18; ++j) BR[bridx(i, j)] = P.ld(i, j);
+}
+template <int S>
+FBUS_HD void br_store_diag(const Cov<S> P, const double* BR) {  // only the b_a / b_g diagonals change while propagating
+    FBUS_UNROLL
+    for (int i = 9; i < 15; ++i) P.st(i, i, BR[bridx(i, i)]);
+}
+
+// BRR = true: the bottom-right 9x9 (b_a, b_g, g covariance; read-only while propagating except for the process noise on
+// its diagonal) is held in the caller's registers BR[45] instead of being re-read from shared memory every step.
+// coefficients of F for one IMU sample: A = -R*[a]x*dt, B = -R*dt (row-major 3x3), u = w*dt
+FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, double dt, double* A, double* B, double* u) {
+    const double ndt = -dt;
+    const double s0 = acc[0] * ndt, s1 = acc[1] * ndt, s2 = acc[2] * ndt;  // -dt * a
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        // (R * [v]x)[i][:] = (R[i][1]v2 - R[i][2]v1, R[i][2]v0 - R[i][0]v2, R[i][0]v1 - R[i][1]v0)
+        A[i * 3 + 0] = R[i * 3 + 1] * s2 - R[i * 3 + 2] * s1;
+        A[i * 3 + 1] = R[i * 3 + 2] * s0 - R[i * 3 + 0] * s2;
+        A[i * 3 + 2] = R[i * 3 + 0] * s1 - R[i * 3 + 1] * s0;
+        FBUS_UNROLL
+        for (int j = 0; j < 3; ++j) B[i * 3 + j] = R[i * 3 + j] * ndt;
     }
     // Wm = -[w]x dt :  Wm01 = w2 dt, Wm02 = -w1 dt, Wm10 = -w2 dt, Wm12 = w0 dt, Wm20 = w1 dt, Wm21 = -w0 dt
-    const double u0 = w[0] * dt, u1 = w[1] * dt, u2 = w[2] * dt;
+    u[0] = w[0] * dt; u[1] = w[1] * dt; u[2] = w[2] * dt;
+}
+
+// TLR = true: the top-left 9x9 (p, v, theta covariance: read AND written by every step) is held in the caller's
+// registers TL[45] across the IMU samples of a window instead of making a round trip through shared memory per step.
+template <int S, bool BRR = false, bool TLR = false>
+FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B, double u0, double u1, double u2, double dt,
+                                const double* Qd, double* BR = nullptr, double* TL = nullptr) {
+#define FBUS_TLLD(i, j) (TLR ? TL[tlidx((i), (j))] : P.ld((i), (j)))
+#define FBUS_TLST(i, j, v)                        \
+    do {                                          \
+        if (TLR) TL[tlidx((i), (j))] = (v);       \
+        else P.st((i), (j), (v));                 \
+    } while (0)
+// block loads/stores of the top-left part through the same switch
+#define FBUS_TL_LDBLK(bi, bj, X)                                                        \
+    do {                                                                                \
+        FBUS_UNROLL                                                                     \
+        for (int r_ = 0; r_ < 3; ++r_)                                                  \
+            FBUS_UNROLL                                                                 \
+            for (int c_ = 0; c_ < 3; ++c_) X[r_ * 3 + c_] = FBUS_TLLD(3 * (bi) + r_, 3 * (bj) + c_); \
+    } while (0)
+#define FBUS_TL_STBLK(bi, bj, X)                                                        \
+    do {                                                                                \
+        FBUS_UNROLL                                                                     \
+        for (int r_ = 0; r_ < 3; ++r_)                                                  \
+            FBUS_UNROLL                                                                 \
+            for (int c_ = ((bi) == (bj) ? r_ : 0); c_ < 3; ++c_) FBUS_TLST(3 * (bi) + r_, 3 * (bj) + c_, X[r_ * 3 + c_]); \
+    } while (0)
+    // Every sum below is written as a chain  s += x*y  so that it compiles to one DFMA per term.
+    const double a = dt;
 // s += (Wm X)[i][j]  and  s += (X Wm^T)[i][j] = sum_k X[i][k] Wm[j][k]   (two DFMA each)
 #define FBUS_WX_ACC(s, X, i, j)                                                \
     do {                                                                       \
@@ -233,11 +311,11 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
     // shared-memory load to the top, which would blow the 255-register budget).
     {
         double P11[9], P12[9];
-        P.ldblk(1, 2, P12);
+        FBUS_TL_LDBLK(1, 2, P12);
         double M12[9];
         {   // 1c: P'22 (without the -a*M24 term) ; M12 = P12 + A*P22 (+ more below)
             double P22[9], P24[9], U22[9], acc22[9];
-            P.lddiag(2, P22);
+            FBUS_TL_LDBLK(2, 2, P22);
             P.ldblk(2, 4, P24);
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
@@ -261,9 +339,9 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                     FBUS_XWT_ACC(t, U22, i, j);
                     acc22[i * 3 + j] = t;
                 }
-            P.stdiag(2, acc22);
+            FBUS_TL_STBLK(2, 2, acc22);
         }
-        FBUS_FENCE;
+        FBUS_FENCE_A;
         {   // M12 += B*P23^T + a*P25^T
             double P23[9], P25[9];
             P.ldblk(2, 3, P23);
@@ -279,10 +357,10 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                     M12[i * 3 + j] = s;
                 }
         }
-        FBUS_FENCE;
+        FBUS_FENCE_A;
         {   // 1b: P'11 (without the M13*B^T + a*M15 term), P'12 (without -a*M14)
             double P13[9], P15[9], acc11[9], acc12[9];
-            P.lddiag(1, P11);
+            FBUS_TL_LDBLK(1, 1, P11);
             P.ldblk(1, 3, P13);
             P.ldblk(1, 5, P15);
             FBUS_UNROLL
@@ -305,15 +383,15 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                         acc11[i * 3 + j] = s;
                     }
                 }
-            P.stdiag(1, acc11);
-            P.stblk(1, 2, acc12);
+            FBUS_TL_STBLK(1, 1, acc11);
+            FBUS_TL_STBLK(1, 2, acc12);
         }
-        FBUS_FENCE;
+        FBUS_FENCE_A;
         {   // 1a: P'00, P'01 (without M03*B^T + a*M05), P'02 (without -a*M04); uses OLD P11, P12 kept in registers
             double P00[9], P01[9], P02[9], acc00[9], acc01[9], acc02[9];
-            P.lddiag(0, P00);
-            P.ldblk(0, 1, P01);
-            P.ldblk(0, 2, P02);
+            FBUS_TL_LDBLK(0, 0, P00);
+            FBUS_TL_LDBLK(0, 1, P01);
+            FBUS_TL_LDBLK(0, 2, P02);
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -342,12 +420,12 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                     FBUS_XWT_ACC(t, P02, i, j);
                     acc02[i * 3 + j] = t;
                 }
-            P.stdiag(0, acc00);
-            P.stblk(0, 1, acc01);
-            P.stblk(0, 2, acc02);
+            FBUS_TL_STBLK(0, 0, acc00);
+            FBUS_TL_STBLK(0, 1, acc01);
+            FBUS_TL_STBLK(0, 2, acc02);
         }
     }
-    FBUS_FENCE;
+    FBUS_FENCE_B;
     // ---------------- phase 2: block columns 4, 3, 5 of rows 0..2 -----------------------------
     double d01[9], d11[9];
     FBUS_UNROLL
@@ -366,9 +444,9 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                 for (int i = 0; i < 3; ++i)
                     FBUS_UNROLL
                     for (int j = 0; j < 3; ++j) {
-                        double t = P.ld(i, 6 + j);
+                        double t = FBUS_TLLD(i, 6 + j);
                         t -= a * M0[i * 3 + j];
-                        P.st(i, 6 + j, t);
+                        FBUS_TLST(i, 6 + j, t);
                     }
             } else if (k == 3) {  // d01 = M03*B^T
                 FBUS_UNROLL
@@ -385,19 +463,29 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                 for (int i = 0; i < 3; ++i)
                     FBUS_UNROLL
                     for (int j = 0; j < 3; ++j) {
-                        double t = P.ld(i, 3 + j) + d01[i * 3 + j];
+                        double t = FBUS_TLLD(i, 3 + j) + d01[i * 3 + j];
                         t += a * M0[i * 3 + j];
-                        P.st(i, 3 + j, t);
+                        FBUS_TLST(i, 3 + j, t);
                     }
             }
         }
-        FBUS_FENCE;
+        FBUS_FENCE_A;
         double X2[9];
         P.ldblk(2, k, X2);
         {   // row 1: M1 = P1k + A*P2k + B*P3k + a*P5k
             double X3[9], X5[9];
-            P.ldany(3, k, X3);
-            P.ldany(5, k, X5);
+            if (BRR) {
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r)
+                    FBUS_UNROLL
+                    for (int c = 0; c < 3; ++c) {
+                        X3[r * 3 + c] = BR[bridx(9 + r, 3 * k + c)];
+                        X5[r * 3 + c] = BR[bridx(15 + r, 3 * k + c)];
+                    }
+            } else {
+                P.ldany(3, k, X3);
+                P.ldany(5, k, X5);
+            }
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -417,9 +505,9 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                 for (int i = 0; i < 3; ++i)
                     FBUS_UNROLL
                     for (int j = 0; j < 3; ++j) {
-                        double t = P.ld(3 + i, 6 + j);
+                        double t = FBUS_TLLD(3 + i, 6 + j);
                         t -= a * X1[i * 3 + j];
-                        P.st(3 + i, 6 + j, t);
+                        FBUS_TLST(3 + i, 6 + j, t);
                     }
             } else if (k == 3) {  // d11 = M13*B^T (upper) ; accel-bias process noise on P33's diagonal
                 FBUS_UNROLL
@@ -432,22 +520,32 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                         d11[i * 3 + j] = s;
                     }
                 FBUS_UNROLL
-                for (int i = 0; i < 3; ++i) P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);
+                for (int i = 0; i < 3; ++i) {
+                    if (BRR) BR[bridx(9 + i, 9 + i)] = X3[i * 3 + i] + Qd[2];
+                    else P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);
+                }
             } else {  // P'11 += d11 + a*M15 (upper)
                 FBUS_UNROLL
                 for (int i = 0; i < 3; ++i)
                     FBUS_UNROLL
                     for (int j = i; j < 3; ++j) {
-                        double t = P.ld(3 + i, 3 + j) + d11[i * 3 + j];
+                        double t = FBUS_TLLD(3 + i, 3 + j) + d11[i * 3 + j];
                         t += a * X1[i * 3 + j];
-                        P.st(3 + i, 3 + j, t);
+                        FBUS_TLST(3 + i, 3 + j, t);
                     }
             }
         }
-        FBUS_FENCE;
+        FBUS_FENCE_A;
         {   // row 2: M2 = (I+Wm)*P2k - a*P4k
             double X4[9], M2[9];
-            P.ldany(4, k, X4);
+            if (BRR) {
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r)
+                    FBUS_UNROLL
+                    for (int c = 0; c < 3; ++c) X4[r * 3 + c] = BR[bridx(12 + r, 3 * k + c)];
+            } else {
+                P.ldany(4, k, X4);
+            }
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -463,18 +561,33 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
                 for (int i = 0; i < 3; ++i)
                     FBUS_UNROLL
                     for (int j = i; j < 3; ++j) {
-                        double t = P.ld(6 + i, 6 + j);
+                        double t = FBUS_TLLD(6 + i, 6 + j);
                         t -= a * M2[i * 3 + j];
-                        P.st(6 + i, 6 + j, t);
+                        FBUS_TLST(6 + i, 6 + j, t);
                     }
                 FBUS_UNROLL
-                for (int i = 0; i < 3; ++i) P.st(12 + i, 12 + i, X4[i * 3 + i] + Qd[3]);
+                for (int i = 0; i < 3; ++i) {
+                    if (BRR) BR[bridx(12 + i, 12 + i)] = X4[i * 3 + i] + Qd[3];
+                    else P.st(12 + i, 12 + i, X4[i * 3 + i] + Qd[3]);
+                }
             }
         }
-        FBUS_FENCE;
+        FBUS_FENCE_B;
     }
 #undef FBUS_WX_ACC
 #undef FBUS_XWT_ACC
+#undef FBUS_TLLD
+#undef FBUS_TLST
+#undef FBUS_TL_LDBLK
+#undef FBUS_TL_STBLK
+}
+
+template <int S, bool BRR = false>
+FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, const double* w, double dt, const double* Qd,
+                           double* BR = nullptr) {
+    double A[9], B[9], u[3];
+    cov_coeffs(R, acc, w, dt, A, B, u);
+    propagate_cov_core<S, BRR, false>(P, A, B, u[0], u[1], u[2], dt, Qd, BR, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
