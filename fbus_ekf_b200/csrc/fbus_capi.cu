@@ -5,6 +5,7 @@
 // kernel from fbus_kernels.cuh, and fbus_create fails when no CUDA device is usable.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -65,6 +66,8 @@ struct fbus_handle {
     DevConsts k;
     MarkerTable tab;
     MarkerTable* d_tab = nullptr;
+    uint32_t* d_ticket = nullptr;
+    uint32_t stagger_cycles = 0;
     double* d_nom = nullptr;
     double* d_P = nullptr;
     int32_t* d_prev = nullptr;
@@ -109,6 +112,8 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.status = h->d_status;
     prm.B = h->B;
     prm.tab = h->d_tab;
+    prm.sm_ticket = h->d_ticket;
+    prm.stagger_cycles = (prm.mode & M_FUSED) ? h->stagger_cycles : 0u;
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
 #if FBUS_SPLIT
     ekf_window_split_kernel<WIN_BS><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
@@ -186,6 +191,12 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     if ((e = cudaMalloc(&h->d_prev, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc prev", e);
     if ((e = cudaMalloc(&h->d_init, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc init", e);
     if ((e = cudaMalloc(&h->d_status, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc status", e);
+    if ((e = cudaMalloc(&h->d_ticket, 256 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc tickets", e);
+    if ((e = cudaMemset(h->d_ticket, 0, 256 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset tickets", e);
+    {
+        const char* sc = getenv("FBUS_STAGGER_CYCLES");
+        h->stagger_cycles = sc ? (uint32_t)strtoul(sc, nullptr, 10) : 20000u;
+    }
     if ((e = cudaMalloc(&h->d_tab, sizeof(MarkerTable))) != cudaSuccess) return bail("cudaMalloc marker table", e);
     if ((e = cudaMemcpy(h->d_tab, &h->tab, sizeof(MarkerTable), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("marker table copy", e);
 #if FBUS_SPLIT
@@ -194,6 +205,15 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     e = cudaFuncSetAttribute(ekf_window_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
 #endif
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if (getenv("FBUS_DEBUG")) {
+        int nb = -1;
+#if FBUS_SPLIT
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_window_split_kernel<WIN_BS>, 2 * WIN_BS, WIN_SMEM);
+#else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_window_kernel<WIN_BS>, WIN_BS, WIN_SMEM);
+#endif
+        fprintf(stderr, "[fbus] window kernel: %d filters/CTA, %zu B dynamic smem, %d CTA(s)/SM\n", WIN_BS, WIN_SMEM, nb);
+    }
     const unsigned grid = (unsigned)((batch + 127) / 128);
     ctor_kernel<<<grid, 128, 0, h->stream>>>(h->d_nom, h->d_P, h->d_prev, h->d_init, h->d_status, batch, cfg->p0_diag[0],
                                              cfg->p0_diag[1], cfg->p0_diag[2], cfg->p0_diag[3], cfg->p0_diag[4], cfg->p0_diag[5]);
@@ -207,7 +227,7 @@ int fbus_destroy(fbus_handle* h) {
     if (!h) return FBUS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_nom); cudaFree(h->d_P); cudaFree(h->d_prev); cudaFree(h->d_init); cudaFree(h->d_status); cudaFree(h->d_tab);
+    cudaFree(h->d_nom); cudaFree(h->d_P); cudaFree(h->d_prev); cudaFree(h->d_init); cudaFree(h->d_status); cudaFree(h->d_tab); cudaFree(h->d_ticket);
     DevBuf* bufs[] = {&h->imu_t, &h->det_t, &h->win_off, &h->imu_data, &h->det_id, &h->det_pose, &h->trace,
                       &h->scratch_in, &h->scratch_out, &h->scratch_aux, &h->stats_partial, &h->stats_out};
     for (DevBuf* b : bufs) b->release();

@@ -22,15 +22,37 @@
 #ifndef FBUS_TL_REGS
 #define FBUS_TL_REGS 1
 #endif
+// 1: both warps of a filter group share the covariance sweeps of the update; 0: the covariance warp does it alone
+#ifndef FBUS_COOP_UPDATE
+#define FBUS_COOP_UPDATE 0
+#endif
+// 1: the per-sample ring barrier is private to a warp pair (64 threads); the CTA re-aligns once per frame
+#ifndef FBUS_PAIR_BARRIER
+#define FBUS_PAIR_BARRIER 1
+#endif
+// 1: additionally keep the bottom-right 9x9 block (bias / gravity covariance) in the covariance warp's registers
+#ifndef FBUS_BR_REGS_SPLIT
+#define FBUS_BR_REGS_SPLIT 0
+#endif
 
 namespace fbus {
 
-constexpr int XCH = 44;  // doubles of exchange area per filter: ring 2 x 22, reused for the update hand-off (23 in, 19 out)
+constexpr int XCH = 46;  // doubles of exchange area per filter: ring 2 x 22; reused by the update: Lc 21 + y 6, dx 18
 
 // CTA-wide named barrier used by both roles (the two roles run different code, so the barrier is issued from
 // different program counters; whole warps take each path, and arrivals are counted per barrier id)
 template <int NT>
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+// per-sample barrier: either the whole CTA or only the covariance + nominal warp of one filter group (ids 2..9)
+template <int NT>
+__device__ __forceinline__ void step_bar(int pair) {
+#if FBUS_PAIR_BARRIER
+    asm volatile("bar.sync %0, 64;" ::"r"(pair + 2) : "memory");
+#else
+    (void)pair;
+    cta_bar<NT>();
+#endif
+}
 
 struct SplitShared {
     uint32_t lo_hi[2][8];   // per nominal warp: min first / max end of the candidate IMU range
@@ -58,8 +80,12 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
             tl_load<BSF>(P, TL);
 #endif
+#if FBUS_BR_REGS_SPLIT
+            double BR[NBR];
+            br_load<BSF>(P, BR);
+#endif
             for (uint32_t i = lo; i < hi; ++i) {
-                cta_bar<NT>();  // record (i) is complete; the nominal warp moves on to sample i+1
+                step_bar<NT>(fl >> 5);  // record (i) is complete; the nominal warp moves on to sample i+1
                 const int slot = (int)((i - lo) & 1u);
                 if (sflag[slot][fl]) {
                     const double* rec = X + (size_t)slot * 22 * BSF;
@@ -68,7 +94,9 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                     for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * BSF]; Bm[e] = rec[(size_t)(9 + e) * BSF]; }
                     const double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
                     const double dt = rec[(size_t)21 * BSF];
-#if FBUS_TL_REGS
+#if FBUS_TL_REGS && FBUS_BR_REGS_SPLIT
+                    propagate_cov_core<BSF, true, true>(P, A, Bm, u0, u1, u2, dt, k.Qd, BR, TL);
+#elif FBUS_TL_REGS
                     propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, k.Qd, nullptr, TL);
 #else
                     propagate_cov_core<BSF>(P, A, Bm, u0, u1, u2, dt, k.Qd);
@@ -78,12 +106,59 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #if FBUS_TL_REGS
             tl_store<BSF>(P, TL);
 #endif
+#if FBUS_BR_REGS_SPLIT
+            br_store_diag<BSF>(P, BR);
+#endif
         }
         cta_bar<NT>();  // (b) ring consumed: the exchange area is free for the update hand-off
         cta_bar<NT>();  // (c) update requests posted
         int any = sh.any_upd[0];
 #pragma unroll
         for (int q = 1; q < NW; ++q) any |= sh.any_upd[q];
+#if FBUS_COOP_UPDATE
+        if (any) {
+            // Cooperative update.  This warp computes the gain factors (prologue) from the posted measurement and pose,
+            // publishes Lc and y, then applies the first half-rank factor Za while the nominal warp applies the second
+            // (Zb).  Both factors come from the OLD covariance; the two sweeps work on disjoint row sets and swap.
+            const int req = sflag[2][fl];
+            double Z[54];
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+            double Cm[21];
+            if (req) {
+                Nominal t;
+                double yP[3], yQ[4], y[6];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) yP[c] = X[(size_t)c * BSF];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { yQ[c] = X[(size_t)(3 + c) * BSF]; t.q[c] = X[(size_t)(7 + c) * BSF]; }
+#pragma unroll
+                for (int c = 0; c < 9; ++c) t.R[c] = X[(size_t)(11 + c) * BSF];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) t.p[c] = X[(size_t)(20 + c) * BSF];
+                const MarkerConst mkc = prm.tab->mk[req - 1];  // 3 KB table, L2-resident
+                // X = L^-1 Hs (42 doubles) is parked in the exchange area: its inputs are already in registers
+                update_prologue<BSF, BSF>(P, t, k, mkc, yP, yQ, Cm, y, X);
+#pragma unroll
+                for (int c = 0; c < 21; ++c) X[(size_t)c * BSF] = Cm[c];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) X[(size_t)(21 + c) * BSF] = y[3 + c];
+                y0 = y[0]; y1 = y[1]; y2 = y[2];
+            }
+            cta_bar<NT>();  // (c2) gain factors published
+            if (req) update_Za<BSF>(P, Cm, Z);
+            cta_bar<NT>();  // (d1) both factors taken from the old covariance
+            if (req) update_sweep<BSF, 0, 5>(P, Z);
+            cta_bar<NT>();  // (d2)
+            if (req) {
+                update_sweep<BSF, 5, 18>(P, Z);
+                double dx[18];
+                update_dx<false>(Z, y0, y1, y2, dx);
+#pragma unroll
+                for (int c = 0; c < 18; ++c) X[(size_t)(27 + c) * BSF] = dx[c];
+            }
+            cta_bar<NT>();  // (e) first half of dx posted
+        }
+#else
         if (any) {
             const int req = sflag[2][fl];
             if (req) {
@@ -115,6 +190,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             cta_bar<NT>();  // (d) results posted
             cta_bar<NT>();  // (e) results consumed: the exchange area may be overwritten by the next frame's ring
         }
+#endif
     }
     if (live)
         for (int e = 0; e < NPK; ++e) prm.P[(size_t)e * B + b] = smem[e * BSF + fl];
@@ -268,6 +344,28 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             }
         }
 
+#if FBUS_COOP_UPDATE
+        // ---- marker of this frame's update (filter.cpp:666-675), fetched now so that the loads overlap the propagation ----
+        int req = 0;
+        double yP[3], yQ[4];
+        if (do_update && n_det > 0) {
+            const size_t slot = (size_t)w * prm.m + idx_upd;
+            const int did = prm.det_id[slot * B + b];
+            const int mk = find_marker(k, prm.tab, did);
+            if (mk >= 0) {
+                prev_id = did;
+                req = mk + 1;
+                const double* pp = prm.det_pose + slot * 7 * B + b;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) yP[c] = pp[(size_t)c * B];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) yQ[c] = pp[(size_t)(3 + c) * B];
+            } else {
+                status |= FBUS_ST_UPDATE_SKIPPED;
+            }
+        }
+
+#endif
         // ---- F3 BatchImuProcessing (filter.cpp:483-531): one sample ahead of the covariance warp -------------
         {
             const uint32_t vlo = __reduce_min_sync(0xffffffffu, do_prop ? p_first : 0xffffffffu);
@@ -320,21 +418,69 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                     }
                 }
                 sflag[slot][fl] = valid;
-                cta_bar<NT>();  // publish record (i); also: the covariance warp has finished sample i-1
+                step_bar<NT>(fl >> 5);  // publish record (i); also: the covariance warp has finished sample i-1
             }
             if (fused && do_prop) cursor = consumed;
         }
         cta_bar<NT>();  // (b) the covariance warp is done with the ring
 
+#if FBUS_COOP_UPDATE
+        // ---- F4 ObservationUpdate (filter.cpp:622-739), cooperative: post measurement + pose, the covariance warp
+        //      computes the gain factors, then both warps apply one half-rank factor each --------------------------
+        if (req) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) X[(size_t)c * BSF] = yP[c];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { X[(size_t)(3 + c) * BSF] = yQ[c]; X[(size_t)(7 + c) * BSF] = n.q[c]; }
+#pragma unroll
+            for (int c = 0; c < 9; ++c) X[(size_t)(11 + c) * BSF] = n.R[c];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) X[(size_t)(20 + c) * BSF] = n.p[c];
+        }
+        sflag[2][fl] = req;
+        {
+            const int wany = __any_sync(0xffffffffu, req != 0);
+            if ((fl & 31) == 0) sh.any_upd[wq] = wany;
+        }
+        cta_bar<NT>();  // (c)
+        int any = sh.any_upd[0];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) any |= sh.any_upd[q];
+        if (any) {
+            const Cov<BSF> P{smem + fl};
+            double Z[54];
+            double y3 = 0.0, y4 = 0.0, y5 = 0.0;
+            cta_bar<NT>();  // (c2)
+            if (req) {
+                double Cm[21];
+#pragma unroll
+                for (int c = 0; c < 21; ++c) Cm[c] = X[(size_t)c * BSF];
+                y3 = X[(size_t)21 * BSF]; y4 = X[(size_t)22 * BSF]; y5 = X[(size_t)23 * BSF];
+                update_Zb<BSF>(P, Cm, Z);
+            }
+            cta_bar<NT>();  // (d1)
+            if (req) update_sweep<BSF, 5, 18>(P, Z);
+            cta_bar<NT>();  // (d2)
+            if (req) update_sweep<BSF, 0, 5>(P, Z);
+            cta_bar<NT>();  // (e)
+            if (req) {
+                double dx[18];
+#pragma unroll
+                for (int c = 0; c < 18; ++c) dx[c] = X[(size_t)(27 + c) * BSF];
+                update_dx<true>(Z, y3, y4, y5, dx);
+                inject_error_state(n, dx);
+            }
+        }
+#else
         // ---- F4 ObservationUpdate (filter.cpp:622-739): post the request, the covariance warp does the algebra ----
-        int req = 0;
+        int req_old = 0;
         if (do_update && n_det > 0) {
             const size_t slot = (size_t)w * prm.m + idx_upd;
             const int did = prm.det_id[slot * B + b];
             const int mk = find_marker(k, prm.tab, did);
             if (mk >= 0) {
                 prev_id = did;
-                req = mk + 1;
+                req_old = mk + 1;
                 const double* pp = prm.det_pose + slot * 7 * B + b;
 #pragma unroll
                 for (int c = 0; c < 7; ++c) X[(size_t)c * BSF] = pp[(size_t)c * B];  // yP (3), yQ (4)
@@ -348,9 +494,9 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                 status |= FBUS_ST_UPDATE_SKIPPED;
             }
         }
-        sflag[2][fl] = req;
+        sflag[2][fl] = req_old;
         {
-            const int wany = __any_sync(0xffffffffu, req != 0);
+            const int wany = __any_sync(0xffffffffu, req_old != 0);
             if ((fl & 31) == 0) sh.any_upd[wq] = wany;
         }
         cta_bar<NT>();  // (c)
@@ -359,7 +505,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         for (int q = 1; q < NW; ++q) any |= sh.any_upd[q];
         if (any) {
             cta_bar<NT>();  // (d) results posted
-            if (req) {
+            if (req_old) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     n.p[c] = X[(size_t)(23 + c) * BSF];
@@ -373,6 +519,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             }
             cta_bar<NT>();  // (e)
         }
+#endif
         // ---- trace row: the data/fusion.txt record (filter.cpp:241-246) -------------------------
         if (prm.trace && live) {
             double* row = prm.trace + (size_t)(w - prm.w0) * 17 * B + b;
@@ -414,14 +561,36 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     prm.status[b] = status;
 }
 
-template <int BSF>  // filters per CTA; the CTA has 2*BSF threads: warps [0, BSF/32) covariance, [BSF/32, 2*BSF/32) nominal
+// Two CTAs can share an SM when BSF = 64 (2 x 110 KB of shared memory, 2 x 128 threads x 255 registers).  Warp w of
+// every CTA lands on scheduler w % 4, so with a fixed role order both CTAs would stack their covariance warps on the
+// same two schedulers.  Each CTA therefore takes an arrival ticket per SM: odd tickets swap the role order (covariance
+// warps on schedulers 2,3 instead of 0,1) and start half a frame period late, so that one CTA's update phase (one busy
+// warp per filter group) overlaps the other's propagation phase.
+template <int BSF>  // filters per CTA; the CTA has 2*BSF threads
 __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
     extern __shared__ double smem[];
     __shared__ SplitShared sh;
     __shared__ int32_t sflag[3][BSF];  // [0],[1]: ring slot valid ; [2]: update requested (marker index + 1, 0 = none)
+    __shared__ uint32_t s_ticket;
     static_assert(BSF % 32 == 0 && BSF / 32 <= 8, "BSF must be a multiple of the warp size, at most 256");
-    const bool is_cov = threadIdx.x < BSF;
-    const int fl = is_cov ? threadIdx.x : threadIdx.x - BSF;  // filter lane inside the CTA
+    constexpr int NW = BSF / 32;
+    uint32_t parity = 0;
+    if (BSF < 128 && prm.sm_ticket != nullptr) {
+        if (threadIdx.x == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_ticket = atomicAdd(prm.sm_ticket + (smid & 255u), 1u);
+        }
+        __syncthreads();
+        parity = s_ticket & 1u;
+        if (parity && prm.stagger_cycles > 0) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < (long long)prm.stagger_cycles) { }
+        }
+    }
+    const int wi = threadIdx.x >> 5;
+    const bool is_cov = ((wi < NW) ? 1u : 0u) != parity;
+    const int fl = (wi % NW) * 32 + (threadIdx.x & 31);  // filter lane inside the CTA
     const size_t b0 = (size_t)blockIdx.x * BSF + fl;
     const bool live = b0 < prm.B;
     const size_t b = live ? b0 : prm.B - 1;  // threads past the batch mirror the last filter and never store

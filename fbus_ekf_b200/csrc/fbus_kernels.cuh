@@ -54,7 +54,8 @@ struct WinParams {
     uint32_t prop_first, prop_count;
     double prop_t_end;
     uint32_t n_imu_before;  // un-fused init
-    uint32_t pad;
+    uint32_t stagger_cycles;  // split kernel, 2 CTAs per SM: start delay of odd-ticket CTAs
+    uint32_t* sm_ticket;      // split kernel: per-SM arrival counters [256] (device), or nullptr
 };
 
 template <int BS>

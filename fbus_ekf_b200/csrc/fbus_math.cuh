@@ -709,9 +709,13 @@ struct CholStep<N, N> {
     static FBUS_HD void run(double*, double*) {}
 };
 
-template <int S>
-FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
-                                const double* yQ) {
+// Prologue of the update: everything up to the gain factors.  Reads only the 21 entries of P6 = P[{p,theta},{p,theta}].
+// Outputs Cm = lower-packed Cholesky factor Lc of C = Hs^T S^-1 Hs and y = Lc^-1 u (u = Hs^T S^-1 r), so that
+//   (I-KH)P = P - Z^T Z with Z = Lc^T G, and dx = K r = Z^T y.
+template <int S, int XS>
+FBUS_HD void update_prologue(const Cov<S> P, const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+                             const double* yQ, double* Cm, double* y, double* scr) {
+    // scr: 42 doubles of scratch with element stride XS (shared memory in the warp-specialised kernel) for X = L^-1 Hs
     // ---- predicted measurement and Hs ------------------------------------------------------
     double Hp0[9], Hp2[9], Hq[12], r[7];
     {
@@ -845,18 +849,19 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
     double Li[7];
     CholStep<7, 0>::run(L, Li);
     // ---- X = L^-1 Hs (7x6), z = L^-1 r ; C = X^T X ; u = X^T z -------------------------------
-    double Cm[21], u[6];  // C lower packed: Cm[i*(i+1)/2+j]
+    double u[6];  // (Cm: C lower packed, Cm[i*(i+1)/2+j])
 #define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
     {
-        double X[42], z[7];
+        double z[7];
+#define FBUS_X(i) scr[(i) * XS]
         FBUS_UNROLL
         for (int i = 0; i < 7; ++i) {
             FBUS_UNROLL
             for (int c = 0; c < 6; ++c) {
                 double s = (i < 3) ? ((c < 3) ? Hp0[i * 3 + c] : Hp2[i * 3 + (c - 3)]) : ((c < 3) ? 0.0 : Hq[(i - 3) * 3 + (c - 3)]);
                 FBUS_UNROLL
-                for (int j = 0; j < i; ++j) s -= FBUS_L(i, j) * X[j * 6 + c];
-                X[i * 6 + c] = s * Li[i];
+                for (int j = 0; j < i; ++j) s -= FBUS_L(i, j) * FBUS_X(j * 6 + c);
+                FBUS_X(i * 6 + c) = s * Li[i];
             }
             double s = r[i];
             FBUS_UNROLL
@@ -867,21 +872,21 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
         for (int i = 0; i < 6; ++i) {
             FBUS_UNROLL
             for (int j = 0; j <= i; ++j) {
-                double s = X[i] * X[j];
+                double s = FBUS_X(i) * FBUS_X(j);
                 FBUS_UNROLL
-                for (int c = 1; c < 7; ++c) s += X[c * 6 + i] * X[c * 6 + j];
+                for (int c = 1; c < 7; ++c) s += FBUS_X(c * 6 + i) * FBUS_X(c * 6 + j);
                 FBUS_C(i, j) = s;
             }
-            double s = X[i] * z[0];
+            double s = FBUS_X(i) * z[0];
             FBUS_UNROLL
-            for (int c = 1; c < 7; ++c) s += X[c * 6 + i] * z[c];
+            for (int c = 1; c < 7; ++c) s += FBUS_X(c * 6 + i) * z[c];
             u[i] = s;
         }
     }
 #undef FBUS_L
+#undef FBUS_X
     // ---- Cholesky C = Lc Lc^T (in place in Cm) ; y = Lc^-1 u -------------------------------------
     // dx = K r = G^T u = Z^T y = Za^T y[0:3] + Zb^T y[3:6]
-    double y[6];
     {
         double Lci[6];
         CholStep<6, 0>::run(Cm, Lci);
@@ -893,6 +898,117 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
             y[i] = s * Lci[i];
         }
     }
+#undef FBUS_C
+}
+
+// rows 0..2 of Z = Lc^T G from the current P (G = rows {0,1,2,6,7,8} of P)
+#define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
+template <int S>
+FBUS_HD void update_Za(const Cov<S> P, const double* Cm, double* Z) {
+    FBUS_UNROLL
+    for (int m = 0; m < 6; ++m) {
+        const int row = (m < 3) ? m : (3 + m);  // 0,1,2,6,7,8
+        FBUS_UNROLL
+        for (int c = 0; c < 18; ++c) {
+            const double g = P.ld(row, c);
+            FBUS_UNROLL
+            for (int kz = 0; kz < 3; ++kz) {
+                if (m == kz) Z[kz * 18 + c] = FBUS_C(m, kz) * g;
+                else if (m > kz) Z[kz * 18 + c] += FBUS_C(m, kz) * g;
+            }
+        }
+    }
+}
+// rows 3..5 of Z = Lc^T G from the current (not yet swept) P: only the theta rows 6..8 are needed
+template <int S>
+FBUS_HD void update_Zb(const Cov<S> P, const double* Cm, double* Z) {
+    FBUS_UNROLL
+    for (int c = 0; c < 18; ++c) {
+        const double g3 = P.ld(6, c), g4 = P.ld(7, c), g5 = P.ld(8, c);
+        double t3 = FBUS_C(3, 3) * g3;
+        t3 += FBUS_C(4, 3) * g4;
+        t3 += FBUS_C(5, 3) * g5;
+        double t4 = FBUS_C(4, 4) * g4;
+        t4 += FBUS_C(5, 4) * g5;
+        Z[c] = t3;
+        Z[18 + c] = t4;
+        Z[36 + c] = FBUS_C(5, 5) * g5;
+    }
+}
+#undef FBUS_C
+// P[i][j] -= sum_k Z[k][i] Z[k][j] for rows R0 <= i < R1 (j >= i)
+template <int S, int R0, int R1>
+FBUS_HD void update_sweep(const Cov<S> P, const double* Z) {
+    FBUS_UNROLL
+    for (int i = R0; i < R1; ++i)
+        FBUS_UNROLL
+        for (int j = i; j < 18; ++j) {
+            double v = P.ld(i, j);
+            v -= Z[i] * Z[j];
+            v -= Z[18 + i] * Z[18 + j];
+            v -= Z[36 + i] * Z[36 + j];
+            P.st(i, j, v);
+        }
+}
+// dx[c] (+)= y0 Z[0][c] + y1 Z[1][c] + y2 Z[2][c]
+template <bool ACC>
+FBUS_HD void update_dx(const double* Z, double y0, double y1, double y2, double* dx) {
+    FBUS_UNROLL
+    for (int c = 0; c < 18; ++c) {
+        double s = ACC ? dx[c] : 0.0;
+        s += y0 * Z[c];
+        s += y1 * Z[18 + c];
+        s += y2 * Z[36 + c];
+        dx[c] = s;
+    }
+}
+// error-state injection (filter.cpp:726-733); rotmatI2G deliberately NOT refreshed
+FBUS_HD void inject_error_state(Nominal& n, const double* dx) {
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        n.p[i] += dx[i];
+        n.v[i] += dx[3 + i];
+        n.ba[i] += dx[9 + i];
+        n.bg[i] += dx[12 + i];
+        n.g[i] += dx[15 + i];
+    }
+    // VectorToQuaterniond (matrix_math.hpp:90-99): v/|v| * sin(|v|/2); NaN at exactly zero, as the reference
+    const double vn = norm3(dx + 6);
+    double sh, ch;
+    sincos(vn / 2, &sh, &ch);
+    const double dq[4] = {ch, dx[6] / vn * sh, dx[7] / vn * sh, dx[8] / vn * sh};
+    double qn[4];
+    qmul(n.q, dq, qn);
+    qnormalize(qn);
+    FBUS_UNROLL
+    for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
+}
+
+// Cooperative form used by the warp-specialised kernel (here executed by one thread, for the host harness): both
+// half-rank factors are taken from the OLD covariance, then applied; algebraically identical to measurement_update.
+template <int S>
+FBUS_HD void measurement_update_coop(const Cov<S> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+                                     const double* yQ) {
+    double Cm[21], y[6], Za[54], Zb[54], dx[18], xloc[42];
+    update_prologue<S, 1>(P, n, k, mk, yP, yQ, Cm, y, xloc);
+    update_Za<S>(P, Cm, Za);
+    update_Zb<S>(P, Cm, Zb);
+    update_sweep<S, 0, 18>(P, Za);
+    update_sweep<S, 0, 18>(P, Zb);
+    update_dx<false>(Za, y[0], y[1], y[2], dx);
+    update_dx<true>(Zb, y[3], y[4], y[5], dx);
+    inject_error_state(n, dx);
+}
+
+template <int S>
+FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+                                const double* yQ) {
+    double Cm[21], y[6];
+    {
+        double xloc[42];  // single-thread form: X = L^-1 Hs stays private
+        update_prologue<S, 1>(P, n, k, mk, yP, yQ, Cm, y, xloc);
+    }
+#define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
     double dth[3];  // attitude part of dx (needed whole before the quaternion injection)
     double Z[54];   // 3 x 18
     // ---- stream G (rows 0..2 and 6..8 of P): Za = rows 0..2 of Lc^T G -----------------------------

@@ -52,6 +52,20 @@ int hm_update(const fbus_config* cfg, double* P171, double* nom, int marker_id, 
 }
 }
 
+extern "C" int hm_update_coop(const fbus_config* cfg, double* P171, double* nom, int marker_id, const double* yP, const double* yQ) {
+    DevConsts k;
+    MarkerTable tab;
+    if (make_dev_consts(cfg, &k, &tab)) return -1;
+    const int m = find_marker(k, &tab, marker_id);
+    if (m < 0) return -2;
+    Nominal n;
+    nom_from(nom, n);
+    Cov<1> P{P171};
+    measurement_update_coop<1>(P, n, k, tab.mk[m], yP, yQ);
+    nom_to(n, nom);
+    return 0;
+}
+
 #include "../fbus_ekf_b200/csrc/fbus_refract.cuh"
 extern "C" {
 // corners16: Lxy x4, Rxy x4 (float32) -> corners3d[12], pose[7]; returns valid flag
