@@ -288,12 +288,14 @@ def run_ours(args):
     except Exception:
         pass
     ach_tf = flop_launch / avg_launch_s / 1e12
-    roofline = {"kernel": "ekf_window_kernel<32>", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+    roofline = {"kernel": "ekf_window_split_kernel<128>", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                 "frac": ach_tf / (fp64_peak / 1e12),
                 "peak_source": "DFMA-saturating microbenchmark measured live on this GPU (fbus_measure_fp64_peak, burst); "
                                "MEASURED_PEAKS.json has no FP64 entry; nominal 37.2 TFLOP/s",
                 "algorithmic_flop_per_launch": flop_launch, "avg_launch_ms": avg_launch_s * 1e3,
-                "traffic": prof.get("ekf_window_dram_bytes_per_launch"),
+                "traffic": (prof["ekf_window_dram_bytes_per_filter_per_launch"] * B) if "ekf_window_dram_bytes_per_filter_per_launch" in prof else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at %d filters, scaled per filter "
+                                  "(profiles/roofline_inputs.json)" % prof.get("measured_at_filters", 0) if prof else None,
                 "hbm": {"achieved": bytes_launch / avg_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_launch / avg_launch_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": bytes_launch,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}}
