@@ -365,7 +365,20 @@ def bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak):
     for _ in range(max(K, 4)):
         host_call()
     e2e_rate = n * max(K, 4) / (time.perf_counter() - t0)
-    return {"metric": "refractive solves/sec", "value": rate * world, "unit": "solves/s", "markers_per_launch": n,
+    # R3 (north_star): closed form + 5 Gauss-Newton iterations, same markers
+    cost = torch.empty((n,), dtype=torch.float64, device=dev)
+    lib.fbus_refract_solve_gn(f._h, corners[0].data_ptr(), 0, n, 5, pose.data_ptr(), cost.data_ptr(), valid.data_ptr(), capi.FBUS_MEM_DEVICE)
+    f.Synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g_iters = max(K, 4)
+    g0.record(stream)
+    for i in range(g_iters):
+        lib.fbus_refract_solve_gn(f._h, corners[i % reps].data_ptr(), 0, n, 5, pose.data_ptr(), cost.data_ptr(), valid.data_ptr(),
+                                  capi.FBUS_MEM_DEVICE)
+    g1.record(stream)
+    f.Synchronize()
+    gn_rate = n * g_iters / (g0.elapsed_time(g1) * 1e-3)
+    return {"metric": "refractive solves/sec", "value": rate * world, "gauss_newton_5it_solves_per_s": gn_rate * world, "unit": "solves/s", "markers_per_launch": n,
             "ms_per_launch": sec * 1e3, "valid_fraction": float(valid.float().mean().item()),
             "e2e": {"value": e2e_rate * world, "unit": "solves/s", "h2d_bytes_per_step": 64 * n, "d2h_bytes_per_step": 60 * n},
             "roofline": {"kernel": "refract_kernel", "bound": "fp64", "achieved": rate * FLOP_SOLVE / 1e12, "peak": fp64_peak / 1e12,

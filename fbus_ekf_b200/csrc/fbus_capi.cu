@@ -65,6 +65,7 @@ struct fbus_handle {
     fbus_config cfg;
     DevConsts k;
     MarkerTable tab;
+    GnConsts gn;
     MarkerTable* d_tab = nullptr;
     uint32_t* d_ticket = nullptr;
     uint32_t stagger_cycles = 0;
@@ -179,6 +180,7 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         delete h;
         return fail(nullptr, FBUS_E_BADARG, "fbus_create: bad config (n_markers)");
     }
+    make_gn_consts(cfg, &h->k, &h->gn);
     auto bail = [&](const char* what, cudaError_t ce) {
         std::string msg = std::string("fbus_create: ") + what + ": " + cudaGetErrorString(ce);
         fbus_destroy(h);
@@ -393,6 +395,42 @@ int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* p
     if (mem == FBUS_MEM_HOST) {
         CUDA_TRY(h, cudaMemcpyAsync(pose, dpose, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         if (corners3d) CUDA_TRY(h, cudaMemcpyAsync(corners3d, dc3, 12 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (valid) CUDA_TRY(h, cudaMemcpyAsync(valid, dvalid, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
+int fbus_refract_solve_gn(fbus_handle* h, const void* corners, int32_t corner_dtype, size_t n, int32_t iters, double* pose,
+                          double* cost, int32_t* valid, int32_t mem) {
+    if (!h || !corners || !pose || iters < 0 || iters > 50 || (corner_dtype != 0 && corner_dtype != 1))
+        return fail(h, FBUS_E_BADARG, "fbus_refract_solve_gn: bad argument");
+    if (n == 0) return FBUS_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t esz = corner_dtype ? sizeof(double) : sizeof(float);
+    const void* dc = corners;
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, h->scratch_in.reserve(16 * n * esz));
+        CUDA_TRY(h, cudaMemcpyAsync(h->scratch_in.p, corners, 16 * n * esz, cudaMemcpyHostToDevice, h->stream));
+        dc = h->scratch_in.p;
+    }
+    double* dpose = pose;
+    double* dcost = cost;
+    int32_t* dvalid = valid;
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, h->scratch_out.reserve((7 + 1) * n * sizeof(double)));
+        CUDA_TRY(h, h->scratch_aux.reserve(n * sizeof(int32_t)));
+        dpose = (double*)h->scratch_out.p;
+        dcost = dpose + 7 * n;
+        dvalid = (int32_t*)h->scratch_aux.p;
+    }
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (corner_dtype) refract_gn_kernel<double><<<grid, 128, 0, h->stream>>>(h->k, h->gn, (const double*)dc, n, iters, dpose, dcost, dvalid);
+    else refract_gn_kernel<float><<<grid, 128, 0, h->stream>>>(h->k, h->gn, (const float*)dc, n, iters, dpose, dcost, dvalid);
+    CUDA_TRY(h, cudaGetLastError());
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(pose, dpose, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (cost) CUDA_TRY(h, cudaMemcpyAsync(cost, dcost, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         if (valid) CUDA_TRY(h, cudaMemcpyAsync(valid, dvalid, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }

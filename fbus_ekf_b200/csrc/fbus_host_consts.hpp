@@ -10,6 +10,7 @@
 
 #include "../../include/fbus_ekf.h"
 #include "fbus_math.cuh"
+#include "fbus_refract.cuh"
 
 namespace fbus {
 
@@ -83,6 +84,20 @@ inline int make_dev_consts(const fbus_config* c, DevConsts* k, MarkerTable* tab)
     return FBUS_OK;
 }
 
+// constants of the Gauss-Newton refinement (R3)
+inline void make_gn_consts(const fbus_config* c, const DevConsts* k, GnConsts* g) {
+    g->d0 = c->d_air; g->d1 = c->d_glass;
+    g->k1 = c->n_air / c->n_glass; g->k2 = c->n_air / c->n_water;
+    g->size = c->marker_size;
+    for (int i = 0; i < 3; ++i) g->P_LR[i] = k->P_LR[i];
+    const double* m = k->R_RL;
+    const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    const double id = 1.0 / det;
+    g->R_RL_inv[0] = (m[4] * m[8] - m[5] * m[7]) * id; g->R_RL_inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; g->R_RL_inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    g->R_RL_inv[3] = (m[5] * m[6] - m[3] * m[8]) * id; g->R_RL_inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; g->R_RL_inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    g->R_RL_inv[6] = (m[3] * m[7] - m[4] * m[6]) * id; g->R_RL_inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; g->R_RL_inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
 inline void config_default(fbus_config* c) {
     memset(c, 0, sizeof *c);
     // C++/config/camerainfo1.yml (== matlab/config/camerainfo.yml): the calibration of the bundled logs
@@ -104,6 +119,7 @@ inline void config_default(fbus_config* c) {
     c->n_air = 1.00; c->n_water = 1.32; c->n_glass = 1.49; c->d_air = 0.002; c->d_glass = 0.02;
     c->normal[0] = 0; c->normal[1] = 0; c->normal[2] = 1;
     c->marker_dect_dist_thres = 2.0;  // paramconfig.yml:27
+    c->marker_size = 0.28;            // vision.hpp:114 (paramconfig.yml:23 says 0.48 but is unused)
     // C++/config/markersetup.yml
     static const int ids[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 16, 17, 18};
     static const double pos[12][3] = {{0, 0, 0}, {0, 0.61, 0.285}, {0, 0.61, 1.185}, {0, 0.61, 2.085}, {0, 0.61, 2.985},

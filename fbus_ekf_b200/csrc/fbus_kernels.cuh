@@ -418,6 +418,41 @@ __global__ void __launch_bounds__(128) refract_kernel(const __grid_constant__ De
     if (valid) valid[i] = dead ? 0 : 1;
 }
 
+// K3+K4+K5: closed-form solve, then Gauss-Newton refinement of the pose on the stereo reprojection error (R3)
+template <typename CT>
+__global__ void __launch_bounds__(128) refract_gn_kernel(const __grid_constant__ DevConsts k, const __grid_constant__ GnConsts g,
+                                                         const CT* __restrict__ corners, size_t n, int iters, double* __restrict__ pose,
+                                                         double* __restrict__ cost_out, int32_t* __restrict__ valid) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double c[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) c[e] = (double)corners[(size_t)e * n + i];
+    double C[12];
+    bool dead = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        double Pc[3];
+        const double nrm = triangulate_corner(k, c[2 * e], c[2 * e + 1], c[8 + 2 * e], c[8 + 2 * e + 1], Pc);
+        C[3 * e] = Pc[0]; C[3 * e + 1] = Pc[1]; C[3 * e + 2] = Pc[2];
+        if (nrm > k.dect_thres) dead = true;
+    }
+    double p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0}, cost = 0.0;
+    if (!dead) {
+        marker_pose(C, k.rod_s, k.rod_c, p, q);
+        double Rm[9];
+        quat_to_rotmat_unit(q, Rm);
+        cost = gn_refine(g, c, Rm, p, iters);
+        R2q(Rm, q);
+    }
+#pragma unroll
+    for (int e = 0; e < 3; ++e) pose[(size_t)e * n + i] = p[e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pose[(size_t)(3 + e) * n + i] = q[e];
+    if (cost_out) cost_out[i] = cost;
+    if (valid) valid[i] = dead ? 0 : 1;
+}
+
 __global__ void __launch_bounds__(128) marker_pose_kernel(const __grid_constant__ DevConsts k, const double* __restrict__ c3d, size_t n,
                                                           double* __restrict__ pose) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

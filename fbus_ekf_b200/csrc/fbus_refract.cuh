@@ -191,3 +191,182 @@ FBUS_HD void marker_pose(const double* C, double rod_s, double rod_c, double* p,
 }
 
 }  // namespace fbus
+
+// =================================================================================================
+// R3 (north_star; NOT in the reference -> "parity unpinned"): Gauss-Newton refinement of the marker pose.
+// Minimises sum over 4 corners x 2 cameras of | pi_refr(x_c) - u |^2 over (R_M, p) in the flipped left-camera frame,
+// seeded by the closed-form solve above.  pi_refr = flat-port forward projection (air -> glass -> water): solve the
+// monotone equation  d0 t(s0) + d1 t(k1 s0) + (Z-d0-d1) t(k2 s0) = rho,  t(s) = s/sqrt(1-s^2),  for s0 = sin(theta_air)
+// (SURVEY A.1-4); Jacobian by the implicit-function theorem.  Right perturbation R_M <- R_M Exp(dphi).
+// =================================================================================================
+namespace fbus {
+
+struct GnConsts {
+    double d0, d1, k1, k2;       // air / glass thickness, n_air/n_glass, n_air/n_water
+    double R_RL_inv[9], P_LR[3];  // TRUE inverse of R_RL (the calibration is ~2.5e-6 non-orthonormal)
+    double size;                  // marker side (0.28 m, vision.hpp:114)
+};
+
+// projects X (camera frame) -> uv (2) and the 2x3 Jacobian d(uv)/dX (row-major J[0..2] = du/dX, J[3..5] = dv/dX)
+FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double* J) {
+    const double rho2 = X[0] * X[0] + X[1] * X[1];
+    const double Zw = X[2] - g.d0 - g.d1;
+    const double rho = sqrt(rho2);
+    if (rho < 1e-12) {  // paraxial limit
+        const double den = 1.0 / (g.d0 + g.k1 * g.d1 + g.k2 * Zw);
+        uv[0] = X[0] * den; uv[1] = X[1] * den;
+        J[0] = den; J[1] = 0.0; J[2] = -X[0] * den * den * g.k2;
+        J[3] = 0.0; J[4] = den; J[5] = -X[1] * den * den * g.k2;
+        return;
+    }
+    // Newton on f(s) = d0 t(s) + d1 t(k1 s) + Zw t(k2 s) - rho.  f is increasing and convex on [0,1): from the
+    // straight-line guess (left of the root) the first step lands right of it and the iteration then decreases
+    // monotonically to the root; the only safeguard needed is to stay inside the domain.
+    double s = rho / sqrt(rho2 + X[2] * X[2]);
+    double t0 = 0.0, t2 = 0.0, dt0 = 0.0, gs = 1.0;
+    for (int it = 0; it < 50; ++it) {
+        const double c0 = 1.0 / (1.0 - s * s), c1 = 1.0 / (1.0 - g.k1 * g.k1 * s * s), c2 = 1.0 / (1.0 - g.k2 * g.k2 * s * s);
+        const double r0 = sqrt(c0), r1 = sqrt(c1), r2 = sqrt(c2);
+        gs = g.d0 * c0 * r0 + g.d1 * g.k1 * c1 * r1 + Zw * g.k2 * c2 * r2;
+        const double f = g.d0 * s * r0 + g.d1 * g.k1 * s * r1 + Zw * g.k2 * s * r2 - rho;
+        double sn = s - f / gs;
+        if (!(sn < 1.0)) sn = 0.5 * (s + 1.0);
+        if (!(sn > 0.0)) sn = 0.5 * s;
+        const double ds = sn - s;
+        s = sn;
+        if ((ds < 0 ? -ds : ds) <= 2.3e-16 * s) break;
+    }
+    {   // values at the converged s
+        const double c0 = 1.0 / (1.0 - s * s), c1 = 1.0 / (1.0 - g.k1 * g.k1 * s * s), c2 = 1.0 / (1.0 - g.k2 * g.k2 * s * s);
+        const double r0 = sqrt(c0), r1 = sqrt(c1), r2 = sqrt(c2);
+        t0 = s * r0;
+        t2 = g.k2 * s * r2;
+        dt0 = c0 * r0;
+        gs = g.d0 * dt0 + g.d1 * g.k1 * c1 * r1 + Zw * g.k2 * c2 * r2;
+    }
+    const double ir = 1.0 / rho;
+    const double xh = X[0] * ir, yh = X[1] * ir;
+    uv[0] = t0 * xh; uv[1] = t0 * yh;
+    const double a = t0 * ir;      // tau / rho
+    const double b = dt0 / gs;     // t'(s0) / g_s
+    J[0] = a * (1.0 - xh * xh) + b * xh * xh; J[1] = (b - a) * xh * yh;
+    J[3] = J[1];                               J[4] = a * (1.0 - yh * yh) + b * yh * yh;
+    const double cz = -dt0 * t2 / gs;
+    J[2] = cz * xh; J[5] = cz * yh;
+}
+
+// residuals and normal equations for pose (Rm row-major 3x3, p) against the 16 observed coordinates c[16]
+// (Lx0,Ly0..Lx3,Ly3,Rx0..Ry3).  H: 6x6 lower-packed J^T J, gvec: J^T r, returns the cost sum r^2.
+FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm, const double* p, double* H, double* gvec) {
+    FBUS_UNROLL
+    for (int i = 0; i < 21; ++i) H[i] = 0.0;
+    FBUS_UNROLL
+    for (int i = 0; i < 6; ++i) gvec[i] = 0.0;
+    double cost = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        const double cm[3] = {(i == 1 || i == 2) ? g.size : 0.0, (i >= 2) ? g.size : 0.0, 0.0};  // (0,0),(s,0),(s,s),(0,s)
+        double Rc[3];
+        mat3_vec(Rm, cm, Rc);
+        const double XL[3] = {-(p[0] + Rc[0]), -(p[1] + Rc[1]), p[2] + Rc[2]};  // un-flip: F = diag(-1,-1,1)
+        // d XL / d(dp) = F ; d XL / d(dphi) = -F Rm [cm]x
+        double D[18];  // 3 x 6
+        FBUS_UNROLL
+        for (int r = 0; r < 3; ++r) {
+            const double fs = (r < 2) ? -1.0 : 1.0;
+            D[r * 6 + 0] = (r == 0) ? fs : 0.0; D[r * 6 + 1] = (r == 1) ? fs : 0.0; D[r * 6 + 2] = (r == 2) ? fs : 0.0;
+            // (Rm [cm]x)[r][:] = (Rm[r][1]cm2 - Rm[r][2]cm1, Rm[r][2]cm0 - Rm[r][0]cm2, Rm[r][0]cm1 - Rm[r][1]cm0)
+            D[r * 6 + 3] = -fs * (Rm[r * 3 + 1] * cm[2] - Rm[r * 3 + 2] * cm[1]);
+            D[r * 6 + 4] = -fs * (Rm[r * 3 + 2] * cm[0] - Rm[r * 3 + 0] * cm[2]);
+            D[r * 6 + 5] = -fs * (Rm[r * 3 + 0] * cm[1] - Rm[r * 3 + 1] * cm[0]);
+        }
+        for (int cam = 0; cam < 2; ++cam) {
+            double X[3], DX[18];
+            if (cam == 0) {
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r) X[r] = XL[r];
+                FBUS_UNROLL
+                for (int e = 0; e < 18; ++e) DX[e] = D[e];
+            } else {
+                const double dL[3] = {XL[0] - g.P_LR[0], XL[1] - g.P_LR[1], XL[2] - g.P_LR[2]};
+                mat3_vec(g.R_RL_inv, dL, X);
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r)
+                    FBUS_UNROLL
+                    for (int e = 0; e < 6; ++e)
+                        DX[r * 6 + e] = g.R_RL_inv[r * 3] * D[e] + g.R_RL_inv[r * 3 + 1] * D[6 + e] + g.R_RL_inv[r * 3 + 2] * D[12 + e];
+            }
+            double uv[2], Jp[6];
+            project_refr(g, X, uv, Jp);
+            const double ru = uv[0] - c[cam * 8 + 2 * i], rv = uv[1] - c[cam * 8 + 2 * i + 1];
+            cost += ru * ru + rv * rv;
+            double Ju[6], Jv[6];
+            FBUS_UNROLL
+            for (int e = 0; e < 6; ++e) {
+                Ju[e] = Jp[0] * DX[e] + Jp[1] * DX[6 + e] + Jp[2] * DX[12 + e];
+                Jv[e] = Jp[3] * DX[e] + Jp[4] * DX[6 + e] + Jp[5] * DX[12 + e];
+            }
+            FBUS_UNROLL
+            for (int a = 0; a < 6; ++a) {
+                gvec[a] += Ju[a] * ru + Jv[a] * rv;
+                FBUS_UNROLL
+                for (int b = 0; b <= a; ++b) H[a * (a + 1) / 2 + b] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+            }
+        }
+    }
+    return cost;
+}
+
+// Gauss-Newton iterations; Rm, p updated in place; returns the final cost (sum of squared residuals)
+FBUS_HD double gn_refine(const GnConsts& g, const double* c, double* Rm, double* p, int iters) {
+    double cost = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        double H[21], gv[6], Li[6], d[6];
+        cost = gn_normal_eq(g, c, Rm, p, H, gv);
+        CholStep<6, 0>::run(H, Li);
+        // solve H d = -g
+        FBUS_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            double s = -gv[i];
+            FBUS_UNROLL
+            for (int j = 0; j < i; ++j) s -= H[i * (i + 1) / 2 + j] * d[j];
+            d[i] = s * Li[i];
+        }
+        FBUS_UNROLL
+        for (int i = 5; i >= 0; --i) {
+            double s = d[i];
+            FBUS_UNROLL
+            for (int j = i + 1; j < 6; ++j) s -= H[j * (j + 1) / 2 + i] * d[j];
+            d[i] = s * Li[i];
+        }
+        p[0] += d[0]; p[1] += d[1]; p[2] += d[2];
+        // Rm <- Rm Exp(dphi)  (Rodrigues)
+        const double th2 = d[3] * d[3] + d[4] * d[4] + d[5] * d[5];
+        const double th = sqrt(th2);
+        double A, Bc;  // Exp = I + A [phi]x + Bc [phi]x^2
+        if (th < 1e-8) { A = 1.0 - th2 / 6.0; Bc = 0.5 - th2 / 24.0; }
+        else { double sn, cs; sincos(th, &sn, &cs); A = sn / th; Bc = (1.0 - cs) / th2; }
+        const double x = d[3], y = d[4], z = d[5];
+        const double E[9] = {1.0 - Bc * (y * y + z * z), -A * z + Bc * x * y, A * y + Bc * x * z,
+                             A * z + Bc * x * y, 1.0 - Bc * (x * x + z * z), -A * x + Bc * y * z,
+                             -A * y + Bc * x * z, A * x + Bc * y * z, 1.0 - Bc * (x * x + y * y)};
+        double Rn[9];
+        FBUS_UNROLL
+        for (int r = 0; r < 3; ++r)
+            FBUS_UNROLL
+            for (int cc = 0; cc < 3; ++cc) Rn[r * 3 + cc] = Rm[r * 3] * E[cc] + Rm[r * 3 + 1] * E[3 + cc] + Rm[r * 3 + 2] * E[6 + cc];
+        FBUS_UNROLL
+        for (int e = 0; e < 9; ++e) Rm[e] = Rn[e];
+    }
+    double H[21], gv[6];
+    cost = gn_normal_eq(g, c, Rm, p, H, gv);
+    return cost;
+}
+
+// closed-form seed as a rotation matrix + position (same algebra as marker_pose, which returns the quaternion)
+FBUS_HD void quat_to_rotmat_unit(const double* q, double* R) {
+    double qn[4] = {q[0], q[1], q[2], q[3]};
+    qnormalize(qn);
+    q2R(qn, R);
+}
+
+}  // namespace fbus

@@ -101,6 +101,18 @@ class BatchFilter:
     def RefractSolveDevice(self, corners_ptr: int, n: int, pose_ptr: int, c3_ptr: int | None, valid_ptr: int | None):
         self._ck(self._lib.fbus_refract_solve(self._h, corners_ptr, n, pose_ptr, c3_ptr, valid_ptr, capi.FBUS_MEM_DEVICE))
 
+    def RefractSolveGN(self, corners: np.ndarray, iters: int = 5):
+        """closed-form solve + Gauss-Newton refinement (R3).  corners float32 or float64 [16][n] ->
+        (pose [7][n], cost [n], valid [n])"""
+        assert corners.dtype in (np.float32, np.float64) and corners.flags["C_CONTIGUOUS"] and corners.shape[0] == 16
+        n = corners.shape[1]
+        pose = np.zeros((7, n))
+        cost = np.zeros(n)
+        valid = np.zeros(n, dtype=np.int32)
+        self._ck(self._lib.fbus_refract_solve_gn(self._h, corners.ctypes.data, 1 if corners.dtype == np.float64 else 0, n, iters,
+                                                 pose.ctypes.data, cost.ctypes.data, valid.ctypes.data, capi.FBUS_MEM_HOST))
+        return pose, cost, valid
+
     def MarkerPose(self, corners3d: np.ndarray):
         assert corners3d.dtype == np.float64 and corners3d.flags["C_CONTIGUOUS"] and corners3d.shape[0] == 12
         n = corners3d.shape[1]

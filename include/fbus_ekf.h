@@ -85,6 +85,7 @@ typedef struct fbus_config {
     double d_air, d_glass;
     double normal[3];
     double marker_dect_dist_thres; /* makrer_dect_dist_thres, vision.cpp:602 */
+    double marker_size;            /* marker side length, 0.28 m (vision.hpp:114); used only by the GN refinement */
     /* marker map (markersetup.yml / main.cpp:192-203); rotations are converted to quaternions with
        the Eigen Quaterniond(Matrix3d) rule exactly as main.cpp:201 does */
     int32_t n_markers;
@@ -214,6 +215,16 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
  */
 int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d,
                        int32_t* valid, int32_t mem);
+
+/*
+ * R3 (north_star; NOT in the reference, "parity unpinned"): the closed-form solve above followed by `iters`
+ * Gauss-Newton iterations on the stereo reprojection error through the flat port (16 residuals, 6 parameters,
+ * analytic Jacobians).  corner_dtype: 0 = float32 corners (as the reference holds them), 1 = float64.
+ *   pose [7][n]: refined p xyz, q wxyz of corner 0;  cost [n] or NULL: final sum of squared residuals;
+ *   valid [n] or NULL as fbus_refract_solve.  Checked against oracle/fbus_oracle_np.py and synthetic ground truth.
+ */
+int fbus_refract_solve_gn(fbus_handle* h, const void* corners, int32_t corner_dtype, size_t n, int32_t iters, double* pose,
+                          double* cost, int32_t* valid, int32_t mem);
 
 /* VISION::ComputeMarkerPose alone (vision.cpp:624-759) from 3-D corners [12][n] (the land
    data/corners.txt layout, vision.cpp:120-124). */

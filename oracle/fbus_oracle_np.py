@@ -347,9 +347,10 @@ class Filter:
 
 
 # ----------------------------------------------------------------------------- refraction (R1, R2)
-def refraction_triangulation(k: Consts, c16):
-    """vision.cpp:488-608.  c16: 16 float32-valued numbers (L xy x4, R xy x4). -> (4x3 corners, ok)"""
-    c16 = np.asarray(c16, dtype=np.float32).astype(np.float64)
+def refraction_triangulation(k: Consts, c16, as_float32=True):
+    """vision.cpp:488-608.  c16: 16 numbers (L xy x4, R xy x4), rounded to float32 like cv::Point2f unless
+    as_float32=False. -> (4x3 corners, ok)"""
+    c16 = np.asarray(c16, dtype=np.float32).astype(np.float64) if as_float32 else np.asarray(c16, dtype=np.float64)
     cfg = k.cfg
     nv = np.array(cfg.normal, dtype=np.float64)
     out = np.zeros((4, 3))
@@ -479,3 +480,83 @@ def replay(cfg: Config, imu, image_rows, n_init=500, use_iir=False, joseph=False
             covs.append(f.P.copy())
     return {"rows": np.array(rows), "P": np.array(covs) if trace_cov else None, "filter": f, "win_off": off,
             "frames": frames, "imu": imu}
+
+
+# ----------------------------------------------------------------------------- R3: Gauss-Newton refinement
+# NOT in the reference ("parity unpinned").  Independent restatement of the formulation
+# the CUDA kernel implements: flat-port forward projection by a bracketing root finder (the kernel uses Newton), Jacobian
+# by the implicit-function theorem, 6x6 normal equations solved by LAPACK (the kernel uses Cholesky).
+def project_refr(cfg: Config, X):
+    """X: point in a camera's own frame -> (uv[2], J[2x3])"""
+    from scipy.optimize import brentq
+    d0, d1 = cfg.d_air, cfg.d_glass
+    k1, k2 = cfg.n_air / cfg.n_glass, cfg.n_air / cfg.n_water
+    rho = np.hypot(X[0], X[1])
+    Zw = X[2] - d0 - d1
+    t = lambda s: s / np.sqrt(1 - s * s)
+    dt = lambda s: (1 - s * s) ** -1.5
+    if rho < 1e-12:
+        den = 1.0 / (d0 + k1 * d1 + k2 * Zw)
+        J = np.array([[den, 0, -X[0] * den * den * k2], [0, den, -X[1] * den * den * k2]])
+        return np.array([X[0] * den, X[1] * den]), J
+    f = lambda s: d0 * t(s) + d1 * t(k1 * s) + Zw * t(k2 * s) - rho
+    s0 = brentq(f, 0.0, 1 - 1e-14, xtol=1e-17, rtol=8.9e-16, maxiter=200)
+    xh = np.array([X[0], X[1]]) / rho
+    tau = t(s0)
+    gs = d0 * dt(s0) + d1 * k1 * dt(k1 * s0) + Zw * k2 * dt(k2 * s0)
+    Jxy = (tau / rho) * (np.eye(2) - np.outer(xh, xh)) + (dt(s0) / gs) * np.outer(xh, xh)
+    Jz = -dt(s0) * t(k2 * s0) / gs * xh
+    return tau * xh, np.column_stack([Jxy, Jz])
+
+
+def gn_residuals(k: Consts, c16, Rm, p, size=0.28):
+    """-> (r[16] ordered Lx0,Ly0..Lx3,Ly3,Rx0..Ry3, J[16x6] w.r.t. (dp, dphi) with R <- R Exp(dphi))"""
+    cfg = k.cfg
+    F = np.diag([-1.0, -1.0, 1.0])
+    Rinv = np.linalg.inv(k.R_RL)
+    cm = np.array([[0, 0, 0], [size, 0, 0], [size, size, 0], [0, size, 0]], dtype=np.float64)
+    r = np.zeros(16)
+    J = np.zeros((16, 6))
+    for i in range(4):
+        XL = F @ (p + Rm @ cm[i])
+        D = np.column_stack([F, -F @ Rm @ skew(cm[i])])
+        for cam in range(2):
+            if cam == 0:
+                X, DX = XL, D
+            else:
+                X, DX = Rinv @ (XL - k.P_LR), Rinv @ D
+            uv, Jp = project_refr(cfg, X)
+            r[cam * 8 + 2 * i:cam * 8 + 2 * i + 2] = uv - c16[cam * 8 + 2 * i:cam * 8 + 2 * i + 2]
+            J[cam * 8 + 2 * i:cam * 8 + 2 * i + 2, :] = Jp @ DX
+    return r, J
+
+
+def so3_exp(phi):
+    th = np.linalg.norm(phi)
+    K = skew(phi)
+    if th < 1e-8:
+        return np.eye(3) + K + 0.5 * K @ K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+
+
+def gn_refine(k: Consts, c16, Rm, p, iters=5, size=0.28):
+    c16 = np.asarray(c16, dtype=np.float64)
+    Rm, p = np.array(Rm, dtype=np.float64), np.array(p, dtype=np.float64)
+    for _ in range(iters):
+        r, J = gn_residuals(k, c16, Rm, p, size)
+        d = np.linalg.solve(J.T @ J, -J.T @ r)
+        p = p + d[:3]
+        Rm = Rm @ so3_exp(d[3:])
+    r, _ = gn_residuals(k, c16, Rm, p, size)
+    return Rm, p, float(r @ r)
+
+
+def refract_solve_gn(k: Consts, c16, iters=5, size=0.28):
+    """closed form (R1+R2) then GN; c16 are the coordinates as given (float32- or float64-valued)"""
+    C, ok = refraction_triangulation(k, c16, as_float32=False)
+    if not ok:
+        return None
+    p, q, _ = compute_marker_pose(C)
+    qn = q / np.linalg.norm(q)
+    Rm, p, cost = gn_refine(k, c16, q2R(qn), p, iters, size)
+    return p, R2q(Rm), cost

@@ -89,3 +89,33 @@ int hm_marker_pose(const fbus_config* cfg, const double* c3d, double* pose) {
     return 0;
 }
 }
+
+extern "C" {
+// R3: closed form + GN on one marker; c16 double; returns valid flag; pose[7], cost
+int hm_refract_gn(const fbus_config* cfg, const double* c16, int iters, double* pose, double* cost) {
+    DevConsts k;
+    MarkerTable tab;
+    if (make_dev_consts(cfg, &k, &tab)) return -1;
+    GnConsts g;
+    make_gn_consts(cfg, &k, &g);
+    double C[12];
+    int ok = 1;
+    for (int i = 0; i < 4; ++i)
+        if (triangulate_corner(k, c16[2 * i], c16[2 * i + 1], c16[8 + 2 * i], c16[8 + 2 * i + 1], C + 3 * i) > k.dect_thres) ok = 0;
+    marker_pose(C, k.rod_s, k.rod_c, pose, pose + 3);
+    double Rm[9];
+    quat_to_rotmat_unit(pose + 3, Rm);
+    *cost = gn_refine(g, c16, Rm, pose, iters);
+    R2q(Rm, pose + 3);
+    return ok;
+}
+// projection + Jacobian of one point (for finite-difference checks)
+void hm_project_refr(const fbus_config* cfg, const double* X, double* uv, double* J) {
+    DevConsts k;
+    MarkerTable tab;
+    make_dev_consts(cfg, &k, &tab);
+    GnConsts g;
+    make_gn_consts(cfg, &k, &g);
+    project_refr(g, X, uv, J);
+}
+}
