@@ -226,6 +226,12 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     int inited = prm.init[b];
     int status = prm.status[b];
     uint32_t cursor = fused ? prm.win_off[prm.w0] : 0u;
+    // prefetched inputs of the NEXT frame (issued while this warp waits for the covariance warp's update): frame time,
+    // detection slot 0, and the first IMU sample of the next window
+    uint32_t pf_w = 0xffffffffu, pf_i = 0xffffffffu;
+    int pf_id = -1;
+    double pf_tdet = 0.0, pf_pose[7], pf_st = 0.0, pf_sd[6];
+    const bool uses_det = (mode & (M_INIT | M_RESET | M_UPDATE | M_FUSED)) != 0;
 
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
         bool do_prop = false, do_update = false;
@@ -237,15 +243,16 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             // ---- scan this frame's detections (filter.cpp:329-341 / 418-430 / 639-658) ----------------
             int idx_near = 0, idx_prev = 0;
             double md = 10.0, prev_dist = 0.0;
-            const bool uses_det = (mode & (M_INIT | M_RESET | M_UPDATE | M_FUSED)) != 0;
             if (uses_det) {
-                t_det = prm.det_t[w];
+                const bool pf = (pf_w == w);
+                t_det = pf ? pf_tdet : prm.det_t[w];
                 for (int s = 0; s < prm.m; ++s) {
                     const size_t slot = (size_t)w * prm.m + s;
-                    const int id = prm.det_id[slot * B + b];
+                    const bool use_pf = pf && s == 0;
+                    const int id = use_pf ? pf_id : prm.det_id[slot * B + b];
                     if (id < 0) continue;
                     const double* pp = prm.det_pose + slot * 7 * B + b;
-                    const double px = pp[0], py = pp[B], pz = pp[2 * B];
+                    const double px = use_pf ? pf_pose[0] : pp[0], py = use_pf ? pf_pose[1] : pp[B], pz = use_pf ? pf_pose[2] : pp[2 * B];
                     const double dist = sqrt(px * px + py * py + pz * pz);
                     if (n_det == 0) { idx_near = s; idx_prev = s; }  // detectionResult_[0] defaults (min_dist_id = 0)
                     if (dist < md) { md = dist; idx_near = s; }
@@ -294,12 +301,13 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                 double dp[3], dq[4];
                 if (ok) {
                     const size_t slot = (size_t)w * prm.m + idx_near;
-                    const int did = prm.det_id[slot * B + b];
+                    const bool use_pf = (pf_w == w) && idx_near == 0;
+                    const int did = use_pf ? pf_id : prm.det_id[slot * B + b];
                     const double* pp = prm.det_pose + slot * 7 * B + b;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) dp[c] = pp[(size_t)c * B];
+                    for (int c = 0; c < 3; ++c) dp[c] = use_pf ? pf_pose[c] : pp[(size_t)c * B];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) dq[c] = pp[(size_t)(3 + c) * B];
+                    for (int c = 0; c < 4; ++c) dq[c] = use_pf ? pf_pose[3 + c] : pp[(size_t)(3 + c) * B];
                     mk = find_marker(k, prm.tab, did);
                     ok = mk >= 0;
                 }
@@ -380,9 +388,10 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             const double start = n.t;
             bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
             uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
-            double s_t = prm.imu_t[lo], s_d[6];
+            const bool pfi = (pf_i == lo);
+            double s_t = pfi ? pf_st : prm.imu_t[lo], s_d[6];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)lo * 6 + c) * B + b];
+            for (int c = 0; c < 6; ++c) s_d[c] = pfi ? pf_sd[c] : prm.imu[((size_t)lo * 6 + c) * B + b];
             for (uint32_t i = lo; i < hi; ++i) {
                 const double ti = s_t;
                 double d[6];
@@ -476,14 +485,15 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         int req_old = 0;
         if (do_update && n_det > 0) {
             const size_t slot = (size_t)w * prm.m + idx_upd;
-            const int did = prm.det_id[slot * B + b];
+            const bool use_pf = (pf_w == w) && idx_upd == 0;
+            const int did = use_pf ? pf_id : prm.det_id[slot * B + b];
             const int mk = find_marker(k, prm.tab, did);
             if (mk >= 0) {
                 prev_id = did;
                 req_old = mk + 1;
                 const double* pp = prm.det_pose + slot * 7 * B + b;
 #pragma unroll
-                for (int c = 0; c < 7; ++c) X[(size_t)c * BSF] = pp[(size_t)c * B];  // yP (3), yQ (4)
+                for (int c = 0; c < 7; ++c) X[(size_t)c * BSF] = use_pf ? pf_pose[c] : pp[(size_t)c * B];  // yP (3), yQ (4)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) X[(size_t)(7 + c) * BSF] = n.q[c];
 #pragma unroll
@@ -498,6 +508,24 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         {
             const int wany = __any_sync(0xffffffffu, req_old != 0);
             if ((fl & 31) == 0) sh.any_upd[wq] = wany;
+        }
+        // prefetch the next frame's inputs; the loads complete while this warp waits for the update
+        if (w + 1 < prm.w1) {
+            if (uses_det) {
+                const size_t slot = (size_t)(w + 1) * prm.m;
+                pf_w = w + 1;
+                pf_tdet = prm.det_t[w + 1];
+                pf_id = prm.det_id[slot * B + b];
+                const double* pp = prm.det_pose + slot * 7 * B + b;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) pf_pose[c] = pp[(size_t)c * B];
+            }
+            if (fused && cursor < prm.win_off[prm.w1]) {
+                pf_i = cursor;
+                pf_st = prm.imu_t[cursor];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) pf_sd[c] = prm.imu[((size_t)cursor * 6 + c) * B + b];
+            }
         }
         cta_bar<NT>();  // (c)
         int any = sh.any_upd[0];

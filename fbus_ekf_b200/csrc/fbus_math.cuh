@@ -103,8 +103,17 @@ FBUS_HD void qmul_conjb(const double* a, const double* b, double* o) {  // a * c
     const double bb[4] = {b[0], -b[1], -b[2], -b[3]};
     qmul(a, bb, o);
 }
+// reciprocal square root: one MUFU.RSQ64H + Newton steps on the device (1-2 ulp) instead of a correctly rounded
+// sqrt followed by a correctly rounded division (~4x the instructions); the host build keeps 1/sqrt
+FBUS_HD double rsqrt_d(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 FBUS_HD void qnormalize(double* q) {
-    const double inv = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double inv = rsqrt_d(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
 }
 FBUS_HD void q2R(const double* q, double* R) {  // Eigen toRotationMatrix, literal also for non-unit q
@@ -597,23 +606,24 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
     double w[3];
     FBUS_UNROLL
     for (int i = 0; i < 3; ++i) w[i] = gyro[i] - n.bg[i];
-    const double wn = norm3(w);
+    const double wn2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    const double inv = rsqrt_d(wn2);  // 1/|w| (inf for w = 0: only used in the branch below)
+    const double wn = wn2 * inv;      // |w|
     double R0[9], qh[4], qn[4];
     q2R(n.q, R0);
     if (wn > 10e-5) {
-        const double inv = 1.0 / wn;
         const double ax[3] = {w[0] * inv, w[1] * inv, w[2] * inv};
         // one sincos: the half-interval quaternion needs angle/2 = wn*dt/4, the full one twice that
         // (double-angle identities; ~1 ulp from evaluating sin/cos of wn*dt/2 directly)
         double sh, ch;
-        sincos(wn * dt / 2 / 2, &sh, &ch);
+        sincos(wn * dt * 0.25, &sh, &ch);
         const double sf = 2.0 * sh * ch, cf = 1.0 - 2.0 * sh * sh;
         const double dqh[4] = {ch, sh * ax[0], sh * ax[1], sh * ax[2]};
         const double dq[4] = {cf, sf * ax[0], sf * ax[1], sf * ax[2]};
         qmul(n.q, dqh, qh);
         qmul(n.q, dq, qn);
     } else {
-        const double dqh[4] = {1.0, 0.5 * dt * w[0] / 2, 0.5 * dt * w[1] / 2, 0.5 * dt * w[2] / 2};
+        const double dqh[4] = {1.0, 0.25 * dt * w[0], 0.25 * dt * w[1], 0.25 * dt * w[2]};
         const double dq[4] = {1.0, 0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
         qmul(n.q, dqh, qh);
         qmul(n.q, dq, qn);
@@ -631,7 +641,7 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
     mat3_vec(R0, a, k1);
     mat3_vec(Rh, a, k2);
     mat3_vec(n.R, a, k4);
-    const double dt6 = dt / 6, dt2 = dt / 2;
+    const double dt6 = dt * (1.0 / 6.0), dt2 = dt * 0.5;
     FBUS_UNROLL
     for (int i = 0; i < 3; ++i) {
         const double kv1 = k1[i] + n.g[i], kv2 = k2[i] + n.g[i], kv4 = k4[i] + n.g[i];
