@@ -112,6 +112,19 @@ FBUS_HD double rsqrt_d(double x) {
     return 1.0 / sqrt(x);
 #endif
 }
+// reciprocal: hardware seed (~20 bits) + two Newton steps (~1 ulp), without the slow-path call of a correctly rounded
+// division; arguments here are well inside the normal range
+FBUS_HD double rcp_d(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
 FBUS_HD void qnormalize(double* q) {
     const double inv = rsqrt_d(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
@@ -700,8 +713,8 @@ struct CholStep {
         double s = L[J * (J + 1) / 2 + J];
         FBUS_UNROLL
         for (int c = 0; c < J; ++c) s -= L[J * (J + 1) / 2 + c] * L[J * (J + 1) / 2 + c];
-        const double d = sqrt(s);
-        const double di = 1.0 / d;
+        const double di = rsqrt_d(s);  // 1/sqrt(s) by MUFU.RSQ64H + Newton (1-2 ulp); d = s * di
+        const double d = s * di;
         L[J * (J + 1) / 2 + J] = d;
         Li[J] = di;
         FBUS_UNROLL
@@ -983,10 +996,13 @@ FBUS_HD void inject_error_state(Nominal& n, const double* dx) {
         n.g[i] += dx[15 + i];
     }
     // VectorToQuaterniond (matrix_math.hpp:90-99): v/|v| * sin(|v|/2); NaN at exactly zero, as the reference
-    const double vn = norm3(dx + 6);
+    const double v2 = dx[6] * dx[6] + dx[7] * dx[7] + dx[8] * dx[8];
+    const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
+    const double vn = v2 * iv;
     double sh, ch;
-    sincos(vn / 2, &sh, &ch);
-    const double dq[4] = {ch, dx[6] / vn * sh, dx[7] / vn * sh, dx[8] / vn * sh};
+    sincos(vn * 0.5, &sh, &ch);
+    const double sc = iv * sh;
+    const double dq[4] = {ch, dx[6] * sc, dx[7] * sc, dx[8] * sc};
     double qn[4];
     qmul(n.q, dq, qn);
     qnormalize(qn);
@@ -1116,10 +1132,13 @@ FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, 
             P.st(i, j, v);
         }
     {   // VectorToQuaterniond (matrix_math.hpp:90-99): v/|v| * sin(|v|/2); NaN at exactly zero, as the reference
-        const double vn = norm3(dth);
+        const double v2 = dth[0] * dth[0] + dth[1] * dth[1] + dth[2] * dth[2];
+        const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
+        const double vn = v2 * iv;
         double sh, ch;
-        sincos(vn / 2, &sh, &ch);
-        const double dq[4] = {ch, dth[0] / vn * sh, dth[1] / vn * sh, dth[2] / vn * sh};
+        sincos(vn * 0.5, &sh, &ch);
+        const double sc = iv * sh;
+        const double dq[4] = {ch, dth[0] * sc, dth[1] * sc, dth[2] * sc};
         double qn[4];
         qmul(n.q, dq, qn);
         qnormalize(qn);

@@ -32,7 +32,7 @@ FBUS_HD double det3_cols(const double* a, const double* b, const double* c) {  /
 FBUS_HD double triangulate_corner(const DevConsts& k, double xl, double yl, double xr, double yr, double* Pout) {
     double r0L[3] = {xl, yl, 1.0}, r0R[3] = {xr, yr, 1.0};
     {
-        const double il = 1.0 / norm3(r0L), ir = 1.0 / norm3(r0R);
+        const double il = rsqrt_d(r0L[0] * r0L[0] + r0L[1] * r0L[1] + 1.0), ir = rsqrt_d(r0R[0] * r0R[0] + r0R[1] * r0R[1] + 1.0);
         FBUS_UNROLL
         for (int j = 0; j < 3; ++j) { r0L[j] *= il; r0R[j] *= ir; }
     }
@@ -43,7 +43,7 @@ FBUS_HD double triangulate_corner(const DevConsts& k, double xl, double yl, doub
     refract_ray(r1R, k.normal, k.a1, k.glass_gt_water, r2R, &v1R);
     double P1L[3], P1R[3];
     {
-        const double s0L = k.d_air / v0L, s0R = k.d_air / v0R, s1L = k.d_glass / v1L, s1R = k.d_glass / v1R;
+        const double s0L = k.d_air * rcp_d(v0L), s0R = k.d_air * rcp_d(v0R), s1L = k.d_glass * rcp_d(v1L), s1R = k.d_glass * rcp_d(v1R);
         FBUS_UNROLL
         for (int j = 0; j < 3; ++j) {
             P1L[j] = s0L * r0L[j] + s1L * r1L[j];
@@ -57,7 +57,7 @@ FBUS_HD double triangulate_corner(const DevConsts& k, double xl, double yl, doub
     for (int j = 0; j < 3; ++j) pR[j] += k.P_LR[j];
     const double c[3] = {r2L[1] * rR[2] - r2L[2] * rR[1], r2L[2] * rR[0] - r2L[0] * rR[2], r2L[0] * rR[1] - r2L[1] * rR[0]};
     const double d[3] = {pR[0] - P1L[0], pR[1] - P1L[1], pR[2] - P1L[2]};
-    const double inv3 = 1.0 / det3_cols(c, r2L, rR);
+    const double inv3 = rcp_d(det3_cols(c, r2L, rR));
     const double t1 = det3_cols(c, d, rR) * inv3;
     const double t2 = -det3_cols(c, r2L, d) * inv3;
     double P[3];
@@ -83,22 +83,23 @@ FBUS_HD void null_vec(const double* M, double lam, double* v) {
     double b0 = c0[0], b1 = c0[1], b2 = c0[2], nb = n0;
     if (n1 > nb) { b0 = c1[0]; b1 = c1[1]; b2 = c1[2]; nb = n1; }
     if (n2 > nb) { b0 = c2[0]; b1 = c2[1]; b2 = c2[2]; nb = n2; }
-    const double inv = 1.0 / sqrt(nb);
+    const double inv = rsqrt_d(nb);
     v[0] = b0 * inv; v[1] = b1 * inv; v[2] = b2 * inv;
 }
 FBUS_HD void smallest_eigvec_sym3(const double* M, double* z) {
-    const double q = (M[0] + M[4] + M[8]) / 3.0;
+    const double q = (M[0] + M[4] + M[8]) * (1.0 / 3.0);
     const double p1 = M[1] * M[1] + M[2] * M[2] + M[5] * M[5];
     const double a = M[0] - q, b = M[4] - q, c = M[8] - q;
     const double p2 = a * a + b * b + c * c + 2.0 * p1;
-    const double p = sqrt(p2 / 6.0);
+    const double ip0 = rsqrt_d(p2 * (1.0 / 6.0));
+    const double p = p2 * (1.0 / 6.0) * ip0;
     double lam = q;
     if (p > 0.0) {
-        const double ip = 1.0 / p;
+        const double ip = ip0;
         const double B0 = a * ip, B4 = b * ip, B8 = c * ip, B1 = M[1] * ip, B2 = M[2] * ip, B5 = M[5] * ip;
         double r = 0.5 * (B0 * (B4 * B8 - B5 * B5) - B1 * (B1 * B8 - B5 * B2) + B2 * (B1 * B5 - B4 * B2));
         r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-        const double phi = acos(r) / 3.0;
+        const double phi = acos(r) * (1.0 / 3.0);
         lam = q + 2.0 * p * cos(phi + 2.0943951023931953);  // smallest eigenvalue
     }
     double v[3];
@@ -163,7 +164,8 @@ FBUS_HD void marker_pose(const double* C, double rod_s, double rod_c, double* p,
         double V12[3], V14[3];
         FBUS_UNROLL
         for (int j = 0; j < 3; ++j) { V12[j] = P2[j] - P1[j]; V14[j] = P4[j] - P1[j]; }
-        const double i12 = 1.0 / norm3(V12), i14 = 1.0 / norm3(V14);
+        const double i12 = rsqrt_d(V12[0] * V12[0] + V12[1] * V12[1] + V12[2] * V12[2]);
+        const double i14 = rsqrt_d(V14[0] * V14[0] + V14[1] * V14[1] + V14[2] * V14[2]);
         FBUS_UNROLL
         for (int j = 0; j < 3; ++j) m[j] = V12[j] * i12 + V14[j] * i14;
     }
@@ -180,7 +182,7 @@ FBUS_HD void marker_pose(const double* C, double rod_s, double rod_c, double* p,
         Rm[0] = ca[0] * Z[0] + rod_c; Rm[4] = ca[1] * Z[1] + rod_c; Rm[8] = ca[2] * Z[2] + rod_c;
         double Rmm[3];
         mat3_vec(Rm, m, Rmm);
-        const double im = 1.0 / norm3(m);
+        const double im = rsqrt_d(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
         FBUS_UNROLL
         for (int j = 0; j < 3; ++j) X[j] = Rmm[j] * im;
     }
@@ -222,14 +224,14 @@ FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double
     // Newton on f(s) = d0 t(s) + d1 t(k1 s) + Zw t(k2 s) - rho.  f is increasing and convex on [0,1): from the
     // straight-line guess (left of the root) the first step lands right of it and the iteration then decreases
     // monotonically to the root; the only safeguard needed is to stay inside the domain.
-    double s = rho / sqrt(rho2 + X[2] * X[2]);
+    double s = rho * rsqrt_d(rho2 + X[2] * X[2]);
     double t0 = 0.0, t2 = 0.0, dt0 = 0.0, gs = 1.0;
     for (int it = 0; it < 50; ++it) {
-        const double c0 = 1.0 / (1.0 - s * s), c1 = 1.0 / (1.0 - g.k1 * g.k1 * s * s), c2 = 1.0 / (1.0 - g.k2 * g.k2 * s * s);
-        const double r0 = sqrt(c0), r1 = sqrt(c1), r2 = sqrt(c2);
+        const double r0 = rsqrt_d(1.0 - s * s), r1 = rsqrt_d(1.0 - g.k1 * g.k1 * s * s), r2 = rsqrt_d(1.0 - g.k2 * g.k2 * s * s);
+        const double c0 = r0 * r0, c1 = r1 * r1, c2 = r2 * r2;
         gs = g.d0 * c0 * r0 + g.d1 * g.k1 * c1 * r1 + Zw * g.k2 * c2 * r2;
         const double f = g.d0 * s * r0 + g.d1 * g.k1 * s * r1 + Zw * g.k2 * s * r2 - rho;
-        double sn = s - f / gs;
+        double sn = s - f * rcp_d(gs);
         if (!(sn < 1.0)) sn = 0.5 * (s + 1.0);
         if (!(sn > 0.0)) sn = 0.5 * s;
         const double ds = sn - s;
@@ -237,21 +239,22 @@ FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double
         if ((ds < 0 ? -ds : ds) <= 2.3e-16 * s) break;
     }
     {   // values at the converged s
-        const double c0 = 1.0 / (1.0 - s * s), c1 = 1.0 / (1.0 - g.k1 * g.k1 * s * s), c2 = 1.0 / (1.0 - g.k2 * g.k2 * s * s);
-        const double r0 = sqrt(c0), r1 = sqrt(c1), r2 = sqrt(c2);
+        const double r0 = rsqrt_d(1.0 - s * s), r1 = rsqrt_d(1.0 - g.k1 * g.k1 * s * s), r2 = rsqrt_d(1.0 - g.k2 * g.k2 * s * s);
+        const double c0 = r0 * r0, c1 = r1 * r1, c2 = r2 * r2;
         t0 = s * r0;
         t2 = g.k2 * s * r2;
         dt0 = c0 * r0;
         gs = g.d0 * dt0 + g.d1 * g.k1 * c1 * r1 + Zw * g.k2 * c2 * r2;
     }
-    const double ir = 1.0 / rho;
+    const double ir = rcp_d(rho);
     const double xh = X[0] * ir, yh = X[1] * ir;
     uv[0] = t0 * xh; uv[1] = t0 * yh;
     const double a = t0 * ir;      // tau / rho
-    const double b = dt0 / gs;     // t'(s0) / g_s
+    const double igs = rcp_d(gs);
+    const double b = dt0 * igs;    // t'(s0) / g_s
     J[0] = a * (1.0 - xh * xh) + b * xh * xh; J[1] = (b - a) * xh * yh;
     J[3] = J[1];                               J[4] = a * (1.0 - yh * yh) + b * yh * yh;
-    const double cz = -dt0 * t2 / gs;
+    const double cz = -dt0 * t2 * igs;
     J[2] = cz * xh; J[5] = cz * yh;
 }
 
