@@ -75,6 +75,11 @@ struct fbus_handle {
     int32_t* d_init = nullptr;
     int32_t* d_status = nullptr;
     DevBuf imu_t, det_t, win_off, imu_data, det_id, det_pose, trace, scratch_in, scratch_out, scratch_aux, stats_partial, stats_out;
+    // second staging set + copy stream: host-resident streams are copied chunk c+1 while chunk c is computed
+    DevBuf imu_data2, det_id2, det_pose2;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    size_t pipeline_frames = 2;  // frames per chunk of the host-stream pipeline (FBUS_PIPELINE_FRAMES, 0 = off)
     std::string err;
 };
 
@@ -94,15 +99,19 @@ int fail(fbus_handle* h, int code, const std::string& msg) {
 
 // stage a caller array on the device if it lives on the host; returns the device pointer to use
 template <class T>
-int stage(fbus_handle* h, DevBuf& buf, const T* src, size_t count, int mem, const T** out) {
+int stage_on(fbus_handle* h, DevBuf& buf, const T* src, size_t count, int mem, const T** out, cudaStream_t st) {
     if (mem == FBUS_MEM_DEVICE) {
         *out = src;
         return FBUS_OK;
     }
     CUDA_TRY(h, buf.reserve(count * sizeof(T)));
-    CUDA_TRY(h, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
     *out = (const T*)buf.p;
     return FBUS_OK;
+}
+template <class T>
+int stage(fbus_handle* h, DevBuf& buf, const T* src, size_t count, int mem, const T** out) {
+    return stage_on(h, buf, src, count, mem, out, h->stream);
 }
 
 int launch_window(fbus_handle* h, WinParams& prm) {
@@ -117,7 +126,8 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.stagger_cycles = (prm.mode & M_FUSED) ? h->stagger_cycles : 0u;
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
 #if FBUS_SPLIT
-    ekf_window_split_kernel<WIN_BS><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
+    if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_split_kernel<WIN_BS, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
+    else ekf_window_split_kernel<WIN_BS, false><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
 #else
     ekf_window_kernel<WIN_BS><<<grid, WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
 #endif
@@ -125,7 +135,8 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     return FBUS_OK;
 }
 
-int stage_det(fbus_handle* h, const fbus_det_frames* det, size_t w0, size_t w1, WinParams& prm) {
+int stage_det(fbus_handle* h, const fbus_det_frames* det, size_t w0, size_t w1, WinParams& prm, int bufset = 0,
+              cudaStream_t big_stream = nullptr) {
     if (!det || det->batch != h->B || w1 > det->n_frames || w0 > w1 || det->max_markers == 0 || !det->t || !det->id || !det->pose)
         return fail(h, FBUS_E_BADARG, "bad detection frames");
     const size_t m = det->max_markers, B = h->B, nw = w1 - w0;
@@ -135,9 +146,10 @@ int stage_det(fbus_handle* h, const fbus_det_frames* det, size_t w0, size_t w1, 
     if (rc) return rc;
     const int32_t* did;
     const double* dpose;
-    rc = stage(h, h->det_id, det->id + w0 * m * B, nw * m * B, det->mem, &did);
+    cudaStream_t bs = big_stream ? big_stream : h->stream;
+    rc = stage_on(h, bufset ? h->det_id2 : h->det_id, det->id + w0 * m * B, nw * m * B, det->mem, &did, bs);
     if (rc) return rc;
-    rc = stage(h, h->det_pose, det->pose + w0 * m * 7 * B, nw * m * 7 * B, det->mem, &dpose);
+    rc = stage_on(h, bufset ? h->det_pose2 : h->det_pose, det->pose + w0 * m * 7 * B, nw * m * 7 * B, det->mem, &dpose, bs);
     if (rc) return rc;
     prm.det_t = dt;
     prm.det_id = did;
@@ -188,6 +200,12 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate(copy)", e);
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    if (const char* pf = getenv("FBUS_PIPELINE_FRAMES")) h->pipeline_frames = (size_t)strtoul(pf, nullptr, 10);
     if ((e = cudaMalloc(&h->d_nom, sizeof(double) * NOM_FIELDS * batch)) != cudaSuccess) return bail("cudaMalloc nom", e);
     if ((e = cudaMalloc(&h->d_P, sizeof(double) * NPK * batch)) != cudaSuccess) return bail("cudaMalloc P", e);
     if ((e = cudaMalloc(&h->d_prev, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc prev", e);
@@ -202,7 +220,8 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     if ((e = cudaMalloc(&h->d_tab, sizeof(MarkerTable))) != cudaSuccess) return bail("cudaMalloc marker table", e);
     if ((e = cudaMemcpy(h->d_tab, &h->tab, sizeof(MarkerTable), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("marker table copy", e);
 #if FBUS_SPLIT
-    e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+    e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
 #else
     e = cudaFuncSetAttribute(ekf_window_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
 #endif
@@ -210,7 +229,7 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     if (getenv("FBUS_DEBUG")) {
         int nb = -1;
 #if FBUS_SPLIT
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_window_split_kernel<WIN_BS>, 2 * WIN_BS, WIN_SMEM);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_window_split_kernel<WIN_BS, false>, 2 * WIN_BS, WIN_SMEM);
 #else
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_window_kernel<WIN_BS>, WIN_BS, WIN_SMEM);
 #endif
@@ -230,7 +249,12 @@ int fbus_destroy(fbus_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nom); cudaFree(h->d_P); cudaFree(h->d_prev); cudaFree(h->d_init); cudaFree(h->d_status); cudaFree(h->d_tab); cudaFree(h->d_ticket);
-    DevBuf* bufs[] = {&h->imu_t, &h->det_t, &h->win_off, &h->imu_data, &h->det_id, &h->det_pose, &h->trace,
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    DevBuf* bufs[] = {&h->imu_data2, &h->det_id2, &h->det_pose2, &h->imu_t, &h->det_t, &h->win_off, &h->imu_data, &h->det_id, &h->det_pose, &h->trace,
                       &h->scratch_in, &h->scratch_out, &h->scratch_aux, &h->stats_partial, &h->stats_out};
     for (DevBuf* b : bufs) b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -318,20 +342,17 @@ int fbus_update(fbus_handle* h, const fbus_det_frames* det, size_t frame) {
     return launch_window(h, prm);
 }
 
-int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det_frames* det, const uint32_t* win_off,
-                      size_t w0, size_t w1, double* trace, int32_t trace_mem) {
-    if (!h || !imu || !det || !win_off || imu->batch != h->B || !imu->t || !imu->data)
-        return fail(h, FBUS_E_BADARG, "fbus_step_windows: bad argument");
-    if (w0 >= w1) return (w0 == w1) ? FBUS_OK : fail(h, FBUS_E_BADARG, "fbus_step_windows: w0 > w1");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+// one launch of the fused window kernel for frames [w0, w1).  With a copy stream the bulky host arrays of this
+// chunk are copied on that stream into staging set `bufset` and the kernel waits for them through an event, so the
+// copy of the next chunk overlaps this chunk's kernel.
+static int step_windows_chunk(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det_frames* det, const uint32_t* win_off,
+                              size_t w0, size_t w1, double* trace, int32_t trace_mem, int bufset, cudaStream_t copy_stream) {
     const size_t B = h->B, nw = w1 - w0;
     const size_t s0 = win_off[w0], s1 = win_off[w1];
-    for (size_t w = w0; w < w1; ++w)
-        if (win_off[w + 1] < win_off[w]) return fail(h, FBUS_E_BADARG, "fbus_step_windows: win_off must be non-decreasing");
-    if (s1 > imu->n_samples) return fail(h, FBUS_E_BADARG, "fbus_step_windows: win_off beyond the IMU stream");
     WinParams prm;
     memset(&prm, 0, sizeof prm);
-    int rc = stage_det(h, det, w0, w1, prm);
+    if (copy_stream) CUDA_TRY(h, cudaStreamWaitEvent(copy_stream, h->ev_done[bufset], 0));  // staging set free again
+    int rc = stage_det(h, det, w0, w1, prm, bufset, copy_stream);
     if (rc) return rc;
     // IMU samples of this call, re-based to index 0
     const double* dt;
@@ -341,8 +362,13 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
     if (rc) return rc;
     if (imu->mem == FBUS_MEM_HOST && ns == 0) dd = nullptr;
     else {
-        rc = stage(h, h->imu_data, imu->data + s0 * 6 * B, ns * 6 * B, imu->mem, &dd);
+        rc = stage_on(h, bufset ? h->imu_data2 : h->imu_data, imu->data + s0 * 6 * B, ns * 6 * B, imu->mem, &dd,
+                      copy_stream ? copy_stream : h->stream);
         if (rc) return rc;
+    }
+    if (copy_stream) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_copied[bufset], copy_stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[bufset], 0));
     }
     std::vector<uint32_t> off(nw + 1);
     for (size_t w = 0; w <= nw; ++w) off[w] = (uint32_t)(win_off[w0 + w] - s0);
@@ -365,11 +391,40 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
     prm.trace = dtrace;
     rc = launch_window(h, prm);
     if (rc) return rc;
+    if (copy_stream) CUDA_TRY(h, cudaEventRecord(h->ev_done[bufset], h->stream));
     if (trace && trace_mem == FBUS_MEM_HOST) {
         CUDA_TRY(h, cudaMemcpyAsync(trace, dtrace, nw * 17 * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
     return FBUS_OK;
+}
+
+int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det_frames* det, const uint32_t* win_off,
+                      size_t w0, size_t w1, double* trace, int32_t trace_mem) {
+    if (!h || !imu || !det || !win_off || imu->batch != h->B || !imu->t || !imu->data)
+        return fail(h, FBUS_E_BADARG, "fbus_step_windows: bad argument");
+    if (w0 >= w1) return (w0 == w1) ? FBUS_OK : fail(h, FBUS_E_BADARG, "fbus_step_windows: w0 > w1");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (size_t w = w0; w < w1; ++w)
+        if (win_off[w + 1] < win_off[w]) return fail(h, FBUS_E_BADARG, "fbus_step_windows: win_off must be non-decreasing");
+    if (win_off[w1] > imu->n_samples) return fail(h, FBUS_E_BADARG, "fbus_step_windows: win_off beyond the IMU stream");
+    const size_t nw = w1 - w0, B = h->B;
+    // Host-resident streams that are large enough to matter: pipeline the frames in chunks so that the PCIe copy of
+    // chunk c+1 runs while chunk c is computed (the state makes one extra HBM round trip per chunk).
+    const size_t ch = h->pipeline_frames;
+    const bool host_streams = imu->mem == FBUS_MEM_HOST && det->mem == FBUS_MEM_HOST;
+    const size_t bytes = (size_t)(win_off[w1] - win_off[w0]) * 48 * B;
+    if (host_streams && ch > 0 && nw >= 2 * ch && bytes >= ((size_t)64 << 20) && h->copy_stream) {
+        int c = 0;
+        for (size_t a = w0; a < w1; a += ch, ++c) {
+            const size_t e = (a + ch < w1) ? a + ch : w1;
+            double* tr = trace ? trace + (a - w0) * 17 * B : nullptr;
+            int rc = step_windows_chunk(h, imu, det, win_off, a, e, tr, trace_mem, c & 1, h->copy_stream);
+            if (rc) return rc;
+        }
+        return FBUS_OK;
+    }
+    return step_windows_chunk(h, imu, det, win_off, w0, w1, trace, trace_mem, 0, nullptr);
 }
 
 int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid, int32_t mem) {

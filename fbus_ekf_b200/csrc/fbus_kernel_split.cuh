@@ -62,7 +62,7 @@ struct SplitShared {
 // ------------------------------------------------------------------------------------------------------------------
 // COVARIANCE role: owns P (shared memory; top-left 9x9 in registers while propagating)
 // ------------------------------------------------------------------------------------------------------------------
-template <int BSF>
+template <int BSF, bool JOSEPH>
 __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh, int32_t (*sflag)[BSF],
                                          int fl, size_t b, bool live) {
     constexpr int NT = 2 * BSF, NW = BSF / 32;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                 for (int c = 0; c < 3; ++c) t.p[c] = X[(size_t)(20 + c) * BSF];
                 const MarkerConst mkc = prm.tab->mk[req - 1];  // 3 KB table, L2-resident
                 // X = L^-1 Hs (42 doubles) is parked in the exchange area: its inputs are already in registers
-                update_prologue<BSF, BSF>(P, t, k, mkc, yP, yQ, Cm, y, X);
+                update_prologue<BSF, BSF, JOSEPH>(P, t, k, mkc, yP, yQ, Cm, y, X);
 #pragma unroll
                 for (int c = 0; c < 21; ++c) X[(size_t)c * BSF] = Cm[c];
 #pragma unroll
@@ -174,7 +174,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                 for (int c = 0; c < 3; ++c) { t.p[c] = X[(size_t)(20 + c) * BSF]; t.v[c] = 0.0; t.ba[c] = 0.0; t.bg[c] = 0.0; t.g[c] = 0.0; }
                 t.t = 0.0;
                 const MarkerConst mkc = prm.tab->mk[req - 1];
-                measurement_update<BSF>(P, t, k, mkc, yP, yQ);
+                measurement_update<BSF, JOSEPH ? 1 : 0>(P, t, k, mkc, yP, yQ);
                 // hand back: corrected p, q and the increments of v, b_a, b_g, g
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -594,7 +594,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 // same two schedulers.  Each CTA therefore takes an arrival ticket per SM: odd tickets swap the role order (covariance
 // warps on schedulers 2,3 instead of 0,1) and start half a frame period late, so that one CTA's update phase (one busy
 // warp per filter group) overlaps the other's propagation phase.
-template <int BSF>  // filters per CTA; the CTA has 2*BSF threads
+template <int BSF, bool JOSEPH>  // filters per CTA; the CTA has 2*BSF threads
 __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
     extern __shared__ double smem[];
     __shared__ SplitShared sh;
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
     const size_t b0 = (size_t)blockIdx.x * BSF + fl;
     const bool live = b0 < prm.B;
     const size_t b = live ? b0 : prm.B - 1;  // threads past the batch mirror the last filter and never store
-    if (is_cov) cov_role<BSF>(prm, k, smem, sh, sflag, fl, b, live);
+    if (is_cov) cov_role<BSF, JOSEPH>(prm, k, smem, sh, sflag, fl, b, live);
     else nominal_role<BSF>(prm, k, smem, sh, sflag, fl, b, live);
 }
 

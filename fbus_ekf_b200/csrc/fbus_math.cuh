@@ -735,7 +735,7 @@ struct CholStep<N, N> {
 // Prologue of the update: everything up to the gain factors.  Reads only the 21 entries of P6 = P[{p,theta},{p,theta}].
 // Outputs Cm = lower-packed Cholesky factor Lc of C = Hs^T S^-1 Hs and y = Lc^-1 u (u = Hs^T S^-1 r), so that
 //   (I-KH)P = P - Z^T Z with Z = Lc^T G, and dx = K r = Z^T y.
-template <int S, int XS>
+template <int S, int XS, bool JOSEPH = false>
 FBUS_HD void update_prologue(const Cov<S> P, const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
                              const double* yQ, double* Cm, double* y, double* scr) {
     // scr: 42 doubles of scratch with element stride XS (shared memory in the warp-specialised kernel) for X = L^-1 Hs
@@ -906,6 +906,50 @@ FBUS_HD void update_prologue(const Cov<S> P, const Nominal& n, const DevConsts& 
             u[i] = s;
         }
     }
+    if (JOSEPH) {
+        // FBUS_FLAG_JOSEPH (compile-time variant so that the default path carries none of this code): Joseph-form covariance update  P' = (I-KH) P (I-KH)^T + K R K^T  evaluated in the same reduced
+        // space.  With K = G^T Hs^T S^-1 it equals  P - G^T C_J G,  C_J = 2C - C P6 C - D,  D = Y^T R Y,  Y = S^-1 Hs
+        // (C P6 C + D = C in exact arithmetic, so C_J = C up to rounding; the default is the reference's (I-KH)P).
+        double Y[42];  // S^-1 Hs = L^-T X  (back substitution)
+        FBUS_UNROLL
+        for (int i = 6; i >= 0; --i)
+            FBUS_UNROLL
+            for (int c = 0; c < 6; ++c) {
+                double s = FBUS_X(i * 6 + c);
+                FBUS_UNROLL
+                for (int j = i + 1; j < 7; ++j) s -= FBUS_L(j, i) * Y[j * 6 + c];
+                Y[i * 6 + c] = s * Li[i];
+            }
+        double P6[36];  // [[P00 P02],[P02^T P22]]
+        FBUS_UNROLL
+        for (int i = 0; i < 6; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j < 6; ++j) P6[i * 6 + j] = P.ld(i < 3 ? i : i + 3, j < 3 ? j : j + 3);
+        double CP[36];  // C P6 (C symmetric, lower packed)
+        FBUS_UNROLL
+        for (int i = 0; i < 6; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j < 6; ++j) {
+                double s = 0.0;
+                FBUS_UNROLL
+                for (int c = 0; c < 6; ++c) s += ((i >= c) ? FBUS_C(i, c) : FBUS_C(c, i)) * P6[c * 6 + j];
+                CP[i * 6 + j] = s;
+            }
+        double CJ[21];
+        FBUS_UNROLL
+        for (int i = 0; i < 6; ++i)
+            FBUS_UNROLL
+            for (int j = 0; j <= i; ++j) {
+                double s = 2.0 * FBUS_C(i, j);
+                FBUS_UNROLL
+                for (int c = 0; c < 6; ++c) s -= CP[i * 6 + c] * ((c >= j) ? FBUS_C(c, j) : FBUS_C(j, c));
+                FBUS_UNROLL
+                for (int c = 0; c < 7; ++c) s -= ((c < 3) ? k.Rp : k.Rq) * Y[c * 6 + i] * Y[c * 6 + j];
+                CJ[i * (i + 1) / 2 + j] = s;
+            }
+        FBUS_UNROLL
+        for (int i = 0; i < 21; ++i) Cm[i] = CJ[i];
+    }
 #undef FBUS_L
 #undef FBUS_X
     // ---- Cholesky C = Lc Lc^T (in place in Cm) ; y = Lc^-1 u -------------------------------------
@@ -1026,13 +1070,15 @@ FBUS_HD void measurement_update_coop(const Cov<S> P, Nominal& n, const DevConsts
     inject_error_state(n, dx);
 }
 
-template <int S>
+// JMODE: 0 = reference form (I-KH)P, 1 = Joseph form, -1 = decided at run time from k.flags (host harness, un-split kernel)
+template <int S, int JMODE = -1>
 FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
                                 const double* yQ) {
     double Cm[21], y[6];
     {
         double xloc[42];  // single-thread form: X = L^-1 Hs stays private
-        update_prologue<S, 1>(P, n, k, mk, yP, yQ, Cm, y, xloc);
+        if (JMODE == 1 || (JMODE < 0 && (k.flags & 1))) update_prologue<S, 1, true>(P, n, k, mk, yP, yQ, Cm, y, xloc);
+        else update_prologue<S, 1, false>(P, n, k, mk, yP, yQ, Cm, y, xloc);
     }
 #define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
     double dth[3];  // attitude part of dx (needed whole before the quaternion injection)

@@ -18,6 +18,10 @@
  *     the reference holds them as cv::Point2f (vision.cpp:492-494);
  *   - every call returns 0 on success or a negative FBUS_E_* code; fbus_last_error() gives text;
  *   - a handle is bound to one CUDA device and one stream and is not internally locked;
+ *   - work is asynchronous: caller-owned buffers (host or device) must stay valid and unchanged until
+ *     fbus_synchronize() / a synchronising call (fbus_get_state, fbus_stats with a host output);
+ *     pinned host memory is read by DMA after the call returns, and large host-resident streams are
+ *     copied in frame chunks on a second stream so that the PCIe copy overlaps the kernels;
  *   - there is NO CPU fallback: if no CUDA device is usable fbus_create fails with FBUS_E_CUDA.
  */
 #ifndef FBUS_EKF_H

@@ -249,6 +249,7 @@ struct Consts {
     // VISION view: raw T_SC (vision.hpp:83-84)
     double R_RL[9], P_LR[3];
     double n_air, n_glass, n_water, d_air, d_glass, normal[3], dect_thres;
+    int flags;
 };
 
 void make_consts(const fbus_config* c, Consts* k) {
@@ -292,6 +293,7 @@ void make_consts(const fbus_config* c, Consts* k) {
     k->d_air = c->d_air; k->d_glass = c->d_glass;
     for (int i = 0; i < 3; ++i) k->normal[i] = c->normal[i];
     k->dect_thres = c->marker_dect_dist_thres;
+    k->flags = c->flags;
 }
 
 int find_marker(const Consts& k, int id) {
@@ -590,6 +592,17 @@ void ObservationUpdate(const Consts& k, Filter* f, const Det* d, int n) {
             IKH[i * 18 + j] = ((i == j) ? 1.0 : 0.0) - s;
         }
     matmul<18, 18, 18>(IKH, f->P, Pn);
+    if (k.flags & FBUS_FLAG_JOSEPH) {
+        // opt-in Joseph form (north_star; not what the reference executes): (I-KH) P (I-KH)^T + K R K^T
+        double J1[324];
+        matmul_bt<18, 18, 18>(Pn, IKH, J1);
+        for (int i = 0; i < 18; ++i)
+            for (int j = 0; j < 18; ++j) {
+                double s = 0.0;
+                for (int c = 0; c < 7; ++c) s += KT[c * 18 + i] * k.Rn[c] * KT[c * 18 + j];
+                Pn[i * 18 + j] = J1[i * 18 + j] + s;
+            }
+    }
     for (int i = 0; i < 18; ++i)
         for (int j = 0; j < 18; ++j) f->P[i * 18 + j] = (Pn[i * 18 + j] + Pn[j * 18 + i]) / 2.0;
 }

@@ -133,3 +133,29 @@ def test_known_answers(cfg):
     assert np.array_equal(P1, P1.transpose(1, 0, 2))
     for k in ("p", "v", "q"):
         assert np.abs(sg[k] - st[k]).max() <= 1e-15
+
+
+def test_joseph_flag(cfg):
+    """FBUS_FLAG_JOSEPH (opt-in, north_star): Joseph-form covariance update.  Checked against the oracle's dense
+    (I-KH)P(I-KH)^T + K R K^T and, being algebraically equal, against the default form at rounding level."""
+    import copy
+    import orc
+    from fbus_ekf_b200 import BatchFilter, capi
+    rng = np.random.default_rng(6)
+    B = 64
+    cj = copy.copy(cfg)
+    cj.flags = capi.FLAG_JOSEPH
+    fj, oj, fd = BatchFilter(cj, batch=B), orc.Oracle(cj, B), BatchFilter(cfg, batch=B)
+    st = random_states(B, rng)
+    for x in (fj, fd):
+        x.SetState(st)
+    oj.set_state(st)
+    det = _random_dets(rng, 2, 2, B, [1.02, 1.06], ids_pool=(0, 1, 5), p_empty=0.0)
+    for w in range(2):
+        fj.MeasureUpdate(det, w)
+        fd.MeasureUpdate(det, w)
+        oj.update(det, w)
+    sj, sd, so = fj.GetState(), fd.GetState(), oj.get_state()
+    assert state_close(sj, so, RTOL)[0] and cov_close(sj["P"], so["P"], RTOL)[0]
+    assert cov_close(sj["P"], sd["P"], 1e-9)[0]
+    assert not np.array_equal(sj["P"], sd["P"])  # a different evaluation, not a no-op
