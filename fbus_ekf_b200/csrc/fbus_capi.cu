@@ -427,8 +427,17 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
     return step_windows_chunk(h, imu, det, win_off, w0, w1, trace, trace_mem, 0, nullptr);
 }
 
+static int stereo_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid, int32_t mem,
+                        bool underwater);
 int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid, int32_t mem) {
-    if (!h || !corners || !pose) return fail(h, FBUS_E_BADARG, "fbus_refract_solve: bad argument");
+    return stereo_solve(h, corners, n, pose, corners3d, valid, mem, true);
+}
+int fbus_inair_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid, int32_t mem) {
+    return stereo_solve(h, corners, n, pose, corners3d, valid, mem, false);
+}
+static int stereo_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid, int32_t mem,
+                        bool underwater) {
+    if (!h || !corners || !pose) return fail(h, FBUS_E_BADARG, "fbus_refract_solve / fbus_inair_solve: bad argument");
     if (n == 0) return FBUS_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
     const float* dc;
@@ -445,7 +454,8 @@ int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* p
         dvalid = (int32_t*)h->scratch_aux.p;
     }
     const unsigned grid = (unsigned)((n + 127) / 128);
-    refract_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc, n, dpose, dc3, dvalid);
+    if (underwater) refract_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc, n, dpose, dc3, dvalid);
+    else inair_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc, n, dpose, dc3, dvalid);
     CUDA_TRY(h, cudaGetLastError());
     if (mem == FBUS_MEM_HOST) {
         CUDA_TRY(h, cudaMemcpyAsync(pose, dpose, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

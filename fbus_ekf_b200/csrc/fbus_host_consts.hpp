@@ -52,6 +52,18 @@ inline int make_dev_consts(const fbus_config* c, DevConsts* k, MarkerTable* tab)
         const double t = k->R_RL[i * 3] * c->tsc_right[3] + k->R_RL[i * 3 + 1] * c->tsc_right[7] + k->R_RL[i * 3 + 2] * c->tsc_right[11];
         k->P_LR[i] = c->tsc_left[i * 4 + 3] - t;
     }
+    // in-air stereo (vision.cpp:402-408): T_L_R = [R_IR R_IL^T | P_LI - (R_IR R_IL^T) P_RI] with the raw T_SC
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int x = 0; x < 3; ++x) s += c->tsc_right[i * 4 + x] * c->tsc_left[j * 4 + x];
+            k->T_LR_air[i * 4 + j] = s;
+        }
+    }
+    for (int i = 0; i < 3; ++i) {
+        const double t = k->T_LR_air[i * 4] * c->tsc_right[3] + k->T_LR_air[i * 4 + 1] * c->tsc_right[7] + k->T_LR_air[i * 4 + 2] * c->tsc_right[11];
+        k->T_LR_air[i * 4 + 3] = c->tsc_left[i * 4 + 3] - t;
+    }
     k->a0 = c->n_air / c->n_glass;
     k->a1 = c->n_glass / c->n_water;
     k->air_lt_glass = c->n_air < c->n_glass;      // vision.cpp:511

@@ -418,6 +418,38 @@ __global__ void __launch_bounds__(128) refract_kernel(const __grid_constant__ De
     if (valid) valid[i] = dead ? 0 : 1;
 }
 
+// N3+K4: in-air stereo DLT triangulation (VISION::NormalTriangulation, vision.cpp:395-466) + ComputeMarkerPose
+__global__ void __launch_bounds__(128) inair_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ corners, size_t n,
+                                                    double* __restrict__ pose, double* __restrict__ c3d, int32_t* __restrict__ valid) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float c[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) c[e] = corners[(size_t)e * n + i];
+    double C[12];
+    bool dead = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        double Pc[3];
+        const double nrm = triangulate_corner_inair(k, (double)c[2 * e], (double)c[2 * e + 1], (double)c[8 + 2 * e], (double)c[8 + 2 * e + 1], Pc);
+        C[3 * e] = dead ? 0.0 : Pc[0];
+        C[3 * e + 1] = dead ? 0.0 : Pc[1];
+        C[3 * e + 2] = dead ? 0.0 : Pc[2];
+        if (nrm > k.dect_thres) dead = true;  // break at the first out-of-range corner (vision.cpp:451-455)
+    }
+    double p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0};
+    if (!dead) marker_pose(C, k.rod_s, k.rod_c, p, q);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) pose[(size_t)e * n + i] = p[e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pose[(size_t)(3 + e) * n + i] = q[e];
+    if (c3d) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) c3d[(size_t)e * n + i] = C[e];
+    }
+    if (valid) valid[i] = dead ? 0 : 1;
+}
+
 // K3+K4+K5: closed-form solve, then Gauss-Newton refinement of the pose on the stereo reprojection error (R3)
 template <typename CT>
 __global__ void __launch_bounds__(128) refract_gn_kernel(const __grid_constant__ DevConsts k, const __grid_constant__ GnConsts g,

@@ -194,6 +194,110 @@ FBUS_HD void marker_pose(const double* C, double rod_s, double rod_c, double* p,
 
 }  // namespace fbus
 
+// -------------------------------------------------------------------------------------------------
+// N3: in-air stereo triangulation, VISION::NormalTriangulation (vision.cpp:395-466): homogeneous DLT
+//   A = [ [xL]x [I|0] ; [xR]x T_L_R ]  (6x4),  P = right singular vector of the smallest singular value.
+// That vector is the eigenvector of the smallest eigenvalue of the symmetric 4x4 A^T A, found here by cyclic Jacobi
+// rotations (the reference uses Eigen's JacobiSVD; the result is a direction, its sign cancels in P[0:3]/P[3]).
+// -------------------------------------------------------------------------------------------------
+namespace fbus {
+
+FBUS_HD void smallest_eigvec_sym4(double* A /*[16], destroyed*/, double* v) {
+    double V[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int sweep = 0; sweep < 10; ++sweep) {
+        FBUS_UNROLL
+        for (int p = 0; p < 3; ++p)
+            FBUS_UNROLL
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = A[p * 4 + q];
+                const double app = A[p * 4 + p], aqq = A[q * 4 + q];
+                // rotation angle: tan(2 phi) = 2 apq / (aqq - app); stable t = sgn(th) / (|th| + sqrt(th^2 + 1))
+                double c = 1.0, sn = 0.0;
+                if (apq != 0.0) {
+                    const double th = (aqq - app) / (2.0 * apq);
+                    const double t = (th >= 0 ? 1.0 : -1.0) / ((th >= 0 ? th : -th) + sqrt(th * th + 1.0));
+                    c = rsqrt_d(t * t + 1.0);
+                    sn = t * c;
+                }
+                FBUS_UNROLL
+                for (int k = 0; k < 4; ++k) {  // A <- A J
+                    const double akp = A[k * 4 + p], akq = A[k * 4 + q];
+                    A[k * 4 + p] = c * akp - sn * akq;
+                    A[k * 4 + q] = sn * akp + c * akq;
+                }
+                FBUS_UNROLL
+                for (int k = 0; k < 4; ++k) {  // A <- J^T A
+                    const double apk = A[p * 4 + k], aqk = A[q * 4 + k];
+                    A[p * 4 + k] = c * apk - sn * aqk;
+                    A[q * 4 + k] = sn * apk + c * aqk;
+                }
+                FBUS_UNROLL
+                for (int k = 0; k < 4; ++k) {
+                    const double vkp = V[k * 4 + p], vkq = V[k * 4 + q];
+                    V[k * 4 + p] = c * vkp - sn * vkq;
+                    V[k * 4 + q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    // column of the smallest diagonal entry (static selects: no dynamic register indexing)
+    const double d0 = A[0], d1 = A[5], d2 = A[10], d3 = A[15];
+    const bool s1 = d1 < d0;
+    const double m01 = s1 ? d1 : d0;
+    const bool s3 = d3 < d2;
+    const double m23 = s3 ? d3 : d2;
+    const bool hi = m23 < m01;
+    FBUS_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        const double a = s1 ? V[k * 4 + 1] : V[k * 4 + 0];
+        const double b = s3 ? V[k * 4 + 3] : V[k * 4 + 2];
+        v[k] = hi ? b : a;
+    }
+}
+
+// one stereo corner pair (undistorted normalised coordinates) -> corner in the flipped left frame with z > 0;
+// returns |P| for the range gate, or -1 when the homogeneous coordinate vanishes (the reference `continue`s)
+FBUS_HD double triangulate_corner_inair(const DevConsts& k, double xl, double yl, double xr, double yr, double* Pout) {
+    // rows of [x]x M for x = (x, y, 1):  ( -M1 + y M2,  M0 - x M2,  -y M0 + x M1 )  with M's rows M0, M1, M2
+    double A[24];
+    {   // left: M = [I | 0]
+        const double M0[4] = {1, 0, 0, 0}, M1[4] = {0, 1, 0, 0}, M2[4] = {0, 0, 1, 0};
+        FBUS_UNROLL
+        for (int c = 0; c < 4; ++c) {
+            A[0 * 4 + c] = -M1[c] + yl * M2[c];
+            A[1 * 4 + c] = M0[c] - xl * M2[c];
+            A[2 * 4 + c] = -yl * M0[c] + xl * M1[c];
+        }
+    }
+    FBUS_UNROLL
+    for (int c = 0; c < 4; ++c) {
+        const double m0 = k.T_LR_air[c], m1 = k.T_LR_air[4 + c], m2 = k.T_LR_air[8 + c];
+        A[3 * 4 + c] = -m1 + yr * m2;
+        A[4 * 4 + c] = m0 - xr * m2;
+        A[5 * 4 + c] = -yr * m0 + xr * m1;
+    }
+    double G[16];
+    FBUS_UNROLL
+    for (int i = 0; i < 4; ++i)
+        FBUS_UNROLL
+        for (int j = i; j < 4; ++j) {
+            double s = 0.0;
+            FBUS_UNROLL
+            for (int r = 0; r < 6; ++r) s += A[r * 4 + i] * A[r * 4 + j];
+            G[i * 4 + j] = s;
+            G[j * 4 + i] = s;
+        }
+    double P[4];
+    smallest_eigvec_sym4(G, P);
+    if (P[3] == 0.0) { Pout[0] = 0; Pout[1] = 0; Pout[2] = 0; return -1.0; }
+    const double iw = 1.0 / P[3];
+    const double Pn[3] = {-P[0] * iw, -P[1] * iw, P[2] * iw};  // R_I_C = diag(-1,-1,1)
+    const double sg = signum_ref(Pn[2]);
+    Pout[0] = sg * Pn[0]; Pout[1] = sg * Pn[1]; Pout[2] = sg * Pn[2];
+    return norm3(Pn);
+}
+
+}  // namespace fbus
+
 // =================================================================================================
 // R3 (north_star; NOT in the reference -> "parity unpinned"): Gauss-Newton refinement of the marker pose.
 // Minimises sum over 4 corners x 2 cameras of | pi_refr(x_c) - u |^2 over (R_M, p) in the flipped left-camera frame,

@@ -101,6 +101,15 @@ class BatchFilter:
     def RefractSolveDevice(self, corners_ptr: int, n: int, pose_ptr: int, c3_ptr: int | None, valid_ptr: int | None):
         self._ck(self._lib.fbus_refract_solve(self._h, corners_ptr, n, pose_ptr, c3_ptr, valid_ptr, capi.FBUS_MEM_DEVICE))
 
+    def InAirSolve(self, corners: np.ndarray):
+        """VISION::NormalTriangulation + ComputeMarkerPose (land mode).  corners float32 [16][n] -> (pose, corners3d, valid)"""
+        assert corners.dtype == np.float32 and corners.flags["C_CONTIGUOUS"] and corners.shape[0] == 16
+        n = corners.shape[1]
+        pose, c3, valid = np.zeros((7, n)), np.zeros((12, n)), np.zeros(n, dtype=np.int32)
+        self._ck(self._lib.fbus_inair_solve(self._h, corners.ctypes.data, n, pose.ctypes.data, c3.ctypes.data, valid.ctypes.data,
+                                            capi.FBUS_MEM_HOST))
+        return pose, c3, valid
+
     def RefractSolveGN(self, corners: np.ndarray, iters: int = 5):
         """closed-form solve + Gauss-Newton refinement (R3).  corners float32 or float64 [16][n] ->
         (pose [7][n], cost [n], valid [n])"""

@@ -256,3 +256,24 @@ def marker_corners_from_pose(cfg: capi.FbusConfig, Rm: np.ndarray, p: np.ndarray
 def random_marker_corners(cfg: capi.FbusConfig, n: int, rng, far_fraction: float = 0.0, noise: float = 2e-4):
     Rm, p = random_marker_poses(n, rng, far_fraction)
     return marker_corners_from_pose(cfg, Rm, p, noise=noise, rng=rng)
+
+
+def marker_corners_inair(cfg: capi.FbusConfig, Rm: np.ndarray, p: np.ndarray, size: float = 0.28, noise: float = 0.0, rng=None):
+    """in-air (pinhole) stereo corner observations float32 [16][n] consistent with VISION::NormalTriangulation's geometry:
+    x_R ~ T_L_R [X_L; 1] with T_L_R = [R_IR R_IL^T | P_LI - R P_RI] (vision.cpp:402-408)."""
+    n = p.shape[0]
+    TL = np.array(cfg.tsc_left, dtype=np.float64).reshape(4, 4)
+    TR = np.array(cfg.tsc_right, dtype=np.float64).reshape(4, 4)
+    R = TR[:3, :3] @ TL[:3, :3].T
+    t = TL[:3, 3] - R @ TR[:3, 3]
+    cm = np.array([[0, 0, 0], [size, 0, 0], [size, size, 0], [0, size, 0]], dtype=np.float64)
+    out = np.zeros((16, n))
+    flip = np.array([-1.0, -1.0, 1.0])
+    for i in range(4):
+        XL = (p + np.einsum("nij,j->ni", Rm, cm[i])) * flip
+        XR = XL @ R.T + t
+        out[2 * i], out[2 * i + 1] = XL[:, 0] / XL[:, 2], XL[:, 1] / XL[:, 2]
+        out[8 + 2 * i], out[8 + 2 * i + 1] = XR[:, 0] / XR[:, 2], XR[:, 1] / XR[:, 2]
+    if noise > 0:
+        out = out + (rng or np.random.default_rng(0)).normal(size=out.shape) * noise
+    return np.ascontiguousarray(out.astype(np.float32))

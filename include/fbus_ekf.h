@@ -220,6 +220,11 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
 int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d,
                        int32_t* valid, int32_t mem);
 
+/* VISION::NormalTriangulation (vision.cpp:395-466: homogeneous DLT per stereo corner pair, land mode) followed by
+   VISION::ComputeMarkerPose; same layouts and meaning as fbus_refract_solve. */
+int fbus_inair_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d,
+                     int32_t* valid, int32_t mem);
+
 /*
  * R3 (north_star; NOT in the reference, "parity unpinned"): the closed-form solve above followed by `iters`
  * Gauss-Newton iterations on the stereo reprojection error through the flat port (16 residuals, 6 parameters,

@@ -697,6 +697,77 @@ bool RefractionTriangulation(const Consts& k, const float* c16, double* P3 /*[4]
     return !out_of_range;
 }
 
+// Right singular vector of the smallest singular value of a 6x4 matrix by one-sided (Hestenes) Jacobi SVD; stands in for
+// Eigen::JacobiSVD(A).matrixV().col(3) (vision.cpp:432-437; singular values sorted decreasingly, the sign cancels below).
+void smallest_right_singular_vec_6x4(const double* Ain, double* v) {
+    double A[24], V[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    std::memcpy(A, Ain, sizeof A);
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 3; ++p)
+            for (int q = p + 1; q < 4; ++q) {
+                double a = 0, b = 0, c = 0;
+                for (int r = 0; r < 6; ++r) { a += A[r * 4 + p] * A[r * 4 + p]; b += A[r * 4 + q] * A[r * 4 + q]; c += A[r * 4 + p] * A[r * 4 + q]; }
+                off = std::fmax(off, std::fabs(c) / std::sqrt(a * b + 1e-300));
+                if (c == 0.0) continue;
+                const double zeta = (b - a) / (2.0 * c);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+                for (int r = 0; r < 6; ++r) {
+                    const double x = A[r * 4 + p], y = A[r * 4 + q];
+                    A[r * 4 + p] = cs * x - sn * y;
+                    A[r * 4 + q] = sn * x + cs * y;
+                }
+                for (int r = 0; r < 4; ++r) {
+                    const double x = V[r * 4 + p], y = V[r * 4 + q];
+                    V[r * 4 + p] = cs * x - sn * y;
+                    V[r * 4 + q] = sn * x + cs * y;
+                }
+            }
+        if (off < 1e-17) break;
+    }
+    int best = 0;
+    double bn = 1e300;
+    for (int j = 0; j < 4; ++j) {
+        double nj = 0;
+        for (int r = 0; r < 6; ++r) nj += A[r * 4 + j] * A[r * 4 + j];
+        if (nj < bn) { bn = nj; best = j; }
+    }
+    for (int r = 0; r < 4; ++r) v[r] = V[r * 4 + best];
+}
+
+// N3: vision.cpp:395-466 for one marker (land mode)
+bool NormalTriangulation(const fbus_config* cfg, const Consts& k, const float* c16, double* P3) {
+    double T0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, TLR[12];
+    double R_IL[9], R_IR[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { R_IL[i * 3 + j] = cfg->tsc_left[i * 4 + j]; R_IR[i * 3 + j] = cfg->tsc_right[i * 4 + j]; }
+    double Rm[9];
+    matmul_bt<3, 3, 3>(R_IR, R_IL, Rm);  // T_I_R * T_I_L^T
+    const double P_LI[3] = {cfg->tsc_left[3], cfg->tsc_left[7], cfg->tsc_left[11]};
+    const double P_RI[3] = {cfg->tsc_right[3], cfg->tsc_right[7], cfg->tsc_right[11]};
+    double t[3];
+    mat3_vec(Rm, P_RI, t);
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) TLR[i * 4 + j] = Rm[i * 3 + j]; TLR[i * 4 + 3] = P_LI[i] - t[i]; }
+    bool out = false;
+    for (int i = 0; i < 4; ++i) {
+        const double lp[3] = {(double)c16[2 * i], (double)c16[2 * i + 1], 1.0};
+        const double rp[3] = {(double)c16[8 + 2 * i], (double)c16[8 + 2 * i + 1], 1.0};
+        double Sl[9], Sr[9], A[24];
+        skew(lp, Sl); skew(rp, Sr);
+        matmul<3, 3, 4>(Sl, T0, A);
+        matmul<3, 3, 4>(Sr, TLR, A + 12);
+        double P[4];
+        smallest_right_singular_vec_6x4(A, P);
+        if (P[3] == 0) continue;
+        double Pn[3] = {-(P[0] / P[3]), -(P[1] / P[3]), P[2] / P[3]};
+        const double sg = Signum(Pn[2]);
+        for (int j = 0; j < 3; ++j) P3[i * 3 + j] = sg * Pn[j];
+        if (norm3(Pn) > k.dect_thres) { out = true; break; }
+    }
+    return !out;
+}
+
 // R2: vision.cpp:635-759 for one marker; C = 4 corners x 3
 void ComputeMarkerPose(const double* C, double* p, double* q, double* Rml) {
     const double* c0 = C; const double* c1 = C + 3; const double* c2 = C + 6; const double* c3 = C + 9;
@@ -899,6 +970,25 @@ int orc_refract_solve(const fbus_config* cfg, const float* corners, size_t n, do
             if (valid) valid[i] = ok ? 1 : 0;
         }
     });
+    return FBUS_OK;
+}
+
+int orc_inair_solve(const fbus_config* cfg, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid) {
+    Consts k;
+    make_consts(cfg, &k);
+    for (size_t i = 0; i < n; ++i) {
+        float c16[16];
+        for (int c = 0; c < 16; ++c) c16[c] = corners[(size_t)c * n + i];
+        double P3[12];
+        for (int c = 0; c < 12; ++c) P3[c] = 0.0;
+        const bool ok = NormalTriangulation(cfg, k, c16, P3);
+        double p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0};
+        if (ok) ComputeMarkerPose(P3, p, q, nullptr);
+        for (int c = 0; c < 3; ++c) pose[(size_t)c * n + i] = p[c];
+        for (int c = 0; c < 4; ++c) pose[(size_t)(3 + c) * n + i] = q[c];
+        if (corners3d) for (int c = 0; c < 12; ++c) corners3d[(size_t)c * n + i] = P3[c];
+        if (valid) valid[i] = ok ? 1 : 0;
+    }
     return FBUS_OK;
 }
 

@@ -392,6 +392,28 @@ def refraction_triangulation(k: Consts, c16, as_float32=True):
     return out, ok
 
 
+def normal_triangulation(cfg: Config, c16, dect_thres=2.0):
+    """vision.cpp:395-466 (land mode): homogeneous DLT, smallest right singular vector by LAPACK SVD"""
+    c16 = np.asarray(c16, dtype=np.float32).astype(np.float64)
+    T0 = np.hstack([np.eye(3), np.zeros((3, 1))])
+    R = cfg.tsc_right[:3, :3] @ cfg.tsc_left[:3, :3].T
+    TLR = np.hstack([R, (cfg.tsc_left[:3, 3] - R @ cfg.tsc_right[:3, 3])[:, None]])
+    out, ok = np.zeros((4, 3)), True
+    for i in range(4):
+        lp = np.array([c16[2 * i], c16[2 * i + 1], 1.0])
+        rp = np.array([c16[8 + 2 * i], c16[8 + 2 * i + 1], 1.0])
+        A = np.vstack([skew(lp) @ T0, skew(rp) @ TLR])
+        P = np.linalg.svd(A)[2][3]
+        if P[3] == 0:
+            continue
+        Pn = np.diag([-1.0, -1.0, 1.0]) @ (P[:3] / P[3])
+        out[i] = (-1.0 if Pn[2] < 0 else 1.0) * Pn
+        if np.linalg.norm(Pn) > dect_thres:
+            ok = False
+            break
+    return out, ok
+
+
 def compute_marker_pose(C):
     """vision.cpp:635-759.  C: 4x3 corners in the flipped left-camera frame -> (p, q, R)"""
     C = np.asarray(C, dtype=np.float64)

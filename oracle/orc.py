@@ -47,6 +47,8 @@ def lib():
                                    C.c_void_p, C.c_int]
     L.orc_refract_solve.argtypes = [P(capi.FbusConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.orc_marker_pose.argtypes = [P(capi.FbusConfig), C.c_void_p, C.c_size_t, C.c_void_p]
+    L.orc_inair_solve.argtypes = [P(capi.FbusConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_inair_solve.restype = C.c_int
     L.orc_get_state.argtypes = [H, P(capi.StateSoa)]
     L.orc_set_state.argtypes = [H, P(capi.StateSoa)]
     L.orc_stats.argtypes = [H, C.c_void_p, C.c_void_p, capi.c_double_p]
@@ -120,6 +122,16 @@ def refract_solve(cfg, corners: np.ndarray, n_threads=1):
     c3 = np.zeros((12, n))
     valid = np.zeros(n, dtype=np.int32)
     rc = lib().orc_refract_solve(C.byref(cfg), corners.ctypes.data, n, pose.ctypes.data, c3.ctypes.data, valid.ctypes.data, n_threads)
+    assert rc == 0
+    return pose, c3, valid
+
+
+def inair_solve(cfg, corners: np.ndarray):
+    """corners float32 [16][n] -> pose [7][n], corners3d [12][n], valid [n]  (NormalTriangulation + ComputeMarkerPose)"""
+    n = corners.shape[1]
+    assert corners.dtype == np.float32 and corners.flags["C_CONTIGUOUS"]
+    pose, c3, valid = np.zeros((7, n)), np.zeros((12, n)), np.zeros(n, dtype=np.int32)
+    rc = lib().orc_inair_solve(C.byref(cfg), corners.ctypes.data, n, pose.ctypes.data, c3.ctypes.data, valid.ctypes.data)
     assert rc == 0
     return pose, c3, valid
 

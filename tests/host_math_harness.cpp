@@ -119,3 +119,14 @@ void hm_project_refr(const fbus_config* cfg, const double* X, double* uv, double
     project_refr(g, X, uv, J);
 }
 }
+
+extern "C" int hm_inair(const fbus_config* cfg, const float* c16, double* c3d, double* pose) {
+    DevConsts k;
+    MarkerTable tab;
+    if (make_dev_consts(cfg, &k, &tab)) return -1;
+    int ok = 1;
+    for (int i = 0; i < 4; ++i)
+        if (triangulate_corner_inair(k, c16[2 * i], c16[2 * i + 1], c16[8 + 2 * i], c16[8 + 2 * i + 1], c3d + 3 * i) > k.dect_thres) ok = 0;
+    marker_pose(c3d, k.rod_s, k.rod_c, pose, pose + 3);
+    return ok;
+}
