@@ -16,11 +16,24 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-cudart", "static"]
 
 
+HASH_FILE = OUT + ".srchash"
+
+
+def source_hash() -> str:
+    """content hash of every source the library is built from (mtimes do not survive the copy to the GPU box)"""
+    import hashlib
+    h = hashlib.sha256()
+    for d in DEPS:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(HASH_FILE):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return open(HASH_FILE).read().strip() != source_hash()
 
 
 def build_variant(win_bs: int, suffix: str, extra=()) -> str:
@@ -59,6 +72,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libfbus_ekf.so")
+    with open(HASH_FILE, "w") as f:
+        f.write(source_hash())
     if verbose:
         print(log)
     return OUT

@@ -69,6 +69,7 @@ struct fbus_handle {
     MarkerTable* d_tab = nullptr;
     uint32_t* d_ticket = nullptr;
     uint32_t stagger_cycles = 0;
+    bool small_batch = false;
     double* d_nom = nullptr;
     double* d_P = nullptr;
     int32_t* d_prev = nullptr;
@@ -126,7 +127,14 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.stagger_cycles = (prm.mode & M_FUSED) ? h->stagger_cycles : 0u;
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
 #if FBUS_SPLIT
-    if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_split_kernel<WIN_BS, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
+    if (h->small_batch) {
+        // fewer 128-filter CTAs than SMs (e.g. BASELINE configs[2], 4 096 filters): 32-filter CTAs (one covariance + one
+        // nominal warp) spread the batch over four times as many SMs
+        const unsigned g32 = (unsigned)((h->B + 31) / 32);
+        const size_t smem32 = (size_t)(NPK + XCH) * 32 * sizeof(double);
+        if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_split_kernel<32, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
+        else ekf_window_split_kernel<32, false><<<g32, 64, smem32, h->stream>>>(prm, h->k);
+    } else if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_split_kernel<WIN_BS, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
     else ekf_window_split_kernel<WIN_BS, false><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
 #else
     ekf_window_kernel<WIN_BS><<<grid, WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
@@ -215,7 +223,7 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     if ((e = cudaMemset(h->d_ticket, 0, 256 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset tickets", e);
     {
         const char* sc = getenv("FBUS_STAGGER_CYCLES");
-        h->stagger_cycles = sc ? (uint32_t)strtoul(sc, nullptr, 10) : 20000u;
+        h->stagger_cycles = sc ? (uint32_t)strtoul(sc, nullptr, 10) : 0u;  // measured: no benefit, off by default
     }
     if ((e = cudaMalloc(&h->d_tab, sizeof(MarkerTable))) != cudaSuccess) return bail("cudaMalloc marker table", e);
     if ((e = cudaMemcpy(h->d_tab, &h->tab, sizeof(MarkerTable), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("marker table copy", e);
@@ -226,6 +234,18 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     e = cudaFuncSetAttribute(ekf_window_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
 #endif
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+#if FBUS_SPLIT
+    {
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+        h->small_batch = WIN_BS > 32 && (batch + WIN_BS - 1) / WIN_BS < (size_t)prop.multiProcessorCount;
+        if (const char* sb = getenv("FBUS_SMALL_BATCH")) h->small_batch = atoi(sb) != 0;
+        const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
+        e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+        if (e != cudaSuccess) return bail("cudaFuncSetAttribute(32)", e);
+    }
+#endif
     if (getenv("FBUS_DEBUG")) {
         int nb = -1;
 #if FBUS_SPLIT
