@@ -50,6 +50,8 @@ class FbusConfig(C.Structure):
         ("normal", C.c_double * 3),
         ("marker_dect_dist_thres", C.c_double),
         ("marker_size", C.c_double),
+        ("cam_k", (C.c_double * 4) * 2),
+        ("cam_d", (C.c_double * 4) * 2),
         ("n_markers", C.c_int32),
         ("marker_id", C.c_int32 * FBUS_MAX_MARKERS),
         ("marker_pos", C.c_double * (FBUS_MAX_MARKERS * 3)),
@@ -143,6 +145,7 @@ def lib() -> C.CDLL:
                                         C.c_size_t, C.c_void_p, C.c_int32]),
         "fbus_refract_solve": (C.c_int, [H, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
         "fbus_marker_pose": (C.c_int, [H, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32]),
+        "fbus_undistort_fisheye": (C.c_int, [H, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32]),
         "fbus_inair_solve": (C.c_int, [H, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
         "fbus_refract_solve_gn": (C.c_int, [H, C.c_void_p, C.c_int32, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
         "fbus_get_state": (C.c_int, [H, C.POINTER(StateSoa)]),
@@ -164,7 +167,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "fbus_config_default", "fbus_create", "fbus_destroy", "fbus_last_error", "fbus_abi_version", "fbus_synchronize",
     "fbus_batch", "fbus_stream", "fbus_init_gravity_gyrobias", "fbus_init_position_quaternion", "fbus_propagate",
-    "fbus_reset_state", "fbus_update", "fbus_step_windows", "fbus_refract_solve", "fbus_inair_solve", "fbus_refract_solve_gn", "fbus_marker_pose", "fbus_get_state",
+    "fbus_reset_state", "fbus_update", "fbus_step_windows", "fbus_refract_solve", "fbus_inair_solve", "fbus_undistort_fisheye", "fbus_refract_solve_gn", "fbus_marker_pose", "fbus_get_state",
     "fbus_set_state", "fbus_clear_status", "fbus_stats", "fbus_synth_streams", "fbus_quat_from_rotmat",
     "fbus_measure_fp64_peak")
 

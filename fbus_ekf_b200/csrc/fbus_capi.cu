@@ -486,6 +486,27 @@ static int stereo_solve(fbus_handle* h, const float* corners, size_t n, double* 
     return FBUS_OK;
 }
 
+int fbus_undistort_fisheye(fbus_handle* h, const float* pixels, size_t n, float* normalised, int32_t mem) {
+    if (!h || !pixels || !normalised) return fail(h, FBUS_E_BADARG, "fbus_undistort_fisheye: bad argument");
+    if (n == 0) return FBUS_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const float* dp;
+    int rc = stage(h, h->scratch_in, pixels, 16 * n, mem, &dp);
+    if (rc) return rc;
+    float* dout = normalised;
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, h->scratch_out.reserve(16 * n * sizeof(float)));
+        dout = (float*)h->scratch_out.p;
+    }
+    undistort_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->k, dp, n, dout);
+    CUDA_TRY(h, cudaGetLastError());
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(normalised, dout, 16 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
 int fbus_refract_solve_gn(fbus_handle* h, const void* corners, int32_t corner_dtype, size_t n, int32_t iters, double* pose,
                           double* cost, int32_t* valid, int32_t mem) {
     if (!h || !corners || !pose || iters < 0 || iters > 50 || (corner_dtype != 0 && corner_dtype != 1))

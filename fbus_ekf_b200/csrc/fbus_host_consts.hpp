@@ -64,6 +64,8 @@ inline int make_dev_consts(const fbus_config* c, DevConsts* k, MarkerTable* tab)
         const double t = k->T_LR_air[i * 4] * c->tsc_right[3] + k->T_LR_air[i * 4 + 1] * c->tsc_right[7] + k->T_LR_air[i * 4 + 2] * c->tsc_right[11];
         k->T_LR_air[i * 4 + 3] = c->tsc_left[i * 4 + 3] - t;
     }
+    for (int cam = 0; cam < 2; ++cam)
+        for (int i = 0; i < 4; ++i) { k->cam_k[cam][i] = c->cam_k[cam][i]; k->cam_d[cam][i] = c->cam_d[cam][i]; }
     k->a0 = c->n_air / c->n_glass;
     k->a1 = c->n_glass / c->n_water;
     k->air_lt_glass = c->n_air < c->n_glass;      // vision.cpp:511
@@ -131,6 +133,11 @@ inline void config_default(fbus_config* c) {
     c->n_air = 1.00; c->n_water = 1.32; c->n_glass = 1.49; c->d_air = 0.002; c->d_glass = 0.02;
     c->normal[0] = 0; c->normal[1] = 0; c->normal[2] = 1;
     c->marker_dect_dist_thres = 2.0;  // paramconfig.yml:27
+    // camerainfo1.yml K / D of both cameras
+    const double kk[2][4] = {{246.134, 246.265, 325.504, 178.694}, {245.124, 244.704, 341.197, 179.214}};
+    const double dd[2][4] = {{0.584804, 0.158016, -0.5657, 0.272636}, {0.590953, 0.140311, -0.490475, 0.206821}};
+    memcpy(c->cam_k, kk, sizeof kk);
+    memcpy(c->cam_d, dd, sizeof dd);
     c->marker_size = 0.28;            // vision.hpp:114 (paramconfig.yml:23 says 0.48 but is unused)
     // C++/config/markersetup.yml
     static const int ids[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 16, 17, 18};

@@ -418,6 +418,21 @@ __global__ void __launch_bounds__(128) refract_kernel(const __grid_constant__ De
     if (valid) valid[i] = dead ? 0 : 1;
 }
 
+// N4: fisheye undistortion of the detected corner pixels; one thread per marker (16 coordinates)
+__global__ void __launch_bounds__(128) undistort_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ px, size_t n,
+                                                        float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int cam = e >> 2;
+        float xo, yo;
+        undistort_fisheye_point(k.cam_k[cam], k.cam_d[cam], (double)px[(size_t)(2 * e) * n + i], (double)px[(size_t)(2 * e + 1) * n + i], &xo, &yo);
+        out[(size_t)(2 * e) * n + i] = xo;
+        out[(size_t)(2 * e + 1) * n + i] = yo;
+    }
+}
+
 // N3+K4: in-air stereo DLT triangulation (VISION::NormalTriangulation, vision.cpp:395-466) + ComputeMarkerPose
 __global__ void __launch_bounds__(128) inair_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ corners, size_t n,
                                                     double* __restrict__ pose, double* __restrict__ c3d, int32_t* __restrict__ valid) {

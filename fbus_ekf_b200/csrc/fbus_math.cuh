@@ -75,6 +75,7 @@ struct DevConsts {
     double a0, a1;                     // n_air/n_glass, n_glass/n_water
     double d_air, d_glass, normal[3], dect_thres;
     double rod_s, rod_c;               // sin/cos of -3.1415926/4 (common.hpp:14, vision.cpp:740)
+    double cam_k[2][4], cam_d[2][4];   // fisheye intrinsics (fx fy cx cy) and Kannala-Brandt coefficients, left / right
     double T_LR_air[12];               // in-air stereo: [R_IR R_IL^T | P_LI - R P_RI], row-major 3x4 (vision.cpp:402-408)
     int32_t air_lt_glass, glass_gt_water;
     int32_t n_markers, flags;

@@ -195,6 +195,35 @@ FBUS_HD void marker_pose(const double* C, double rod_s, double rod_c, double* p,
 }  // namespace fbus
 
 // -------------------------------------------------------------------------------------------------
+// N4: cv::fisheye::undistortPoints with R = P = identity (OpenCV 3.4.3 semantics, the version the reference links):
+//   pw = ((u-cx)/fx, (v-cy)/fy); theta_d = |pw| clamped to [-pi/2, pi/2]; Newton on
+//   theta (1 + k1 th^2 + k2 th^4 + k3 th^6 + k4 th^8) = theta_d (at most 10 iterations, |step| < 1e-8 stops);
+//   out = pw * tan(theta)/theta_d, rounded to float32 (cv::Point2f).
+// -------------------------------------------------------------------------------------------------
+namespace fbus {
+FBUS_HD void undistort_fisheye_point(const double* K4, const double* D4, double u, double v, float* xo, float* yo) {
+    const double px = (u - K4[2]) / K4[0], py = (v - K4[3]) / K4[1];
+    double scale = 1.0;
+    double theta_d = sqrt(px * px + py * py);
+    const double half_pi = 1.5707963267948966;  // CV_PI / 2 (OpenCV's own constant, not the reference's truncated M_PI)
+    theta_d = theta_d < -half_pi ? -half_pi : (theta_d > half_pi ? half_pi : theta_d);
+    if (theta_d > 1e-8) {
+        double theta = theta_d;
+        for (int j = 0; j < 10; ++j) {
+            const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+            const double k0 = D4[0] * t2, k1 = D4[1] * t4, k2 = D4[2] * t6, k3 = D4[3] * t8;
+            const double fix = (theta * (1 + k0 + k1 + k2 + k3) - theta_d) / (1 + 3 * k0 + 5 * k1 + 7 * k2 + 9 * k3);
+            theta = theta - fix;
+            if ((fix < 0 ? -fix : fix) < 1e-8) break;
+        }
+        scale = tan(theta) / theta_d;
+    }
+    *xo = (float)(px * scale);
+    *yo = (float)(py * scale);
+}
+}  // namespace fbus
+
+// -------------------------------------------------------------------------------------------------
 // N3: in-air stereo triangulation, VISION::NormalTriangulation (vision.cpp:395-466): homogeneous DLT
 //   A = [ [xL]x [I|0] ; [xR]x T_L_R ]  (6x4),  P = right singular vector of the smallest singular value.
 // That vector is the eigenvector of the smallest eigenvalue of the symmetric 4x4 A^T A, found here by cyclic Jacobi

@@ -101,6 +101,13 @@ class BatchFilter:
     def RefractSolveDevice(self, corners_ptr: int, n: int, pose_ptr: int, c3_ptr: int | None, valid_ptr: int | None):
         self._ck(self._lib.fbus_refract_solve(self._h, corners_ptr, n, pose_ptr, c3_ptr, valid_ptr, capi.FBUS_MEM_DEVICE))
 
+    def UndistortFisheye(self, pixels: np.ndarray) -> np.ndarray:
+        """cv::fisheye::undistortPoints as DetectArucoTag applies it: pixel corners float32 [16][n] -> normalised float32 [16][n]"""
+        assert pixels.dtype == np.float32 and pixels.flags["C_CONTIGUOUS"] and pixels.shape[0] == 16
+        out = np.zeros_like(pixels)
+        self._ck(self._lib.fbus_undistort_fisheye(self._h, pixels.ctypes.data, pixels.shape[1], out.ctypes.data, capi.FBUS_MEM_HOST))
+        return out
+
     def InAirSolve(self, corners: np.ndarray):
         """VISION::NormalTriangulation + ComputeMarkerPose (land mode).  corners float32 [16][n] -> (pose, corners3d, valid)"""
         assert corners.dtype == np.float32 and corners.flags["C_CONTIGUOUS"] and corners.shape[0] == 16

@@ -90,6 +90,10 @@ typedef struct fbus_config {
     double normal[3];
     double marker_dect_dist_thres; /* makrer_dect_dist_thres, vision.cpp:602 */
     double marker_size;            /* marker side length, 0.28 m (vision.hpp:114); used only by the GN refinement */
+    /* fisheye intrinsics of the left [0] and right [1] camera (camerainfo*.yml K and D): fx, fy, cx, cy and the four
+       Kannala-Brandt coefficients; used only by fbus_undistort_fisheye */
+    double cam_k[2][4];
+    double cam_d[2][4];
     /* marker map (markersetup.yml / main.cpp:192-203); rotations are converted to quaternions with
        the Eigen Quaterniond(Matrix3d) rule exactly as main.cpp:201 does */
     int32_t n_markers;
@@ -219,6 +223,14 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
  */
 int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d,
                        int32_t* valid, int32_t mem);
+
+/*
+ * N4: cv::fisheye::undistortPoints(distorted, undistorted, K, D) as VISION::DetectArucoTag applies it to the detected
+ * corner pixels (vision.cpp:203,253,318,369): Kannala-Brandt inverse by Newton iterations on theta.
+ *   pixels [16][n] float32 (left xy x4, right xy x4; left rows use cam 0, right rows cam 1) -> normalised [16][n] float32,
+ *   the input layout of fbus_refract_solve / fbus_inair_solve.
+ */
+int fbus_undistort_fisheye(fbus_handle* h, const float* pixels, size_t n, float* normalised, int32_t mem);
 
 /* VISION::NormalTriangulation (vision.cpp:395-466: homogeneous DLT per stereo corner pair, land mode) followed by
    VISION::ComputeMarkerPose; same layouts and meaning as fbus_refract_solve. */

@@ -9,6 +9,7 @@
 
 #include "fbus_oracle.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <thread>
@@ -989,6 +990,37 @@ int orc_inair_solve(const fbus_config* cfg, const float* corners, size_t n, doub
         if (corners3d) for (int c = 0; c < 12; ++c) corners3d[(size_t)c * n + i] = P3[c];
         if (valid) valid[i] = ok ? 1 : 0;
     }
+    return FBUS_OK;
+}
+
+// N4: cv::fisheye::undistortPoints(distorted, undistorted, K, D), OpenCV 3.4.3 (vision.cpp:203,253,318,369)
+int orc_undistort_fisheye(const fbus_config* cfg, const float* pixels, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i)
+        for (int e = 0; e < 8; ++e) {
+            const int cam = e >> 2;
+            const double* K = cfg->cam_k[cam];
+            const double* D = cfg->cam_d[cam];
+            const double u = pixels[(size_t)(2 * e) * n + i], v = pixels[(size_t)(2 * e + 1) * n + i];
+            const double pwx = (u - K[2]) / K[0], pwy = (v - K[3]) / K[1];
+            double scale = 1.0;
+            double theta_d = std::sqrt(pwx * pwx + pwy * pwy);
+            theta_d = std::min(std::max(-3.14159265358979323846 / 2., theta_d), 3.14159265358979323846 / 2.);
+            if (theta_d > 1e-8) {
+                double theta = theta_d;
+                const double EPS = 1e-8;
+                for (int j = 0; j < 10; j++) {
+                    const double theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta4 * theta2, theta8 = theta6 * theta2;
+                    const double k0_theta2 = D[0] * theta2, k1_theta4 = D[1] * theta4, k2_theta6 = D[2] * theta6, k3_theta8 = D[3] * theta8;
+                    const double theta_fix = (theta * (1 + k0_theta2 + k1_theta4 + k2_theta6 + k3_theta8) - theta_d) /
+                                             (1 + 3 * k0_theta2 + 5 * k1_theta4 + 7 * k2_theta6 + 9 * k3_theta8);
+                    theta = theta - theta_fix;
+                    if (std::fabs(theta_fix) < EPS) break;
+                }
+                scale = std::tan(theta) / theta_d;
+            }
+            out[(size_t)(2 * e) * n + i] = (float)(pwx * scale);
+            out[(size_t)(2 * e + 1) * n + i] = (float)(pwy * scale);
+        }
     return FBUS_OK;
 }
 

@@ -47,6 +47,7 @@ int orc_step_windows(orc_handle* h, const fbus_imu_stream* imu, const fbus_det_f
 int orc_refract_solve(const fbus_config* cfg, const float* corners, size_t n, double* pose,
                       double* corners3d, int32_t* valid, int n_threads);
 int orc_inair_solve(const fbus_config* cfg, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid);
+int orc_undistort_fisheye(const fbus_config* cfg, const float* pixels, size_t n, float* out);
 int orc_marker_pose(const fbus_config* cfg, const double* corners3d, size_t n, double* pose);
 
 int orc_get_state(orc_handle* h, fbus_state_soa* out);

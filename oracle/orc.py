@@ -126,6 +126,17 @@ def refract_solve(cfg, corners: np.ndarray, n_threads=1):
     return pose, c3, valid
 
 
+def undistort_fisheye(cfg, pixels: np.ndarray):
+    n = pixels.shape[1]
+    assert pixels.dtype == np.float32 and pixels.flags["C_CONTIGUOUS"] and pixels.shape[0] == 16
+    out = np.zeros_like(pixels)
+    L = lib()
+    L.orc_undistort_fisheye.argtypes = [C.POINTER(capi.FbusConfig), C.c_void_p, C.c_size_t, C.c_void_p]
+    L.orc_undistort_fisheye.restype = C.c_int
+    assert L.orc_undistort_fisheye(C.byref(cfg), pixels.ctypes.data, n, out.ctypes.data) == 0
+    return out
+
+
 def inair_solve(cfg, corners: np.ndarray):
     """corners float32 [16][n] -> pose [7][n], corners3d [12][n], valid [n]  (NormalTriangulation + ComputeMarkerPose)"""
     n = corners.shape[1]
