@@ -486,6 +486,36 @@ static int stereo_solve(fbus_handle* h, const float* corners, size_t n, double* 
     return FBUS_OK;
 }
 
+int fbus_solve_to_detections(fbus_handle* h, const float* corners, const int32_t* marker_ids, size_t n_frames, size_t max_markers,
+                             int32_t underwater, int32_t gn_iters, int32_t* det_id, double* det_pose, int32_t mem) {
+    if (!h || !corners || !marker_ids || !det_id || !det_pose || max_markers == 0 || gn_iters < 0 || gn_iters > 50)
+        return fail(h, FBUS_E_BADARG, "fbus_solve_to_detections: bad argument");
+    const size_t n = n_frames * max_markers * h->B;
+    if (n == 0) return FBUS_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const float* dc;
+    const int32_t* di;
+    int rc = stage(h, h->scratch_in, corners, 16 * n, mem, &dc);
+    if (rc) return rc;
+    rc = stage(h, h->scratch_aux, marker_ids, n, mem, &di);
+    if (rc) return rc;
+    int32_t* oid = det_id;
+    double* opose = det_pose;
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, h->scratch_out.reserve(7 * n * sizeof(double) + n * sizeof(int32_t)));
+        opose = (double*)h->scratch_out.p;
+        oid = (int32_t*)(opose + 7 * n);
+    }
+    solve_to_det_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->k, h->gn, dc, di, n, h->B, underwater, gn_iters, oid, opose);
+    CUDA_TRY(h, cudaGetLastError());
+    if (mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(det_pose, opose, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(det_id, oid, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
 int fbus_undistort_fisheye(fbus_handle* h, const float* pixels, size_t n, float* normalised, int32_t mem) {
     if (!h || !pixels || !normalised) return fail(h, FBUS_E_BADARG, "fbus_undistort_fisheye: bad argument");
     if (n == 0) return FBUS_OK;

@@ -500,6 +500,49 @@ __global__ void __launch_bounds__(128) refract_gn_kernel(const __grid_constant__
     if (valid) valid[i] = dead ? 0 : 1;
 }
 
+// Vision front-end -> filter hand-off in one kernel (what VisionThreadFunction does between DetectArucoTag and
+// SetDetectionResult, vision.cpp:60-139): triangulate (refractive or in-air), marker pose, optional GN refinement, and
+// write the result straight into the detection-frame layout of fbus_det_frames: item i = (frame*m + slot)*B + filter,
+// pose element e at ((i / B) * 7 + e) * B + i % B, id = marker id or -1 when the marker was rejected (only markers
+// with isComputePose enter the DetectionResultList, vision.cpp:88-99).
+__global__ void __launch_bounds__(128) solve_to_det_kernel(const __grid_constant__ DevConsts k, const __grid_constant__ GnConsts g,
+                                                           const float* __restrict__ corners, const int32_t* __restrict__ ids_in, size_t n,
+                                                           size_t B, int underwater, int iters, int32_t* __restrict__ det_id,
+                                                           double* __restrict__ det_pose) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = ids_in[i];
+    double c[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) c[e] = (double)corners[(size_t)e * n + i];
+    double C[12];
+    bool dead = id < 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        double Pc[3];
+        const double nrm = underwater ? triangulate_corner(k, c[2 * e], c[2 * e + 1], c[8 + 2 * e], c[8 + 2 * e + 1], Pc)
+                                      : triangulate_corner_inair(k, c[2 * e], c[2 * e + 1], c[8 + 2 * e], c[8 + 2 * e + 1], Pc);
+        C[3 * e] = Pc[0]; C[3 * e + 1] = Pc[1]; C[3 * e + 2] = Pc[2];
+        if (nrm > k.dect_thres) dead = true;
+    }
+    double p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0};
+    if (!dead) {
+        marker_pose(C, k.rod_s, k.rod_c, p, q);
+        if (underwater && iters > 0) {
+            double Rm[9];
+            quat_to_rotmat_unit(q, Rm);
+            gn_refine(g, c, Rm, p, iters);
+            R2q(Rm, q);
+        }
+    }
+    det_id[i] = dead ? -1 : id;
+    double* out = det_pose + (i / B) * 7 * B + (i % B);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) out[(size_t)e * B] = p[e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[(size_t)(3 + e) * B] = q[e];
+}
+
 __global__ void __launch_bounds__(128) marker_pose_kernel(const __grid_constant__ DevConsts k, const double* __restrict__ c3d, size_t n,
                                                           double* __restrict__ pose) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

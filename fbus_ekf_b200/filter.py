@@ -101,6 +101,23 @@ class BatchFilter:
     def RefractSolveDevice(self, corners_ptr: int, n: int, pose_ptr: int, c3_ptr: int | None, valid_ptr: int | None):
         self._ck(self._lib.fbus_refract_solve(self._h, corners_ptr, n, pose_ptr, c3_ptr, valid_ptr, capi.FBUS_MEM_DEVICE))
 
+    def SolveToDetections(self, corners, marker_ids, n_frames: int, max_markers: int, underwater: bool = True, gn_iters: int = 0,
+                          det_id=None, det_pose=None, mem: int = capi.FBUS_MEM_HOST):
+        """corners float32 [16][W*m*B], marker_ids int32 [W][m][B] -> (det_id int32 [W][m][B], det_pose float64 [W][m][7][B]);
+        numpy arrays (host) or device pointers with preallocated outputs"""
+        if mem == capi.FBUS_MEM_HOST:
+            n = n_frames * max_markers * self.batch
+            assert corners.dtype == np.float32 and corners.shape == (16, n) and corners.flags["C_CONTIGUOUS"]
+            assert marker_ids.dtype == np.int32 and marker_ids.size == n and marker_ids.flags["C_CONTIGUOUS"]
+            det_id = np.zeros((n_frames, max_markers, self.batch), dtype=np.int32)
+            det_pose = np.zeros((n_frames, max_markers, 7, self.batch))
+            self._ck(self._lib.fbus_solve_to_detections(self._h, corners.ctypes.data, marker_ids.ctypes.data, n_frames, max_markers,
+                                                        int(underwater), gn_iters, det_id.ctypes.data, det_pose.ctypes.data, mem))
+            return det_id, det_pose
+        self._ck(self._lib.fbus_solve_to_detections(self._h, int(corners), int(marker_ids), n_frames, max_markers, int(underwater),
+                                                    gn_iters, int(det_id), int(det_pose), mem))
+        return det_id, det_pose
+
     def UndistortFisheye(self, pixels: np.ndarray) -> np.ndarray:
         """cv::fisheye::undistortPoints as DetectArucoTag applies it: pixel corners float32 [16][n] -> normalised float32 [16][n]"""
         assert pixels.dtype == np.float32 and pixels.flags["C_CONTIGUOUS"] and pixels.shape[0] == 16

@@ -84,7 +84,7 @@ def stereo_extrinsics(cfg: capi.FbusConfig):
 
 
 def truth_trajectory(cfg: capi.FbusConfig, duration: float, imu_rate: float = 200.0, frame_rate: float = 25.0, marker_id: int = 0,
-                     seed: int = 20260117, periodic: bool = False):
+                     seed: int = 20260117, periodic: bool = False, standoff: float = 0.50):
     """Smooth trajectory matching the envelope of the reference's logs (position extent < 0.8 m, |v| < 0.4 m/s, a few
     hundredths rad/s of rotation) in front of marker `marker_id`.  Gravity convention of the filter after
     InitializePose: g = (9.8, 0, 0) (filter.cpp:387), i.e. accel_body = R^T (p'' - g).
@@ -111,7 +111,7 @@ def truth_trajectory(cfg: capi.FbusConfig, duration: float, imu_rate: float = 20
         fr = np.repeat(harm, 3, axis=1)
         ap = ap * 0.25 / (harm * duration)
         ar = ar * 0.5 / (harm * duration)
-    p0 = np.array([-0.10, 0.05, 0.50])
+    p0 = np.array([-0.10, 0.05, standoff])  # `standoff` = distance from the marker plane
     q0 = np.array([-0.0203, -0.7053, 0.7086, -0.0065])
     q0 /= np.linalg.norm(q0)
 
@@ -277,3 +277,54 @@ def marker_corners_inair(cfg: capi.FbusConfig, Rm: np.ndarray, p: np.ndarray, si
     if noise > 0:
         out = out + (rng or np.random.default_rng(0)).normal(size=out.shape) * noise
     return np.ascontiguousarray(out.astype(np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- config 4: marker board
+def board_config(cfg: capi.FbusConfig, pitch: float = 0.35) -> capi.FbusConfig:
+    """BASELINE configs[3]: markers 0-7 re-posed as a 4 x 2 planar grid (pitch 0.35 m, side 0.28 m) in the plane of marker 0"""
+    import copy
+    c = copy.copy(cfg)
+    c.n_markers = 8
+    eye = [1, 0, 0, 0, 1, 0, 0, 0, 1]
+    for m in range(8):
+        i, j = m % 4, m // 4
+        c.marker_id[m] = m
+        c.marker_pos[3 * m + 0] = (i - 1.5) * pitch
+        c.marker_pos[3 * m + 1] = (j - 0.5) * pitch
+        c.marker_pos[3 * m + 2] = 0.0
+        for e in range(9):
+            c.marker_rot[9 * m + e] = eye[e]
+    return c
+
+
+def board_base_corners(cfg: capi.FbusConfig, traj: dict):
+    """noise-free stereo corner observations of every board marker for every frame of the truth trajectory, consistent with
+    the filter's own measurement model (P_ML = R_IL R^T (P_M - p - R P_IL), Q_ML = Q_IL * conj(q) * Q_M).
+    -> (corners float64 [16][W*m] with item index frame*m + slot, ids int32 [W][m])"""
+    R_IL, Q_IL, P_IL = filter_extrinsics(cfg)
+    m, W = cfg.n_markers, traj["truth_p"].shape[0]
+    p_all, R_all = np.zeros((W * m, 3)), np.zeros((W * m, 3, 3))
+    for w in range(W):
+        q = traj["truth_q"][w]
+        R = _q2R(q)
+        for s in range(m):
+            P_M = np.array(cfg.marker_pos[3 * s:3 * s + 3])
+            Q_M = quat_from_rotmat(np.array(cfg.marker_rot[9 * s:9 * s + 9]).reshape(3, 3))
+            p_all[w * m + s] = R_IL @ R.T @ (P_M - traj["truth_p"][w] - R @ P_IL)
+            qml = _qmul(_qmul(Q_IL, _qconj(q)), Q_M)
+            R_all[w * m + s] = _q2R(qml / np.linalg.norm(qml))
+    n = W * m
+    R_RL, P_LR = stereo_extrinsics(cfg)
+    Ri = np.linalg.inv(R_RL)
+    size = cfg.marker_size
+    cm = np.array([[0, 0, 0], [size, 0, 0], [size, size, 0], [0, size, 0]], dtype=np.float64)
+    out = np.zeros((16, n))
+    flip = np.array([-1.0, -1.0, 1.0])
+    for i in range(4):
+        XL = (p_all + np.einsum("nij,j->ni", R_all, cm[i])) * flip
+        XR = (XL - P_LR) @ Ri.T
+        uvL, uvR = forward_project(cfg, XL), forward_project(cfg, XR)
+        out[2 * i], out[2 * i + 1] = uvL[:, 0], uvL[:, 1]
+        out[8 + 2 * i], out[9 + 2 * i] = uvR[:, 0], uvR[:, 1]
+    ids = np.tile(np.arange(m, dtype=np.int32)[None, :], (W, 1))
+    return np.ascontiguousarray(out), np.ascontiguousarray(ids), p_all

@@ -225,6 +225,16 @@ int fbus_refract_solve(fbus_handle* h, const float* corners, size_t n, double* p
                        int32_t* valid, int32_t mem);
 
 /*
+ * Vision front-end -> filter hand-off (VisionThreadFunction between DetectArucoTag and SetDetectionResult,
+ * vision.cpp:60-139) for a whole batch: corners [16][W*m*B] float32 (item index (frame*m + slot)*B + filter) and the
+ * detected marker ids [W][m][B] (< 0 = empty slot) -> detection frames in the layout of fbus_det_frames:
+ * det_id [W][m][B] (-1 where the marker was rejected by the range gate) and det_pose [W][m][7][B].
+ * underwater: 1 = RefractionTriangulation, 0 = NormalTriangulation; gn_iters > 0 adds the Gauss-Newton refinement (R3).
+ */
+int fbus_solve_to_detections(fbus_handle* h, const float* corners, const int32_t* marker_ids, size_t n_frames, size_t max_markers,
+                             int32_t underwater, int32_t gn_iters, int32_t* det_id, double* det_pose, int32_t mem);
+
+/*
  * N4: cv::fisheye::undistortPoints(distorted, undistorted, K, D) as VISION::DetectArucoTag applies it to the detected
  * corner pixels (vision.cpp:203,253,318,369): Kannala-Brandt inverse by Newton iterations on theta.
  *   pixels [16][n] float32 (left xy x4, right xy x4; left rows use cam 0, right rows cam 1) -> normalised [16][n] float32,
