@@ -334,6 +334,8 @@ def run_ours(args):
     # ---- refractive solves/sec (second half of the metric): K3+K4 on 524,288 markers per launch ---------------------
     solves = bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak) if not args.no_solves else None
 
+    config4 = bench_config4(cfg, dev, local, rank, world, K, Wm) if not args.no_solves else None
+
     # ---- e2e: HOST buffers through the C ABI, H2D of every step's streams + D2H of the step's statistics -------------
     e2e = bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq) if not args.no_e2e else None
 
@@ -346,7 +348,7 @@ def run_ours(args):
                 "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(B, world), "e2e": e2e, "gpu_launches": K,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "stats": stats, "solves": solves,
-                "small_batch": small,
+                "small_batch": small, "config4": config4,
                 "timing": "CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -417,6 +419,58 @@ def bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak):
                          "unit": "TFLOP/s", "frac": rate * FLOP_SOLVE / fp64_peak,
                          "hbm": {"achieved": rate * BYTES_SOLVE / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": rate * BYTES_SOLVE / 1e9 / hbm_peak}}}
+
+
+def bench_config4(cfg, dev, local, rank, world, K, Wm):
+    """BASELINE configs[3]: 65,536 filters, per frame 8 board markers x 4 corners x stereo -> refractive solve with 5
+    Gauss-Newton iterations -> detection frames -> EKF (nearest of 8 markers), device-resident; one step = 1 s of stream."""
+    import torch
+    from fbus_ekf_b200 import BatchFilter, capi, synth
+    B4, m, gn = env_int("FBUS_BENCH_BATCH4", 65536), 8, 5
+    bcfg = synth.board_config(cfg)
+    traj = synth.truth_trajectory(bcfg, PERIOD, IMU_RATE, FRAME_RATE, periodic=True, standoff=1.0)
+    N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
+    base, ids, _ = synth.board_base_corners(bcfg, traj)
+    f = BatchFilter(bcfg, batch=B4, device=local)
+    stream = torch.cuda.ExternalStream(f.stream, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4 + rank)
+    n = W * m * B4
+    corners = torch.from_numpy(base.astype(np.float32)).to(dev).reshape(16, W * m, 1).expand(16, W * m, B4).reshape(16, n).contiguous()
+    corners += 2e-4 * torch.randn((16, n), device=dev, dtype=torch.float32, generator=g)
+    mids = torch.from_numpy(ids).to(dev).reshape(W, m, 1).expand(W, m, B4).contiguous()
+    det_id = torch.empty((W, m, B4), dtype=torch.int32, device=dev)
+    det_pose = torch.empty((W, m, 7, B4), dtype=torch.float64, device=dev)
+    imu_d = torch.from_numpy(traj["base_imu"]).to(dev).reshape(N, 6, 1).expand(N, 6, B4).contiguous()
+    imu_d += torch.tensor([0.015] * 3 + [1e-3] * 3, device=dev, dtype=torch.float64).reshape(1, 6, 1) * \
+        torch.randn((N, 6, B4), device=dev, dtype=torch.float64, generator=g)
+    torch.cuda.synchronize(dev)
+
+    def step(kk):
+        ti, tf = shifted(traj, kk)
+        f.SolveToDetections(corners.data_ptr(), mids.data_ptr(), W, m, True, gn, det_id.data_ptr(), det_pose.data_ptr(), capi.FBUS_MEM_DEVICE)
+        f.StepWindows(capi.make_imu_stream(ti, imu_d.data_ptr(), B4, capi.FBUS_MEM_DEVICE),
+                      capi.make_det_frames(tf, det_id.data_ptr(), det_pose.data_ptr(), B4, m, capi.FBUS_MEM_DEVICE), traj["win_off"], 0, W)
+    for kk in range(max(Wm, 3)):
+        step(kk)
+    f.Synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(K, 3)
+    e0.record(stream)
+    for kk in range(reps):
+        step(max(Wm, 3) + kk)
+    e1.record(stream)
+    f.Synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    st = f.GetState(with_cov=False)
+    err = np.linalg.norm(st["p"] - traj["truth_p"][-1][:, None], axis=0)
+    out = {"workload": "BASELINE configs[3]: 65,536 filters, 8 markers x 4 corners x stereo per frame, refractive solve + 5 GN "
+                       "iterations -> detections -> EKF, 1 s of 200 Hz IMU + 25 Hz frames per step",
+           "filters_per_gpu": B4, "ms_per_step": sec * 1e3, "filter_steps_per_s": world * B4 * (N + W) / sec,
+           "refractive_gn_solves_per_s": world * n / sec, "rmse_pos_m": float(np.sqrt(np.mean(err ** 2))),
+           "finite": bool(np.isfinite(st["p"]).all()), "gpu_launches_per_step": 2}
+    f.close()
+    return out
 
 
 def bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq):
