@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(128) solve_to_det_kernel(const __grid_constant
         if (underwater && iters > 0) {
             double Rm[9];
             quat_to_rotmat_unit(q, Rm);
-            gn_refine(g, c, Rm, p, iters);
+            gn_refine<false>(g, c, Rm, p, iters);
             R2q(Rm, q);
         }
     }

@@ -334,6 +334,14 @@ FBUS_HD double triangulate_corner_inair(const DevConsts& k, double xl, double yl
 // monotone equation  d0 t(s0) + d1 t(k1 s0) + (Z-d0-d1) t(k2 s0) = rho,  t(s) = s/sqrt(1-s^2),  for s0 = sin(theta_air)
 // (SURVEY A.1-4); Jacobian by the implicit-function theorem.  Right perturbation R_M <- R_M Exp(dphi).
 // =================================================================================================
+#ifndef FBUS_GN_UNROLL_ON
+#define FBUS_GN_UNROLL_ON 0  // 1: inline all 8 projections of a Gauss-Newton iteration (warm starts in registers)
+#endif
+#if FBUS_GN_UNROLL_ON
+#define FBUS_GN_UNROLL FBUS_UNROLL
+#else
+#define FBUS_GN_UNROLL _Pragma("unroll 1")
+#endif
 namespace fbus {
 
 struct GnConsts {
@@ -342,63 +350,77 @@ struct GnConsts {
     double size;                  // marker side (0.28 m, vision.hpp:114)
 };
 
-// projects X (camera frame) -> uv (2) and the 2x3 Jacobian d(uv)/dX (row-major J[0..2] = du/dX, J[3..5] = dv/dX)
-FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double* J) {
+// projects X (camera frame) -> uv (2) and, when JAC, the 2x3 Jacobian d(uv)/dX (row-major J[0..2] = du/dX,
+// J[3..5] = dv/dX).  s_io: warm start for s0 = sin(theta_air) (<= 0: straight-line guess) and, on return, the root --
+// the Gauss-Newton loop carries it from one iteration to the next, where the pose moves by ~the pixel noise and Newton
+// needs two steps instead of six.
+template <bool JAC = true>
+FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double* J, double& s_io) {
     const double rho2 = X[0] * X[0] + X[1] * X[1];
     const double Zw = X[2] - g.d0 - g.d1;
     const double rho = sqrt(rho2);
     if (rho < 1e-12) {  // paraxial limit
         const double den = 1.0 / (g.d0 + g.k1 * g.d1 + g.k2 * Zw);
         uv[0] = X[0] * den; uv[1] = X[1] * den;
-        J[0] = den; J[1] = 0.0; J[2] = -X[0] * den * den * g.k2;
-        J[3] = 0.0; J[4] = den; J[5] = -X[1] * den * den * g.k2;
+        if (JAC) {
+            J[0] = den; J[1] = 0.0; J[2] = -X[0] * den * den * g.k2;
+            J[3] = 0.0; J[4] = den; J[5] = -X[1] * den * den * g.k2;
+        }
+        s_io = 0.0;
         return;
     }
-    // Newton on f(s) = d0 t(s) + d1 t(k1 s) + Zw t(k2 s) - rho.  f is increasing and convex on [0,1): from the
-    // straight-line guess (left of the root) the first step lands right of it and the iteration then decreases
-    // monotonically to the root; the only safeguard needed is to stay inside the domain.
-    double s = rho * rsqrt_d(rho2 + X[2] * X[2]);
-    double t0 = 0.0, t2 = 0.0, dt0 = 0.0, gs = 1.0;
+    // Newton on f(s) = d0 t(s) + d1 t(k1 s) + Zw t(k2 s) - rho.  f is increasing and convex on [0,1): from any start
+    // the first step lands right of the root and the iteration then decreases monotonically to it; the only safeguard
+    // needed is to stay inside the domain.  The loop leaves with r0,r1,r2 evaluated AT the accepted s.
+    double s = (s_io > 0.0 && s_io < 1.0) ? s_io : rho * rsqrt_d(rho2 + X[2] * X[2]);
+    const double k1s = g.k1 * g.k1, k2s = g.k2 * g.k2, a1 = g.d1 * g.k1, a2 = Zw * g.k2;
+    double r0, r1, r2, gs;
     for (int it = 0; it < 50; ++it) {
-        const double r0 = rsqrt_d(1.0 - s * s), r1 = rsqrt_d(1.0 - g.k1 * g.k1 * s * s), r2 = rsqrt_d(1.0 - g.k2 * g.k2 * s * s);
-        const double c0 = r0 * r0, c1 = r1 * r1, c2 = r2 * r2;
-        gs = g.d0 * c0 * r0 + g.d1 * g.k1 * c1 * r1 + Zw * g.k2 * c2 * r2;
-        const double f = g.d0 * s * r0 + g.d1 * g.k1 * s * r1 + Zw * g.k2 * s * r2 - rho;
+        const double s2 = s * s;
+        r0 = rsqrt_d(1.0 - s2); r1 = rsqrt_d(1.0 - k1s * s2); r2 = rsqrt_d(1.0 - k2s * s2);
+        gs = g.d0 * (r0 * r0) * r0 + a1 * (r1 * r1) * r1 + a2 * (r2 * r2) * r2;
+        const double f = s * (g.d0 * r0 + a1 * r1 + a2 * r2) - rho;
         double sn = s - f * rcp_d(gs);
         if (!(sn < 1.0)) sn = 0.5 * (s + 1.0);
         if (!(sn > 0.0)) sn = 0.5 * s;
         const double ds = sn - s;
+        if ((ds < 0 ? -ds : ds) <= 4.5e-16 * s) break;  // s is the root to 2 ulp; r0..gs are its values
         s = sn;
-        if ((ds < 0 ? -ds : ds) <= 2.3e-16 * s) break;
     }
-    {   // values at the converged s
-        const double r0 = rsqrt_d(1.0 - s * s), r1 = rsqrt_d(1.0 - g.k1 * g.k1 * s * s), r2 = rsqrt_d(1.0 - g.k2 * g.k2 * s * s);
-        const double c0 = r0 * r0, c1 = r1 * r1, c2 = r2 * r2;
-        t0 = s * r0;
-        t2 = g.k2 * s * r2;
-        dt0 = c0 * r0;
-        gs = g.d0 * dt0 + g.d1 * g.k1 * c1 * r1 + Zw * g.k2 * c2 * r2;
-    }
+    s_io = s;
+    const double t0 = s * r0;
     const double ir = rcp_d(rho);
     const double xh = X[0] * ir, yh = X[1] * ir;
     uv[0] = t0 * xh; uv[1] = t0 * yh;
-    const double a = t0 * ir;      // tau / rho
-    const double igs = rcp_d(gs);
-    const double b = dt0 * igs;    // t'(s0) / g_s
-    J[0] = a * (1.0 - xh * xh) + b * xh * xh; J[1] = (b - a) * xh * yh;
-    J[3] = J[1];                               J[4] = a * (1.0 - yh * yh) + b * yh * yh;
-    const double cz = -dt0 * t2 * igs;
-    J[2] = cz * xh; J[5] = cz * yh;
+    if (JAC) {
+        const double t2 = g.k2 * s * r2, dt0 = (r0 * r0) * r0;
+        const double a = t0 * ir;      // tau / rho
+        const double igs = rcp_d(gs);
+        const double b = dt0 * igs;    // t'(s0) / g_s
+        J[0] = a * (1.0 - xh * xh) + b * xh * xh; J[1] = (b - a) * xh * yh;
+        J[3] = J[1];                               J[4] = a * (1.0 - yh * yh) + b * yh * yh;
+        const double cz = -dt0 * t2 * igs;
+        J[2] = cz * xh; J[5] = cz * yh;
+    }
+}
+FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double* J) {
+    double s = 0.0;
+    project_refr<true>(g, X, uv, J, s);
 }
 
 // residuals and normal equations for pose (Rm row-major 3x3, p) against the 16 observed coordinates c[16]
-// (Lx0,Ly0..Lx3,Ly3,Rx0..Ry3).  H: 6x6 lower-packed J^T J, gvec: J^T r, returns the cost sum r^2.
-FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm, const double* p, double* H, double* gvec) {
-    FBUS_UNROLL
-    for (int i = 0; i < 21; ++i) H[i] = 0.0;
-    FBUS_UNROLL
-    for (int i = 0; i < 6; ++i) gvec[i] = 0.0;
+// (Lx0,Ly0..Lx3,Ly3,Rx0..Ry3).  H: 6x6 lower-packed J^T J, gvec: J^T r, returns the cost sum r^2.  sw[8]: Newton warm
+// starts per (corner, camera), carried across Gauss-Newton iterations.  JAC = false: cost only (H, gvec untouched).
+template <bool JAC = true>
+FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm, const double* p, double* H, double* gvec, double* sw) {
+    if (JAC) {
+        FBUS_UNROLL
+        for (int i = 0; i < 21; ++i) H[i] = 0.0;
+        FBUS_UNROLL
+        for (int i = 0; i < 6; ++i) gvec[i] = 0.0;
+    }
     double cost = 0.0;
+    FBUS_GN_UNROLL
     for (int i = 0; i < 4; ++i) {
         const double cm[3] = {(i == 1 || i == 2) ? g.size : 0.0, (i >= 2) ? g.size : 0.0, 0.0};  // (0,0),(s,0),(s,s),(0,s)
         double Rc[3];
@@ -415,6 +437,7 @@ FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm
             D[r * 6 + 4] = -fs * (Rm[r * 3 + 2] * cm[0] - Rm[r * 3 + 0] * cm[2]);
             D[r * 6 + 5] = -fs * (Rm[r * 3 + 0] * cm[1] - Rm[r * 3 + 1] * cm[0]);
         }
+        FBUS_GN_UNROLL
         for (int cam = 0; cam < 2; ++cam) {
             double X[3], DX[18];
             if (cam == 0) {
@@ -432,9 +455,10 @@ FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm
                         DX[r * 6 + e] = g.R_RL_inv[r * 3] * D[e] + g.R_RL_inv[r * 3 + 1] * D[6 + e] + g.R_RL_inv[r * 3 + 2] * D[12 + e];
             }
             double uv[2], Jp[6];
-            project_refr(g, X, uv, Jp);
+            project_refr<JAC>(g, X, uv, Jp, sw[cam * 4 + i]);
             const double ru = uv[0] - c[cam * 8 + 2 * i], rv = uv[1] - c[cam * 8 + 2 * i + 1];
             cost += ru * ru + rv * rv;
+            if (!JAC) continue;
             double Ju[6], Jv[6];
             FBUS_UNROLL
             for (int e = 0; e < 6; ++e) {
@@ -452,12 +476,27 @@ FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm
     return cost;
 }
 
-// Gauss-Newton iterations; Rm, p updated in place; returns the final cost (sum of squared residuals)
+FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm, const double* p, double* H, double* gvec) {
+    double sw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    return gn_normal_eq<true>(g, c, Rm, p, H, gvec, sw);
+}
+
+// Gauss-Newton iterations; Rm, p updated in place; returns the final cost (sum of squared residuals) when FINAL_COST
+// (one more residual evaluation), else the cost at the start of the last iteration.
+template <bool FINAL_COST = true>
 FBUS_HD double gn_refine(const GnConsts& g, const double* c, double* Rm, double* p, int iters) {
     double cost = 0.0;
+    // Newton warm starts: the seed pose reproduces the observed corners to ~the pixel noise, so the observed pixel's
+    // own air angle sin(theta) = |uv| / sqrt(1 + |uv|^2) is within ~1e-4 of the root of the first projection
+    double sw[8];
+    FBUS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+        const double r2 = c[2 * e] * c[2 * e] + c[2 * e + 1] * c[2 * e + 1];
+        sw[e] = sqrt(r2) * rsqrt_d(1.0 + r2);
+    }
     for (int it = 0; it < iters; ++it) {
         double H[21], gv[6], Li[6], d[6];
-        cost = gn_normal_eq(g, c, Rm, p, H, gv);
+        cost = gn_normal_eq<true>(g, c, Rm, p, H, gv, sw);
         CholStep<6, 0>::run(H, Li);
         // solve H d = -g
         FBUS_UNROLL
@@ -493,8 +532,7 @@ FBUS_HD double gn_refine(const GnConsts& g, const double* c, double* Rm, double*
         FBUS_UNROLL
         for (int e = 0; e < 9; ++e) Rm[e] = Rn[e];
     }
-    double H[21], gv[6];
-    cost = gn_normal_eq(g, c, Rm, p, H, gv);
+    if (FINAL_COST) cost = gn_normal_eq<false>(g, c, Rm, p, nullptr, nullptr, sw);
     return cost;
 }
 
