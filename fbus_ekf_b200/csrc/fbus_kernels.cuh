@@ -466,8 +466,11 @@ __global__ void __launch_bounds__(128) inair_kernel(const __grid_constant__ DevC
 }
 
 // K3+K4+K5: closed-form solve, then Gauss-Newton refinement of the pose on the stereo reprojection error (R3)
+#ifndef FBUS_GN_MINB
+#define FBUS_GN_MINB 4  // measured on B200: 4 CTAs/SM (128 regs, small spills) beats 2 CTAs/SM at 216 regs by 12 %
+#endif
 template <typename CT>
-__global__ void __launch_bounds__(128) refract_gn_kernel(const __grid_constant__ DevConsts k, const __grid_constant__ GnConsts g,
+__global__ void __launch_bounds__(128, FBUS_GN_MINB) refract_gn_kernel(const __grid_constant__ DevConsts k, const __grid_constant__ GnConsts g,
                                                          const CT* __restrict__ corners, size_t n, int iters, double* __restrict__ pose,
                                                          double* __restrict__ cost_out, int32_t* __restrict__ valid) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(128) refract_gn_kernel(const __grid_constant__
 // write the result straight into the detection-frame layout of fbus_det_frames: item i = (frame*m + slot)*B + filter,
 // pose element e at ((i / B) * 7 + e) * B + i % B, id = marker id or -1 when the marker was rejected (only markers
 // with isComputePose enter the DetectionResultList, vision.cpp:88-99).
-__global__ void __launch_bounds__(128) solve_to_det_kernel(const __grid_constant__ DevConsts k, const __grid_constant__ GnConsts g,
+__global__ void __launch_bounds__(128, FBUS_GN_MINB) solve_to_det_kernel(const __grid_constant__ DevConsts k, const __grid_constant__ GnConsts g,
                                                            const float* __restrict__ corners, const int32_t* __restrict__ ids_in, size_t n,
                                                            size_t B, int underwater, int iters, int32_t* __restrict__ det_id,
                                                            double* __restrict__ det_pose) {

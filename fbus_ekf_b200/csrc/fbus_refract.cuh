@@ -337,6 +337,9 @@ FBUS_HD double triangulate_corner_inair(const DevConsts& k, double xl, double yl
 #ifndef FBUS_GN_UNROLL_ON
 #define FBUS_GN_UNROLL_ON 0  // 1: inline all 8 projections of a Gauss-Newton iteration (warm starts in registers)
 #endif
+#ifndef FBUS_GN_NEWTON_TOL
+#define FBUS_GN_NEWTON_TOL 1e-9
+#endif
 #if FBUS_GN_UNROLL_ON
 #define FBUS_GN_UNROLL FBUS_UNROLL
 #else
@@ -354,7 +357,8 @@ struct GnConsts {
 // J[3..5] = dv/dX).  s_io: warm start for s0 = sin(theta_air) (<= 0: straight-line guess) and, on return, the root --
 // the Gauss-Newton loop carries it from one iteration to the next, where the pose moves by ~the pixel noise and Newton
 // needs two steps instead of six.
-template <bool JAC = true>
+// FAST: stop Newton one evaluation early (see the loop); exact root for uv, 1e-9-relative Jacobian -- for the GN loop.
+template <bool JAC = true, bool FAST = false>
 FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double* J, double& s_io) {
     const double rho2 = X[0] * X[0] + X[1] * X[1];
     const double Zw = X[2] - g.d0 - g.d1;
@@ -374,7 +378,7 @@ FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double
     // needed is to stay inside the domain.  The loop leaves with r0,r1,r2 evaluated AT the accepted s.
     double s = (s_io > 0.0 && s_io < 1.0) ? s_io : rho * rsqrt_d(rho2 + X[2] * X[2]);
     const double k1s = g.k1 * g.k1, k2s = g.k2 * g.k2, a1 = g.d1 * g.k1, a2 = Zw * g.k2;
-    double r0, r1, r2, gs;
+    double r0, r1, r2, gs, ds = 0.0;
     for (int it = 0; it < 50; ++it) {
         const double s2 = s * s;
         r0 = rsqrt_d(1.0 - s2); r1 = rsqrt_d(1.0 - k1s * s2); r2 = rsqrt_d(1.0 - k2s * s2);
@@ -383,12 +387,16 @@ FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double
         double sn = s - f * rcp_d(gs);
         if (!(sn < 1.0)) sn = 0.5 * (s + 1.0);
         if (!(sn > 0.0)) sn = 0.5 * s;
-        const double ds = sn - s;
-        if ((ds < 0 ? -ds : ds) <= 4.5e-16 * s) break;  // s is the root to 2 ulp; r0..gs are its values
+        ds = sn - s;
+        // |ds| <= 1e-9 s: the Newton step that follows would move s by ~ds^2 (1e-18 s): sn is the root to rounding.
+        // r0..gs were evaluated at s = sn - ds; tau below is corrected to first order (error ~ t'' ds^2 / 2 < 1e-16),
+        // the Jacobian keeps a 1e-9 relative error, which only perturbs the GN step by 1e-9 of its length.
+        if ((ds < 0 ? -ds : ds) <= (FAST ? FBUS_GN_NEWTON_TOL : 4.5e-16) * s) break;
         s = sn;
+        ds = 0.0;
     }
-    s_io = s;
-    const double t0 = s * r0;
+    s_io = s + ds;
+    const double t0 = s * r0 + (r0 * r0) * r0 * ds;
     const double ir = rcp_d(rho);
     const double xh = X[0] * ir, yh = X[1] * ir;
     uv[0] = t0 * xh; uv[1] = t0 * yh;
@@ -405,7 +413,7 @@ FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double
 }
 FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double* J) {
     double s = 0.0;
-    project_refr<true>(g, X, uv, J, s);
+    project_refr<true, false>(g, X, uv, J, s);
 }
 
 // residuals and normal equations for pose (Rm row-major 3x3, p) against the 16 observed coordinates c[16]
@@ -455,7 +463,7 @@ FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm
                         DX[r * 6 + e] = g.R_RL_inv[r * 3] * D[e] + g.R_RL_inv[r * 3 + 1] * D[6 + e] + g.R_RL_inv[r * 3 + 2] * D[12 + e];
             }
             double uv[2], Jp[6];
-            project_refr<JAC>(g, X, uv, Jp, sw[cam * 4 + i]);
+            project_refr<JAC, true>(g, X, uv, Jp, sw[cam * 4 + i]);
             const double ru = uv[0] - c[cam * 8 + 2 * i], rv = uv[1] - c[cam * 8 + 2 * i + 1];
             cost += ru * ru + rv * rv;
             if (!JAC) continue;
