@@ -22,10 +22,6 @@
 #ifndef FBUS_TL_REGS
 #define FBUS_TL_REGS 1
 #endif
-// 1: both warps of a filter group share the covariance sweeps of the update; 0: the covariance warp does it alone
-#ifndef FBUS_COOP_UPDATE
-#define FBUS_COOP_UPDATE 0
-#endif
 // 1: the per-sample ring barrier is private to a warp pair (64 threads); the CTA re-aligns once per frame
 #ifndef FBUS_PAIR_BARRIER
 #define FBUS_PAIR_BARRIER 1
@@ -60,6 +56,31 @@ struct SplitShared {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// Hand-off protocol per detection frame (barriers: (a) CTA-wide, the others private to the warp pair):
+//   (a)      IMU ranges posted                      -> both roles know [lo, hi)
+//   step(i)  ring record i published                 (one per IMU sample; the nominal warp is one sample ahead)
+//   (r)      update request posted                   -- written into the ring slot that sample `hi` WOULD use, which is
+//                                                       free while the covariance warp still works on sample hi-1, so the
+//                                                       request is on the table when that warp leaves its last step
+//   (d)      update results posted                   -- meanwhile the nominal warp has planned the NEXT frame (detection
+//                                                       scan, marker lookup, F5/F6b vision pose: none depend on the state)
+// The next frame's (a) doubles as "results consumed".
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RQ_EXTRA = 44;  // the request needs 23 doubles: 22 in the free ring slot + this one
+
+template <int NT>
+__device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) {
+#if FBUS_PAIR_BARRIER
+    return sh.any_upd[wq];
+#else
+    int any = sh.any_upd[0];
+#pragma unroll
+    for (int q = 1; q < NT / 64; ++q) any |= sh.any_upd[q];
+    return any;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // COVARIANCE role: owns P (shared memory; top-left 9x9 in registers while propagating)
 // ------------------------------------------------------------------------------------------------------------------
 template <int BSF, bool JOSEPH>
@@ -69,13 +90,16 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
     const size_t B = prm.B;
     const Cov<BSF> P{smem + fl};
     double* const X = smem + (size_t)NPK * BSF + fl;
+    const int wq = fl >> 5;
     for (int e = 0; e < NPK; ++e) smem[e * BSF + fl] = prm.P[(size_t)e * B + b];
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
         cta_bar<NT>();  // (a) the nominal warps have posted their IMU ranges
         uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
 #pragma unroll
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
+        int fs = 0;  // ring slot that carries the update request
         if (lo < hi) {
+            fs = (int)((hi - lo) & 1u);
 #if FBUS_TL_REGS
             double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
             tl_load<BSF>(P, TL);
@@ -85,7 +109,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             br_load<BSF>(P, BR);
 #endif
             for (uint32_t i = lo; i < hi; ++i) {
-                step_bar<NT>(fl >> 5);  // record (i) is complete; the nominal warp moves on to sample i+1
+                step_bar<NT>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
                 const int slot = (int)((i - lo) & 1u);
                 if (sflag[slot][fl]) {
                     const double* rec = X + (size_t)slot * 22 * BSF;
@@ -110,68 +134,22 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             br_store_diag<BSF>(P, BR);
 #endif
         }
-        cta_bar<NT>();  // (b) ring consumed: the exchange area is free for the update hand-off
-        cta_bar<NT>();  // (c) update requests posted
-        int any = sh.any_upd[0];
-#pragma unroll
-        for (int q = 1; q < NW; ++q) any |= sh.any_upd[q];
-#if FBUS_COOP_UPDATE
-        if (any) {
-            // Cooperative update.  This warp computes the gain factors (prologue) from the posted measurement and pose,
-            // publishes Lc and y, then applies the first half-rank factor Za while the nominal warp applies the second
-            // (Zb).  Both factors come from the OLD covariance; the two sweeps work on disjoint row sets and swap.
-            const int req = sflag[2][fl];
-            double Z[54];
-            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-            double Cm[21];
-            if (req) {
-                Nominal t;
-                double yP[3], yQ[4], y[6];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) yP[c] = X[(size_t)c * BSF];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { yQ[c] = X[(size_t)(3 + c) * BSF]; t.q[c] = X[(size_t)(7 + c) * BSF]; }
-#pragma unroll
-                for (int c = 0; c < 9; ++c) t.R[c] = X[(size_t)(11 + c) * BSF];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) t.p[c] = X[(size_t)(20 + c) * BSF];
-                const MarkerConst mkc = prm.tab->mk[req - 1];  // 3 KB table, L2-resident
-                // X = L^-1 Hs (42 doubles) is parked in the exchange area: its inputs are already in registers
-                update_prologue<BSF, BSF, JOSEPH>(P, t, k, mkc, yP, yQ, Cm, y, X);
-#pragma unroll
-                for (int c = 0; c < 21; ++c) X[(size_t)c * BSF] = Cm[c];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) X[(size_t)(21 + c) * BSF] = y[3 + c];
-                y0 = y[0]; y1 = y[1]; y2 = y[2];
-            }
-            cta_bar<NT>();  // (c2) gain factors published
-            if (req) update_Za<BSF>(P, Cm, Z);
-            cta_bar<NT>();  // (d1) both factors taken from the old covariance
-            if (req) update_sweep<BSF, 0, 5>(P, Z);
-            cta_bar<NT>();  // (d2)
-            if (req) {
-                update_sweep<BSF, 5, 18>(P, Z);
-                double dx[18];
-                update_dx<false>(Z, y0, y1, y2, dx);
-#pragma unroll
-                for (int c = 0; c < 18; ++c) X[(size_t)(27 + c) * BSF] = dx[c];
-            }
-            cta_bar<NT>();  // (e) first half of dx posted
-        }
-#else
-        if (any) {
+        step_bar<NT>(wq);  // (r) update request posted (normally long before this warp gets here)
+        if (pair_any<NT>(sh, wq)) {
             const int req = sflag[2][fl];
             if (req) {
+                const double* rq = X + (size_t)fs * 22 * BSF;
                 Nominal t;
                 double yP[3], yQ[4];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) yP[c] = X[(size_t)c * BSF];
+                for (int c = 0; c < 3; ++c) yP[c] = rq[(size_t)c * BSF];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { yQ[c] = X[(size_t)(3 + c) * BSF]; t.q[c] = X[(size_t)(7 + c) * BSF]; }
+                for (int c = 0; c < 4; ++c) { yQ[c] = rq[(size_t)(3 + c) * BSF]; t.q[c] = rq[(size_t)(7 + c) * BSF]; }
 #pragma unroll
-                for (int c = 0; c < 9; ++c) t.R[c] = X[(size_t)(11 + c) * BSF];
+                for (int c = 0; c < 9; ++c) t.R[c] = rq[(size_t)(11 + c) * BSF];
+                t.p[0] = rq[(size_t)20 * BSF]; t.p[1] = rq[(size_t)21 * BSF]; t.p[2] = X[(size_t)RQ_EXTRA * BSF];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) { t.p[c] = X[(size_t)(20 + c) * BSF]; t.v[c] = 0.0; t.ba[c] = 0.0; t.bg[c] = 0.0; t.g[c] = 0.0; }
+                for (int c = 0; c < 3; ++c) { t.v[c] = 0.0; t.ba[c] = 0.0; t.bg[c] = 0.0; t.g[c] = 0.0; }
                 t.t = 0.0;
                 const MarkerConst mkc = prm.tab->mk[req - 1];
                 measurement_update<BSF, JOSEPH ? 1 : 0>(P, t, k, mkc, yP, yQ);
@@ -187,10 +165,8 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #pragma unroll
                 for (int c = 0; c < 4; ++c) X[(size_t)(26 + c) * BSF] = t.q[c];
             }
-            cta_bar<NT>();  // (d) results posted
-            cta_bar<NT>();  // (e) results consumed: the exchange area may be overwritten by the next frame's ring
+            step_bar<NT>(wq);  // (d) results posted
         }
-#endif
     }
     if (live)
         for (int e = 0; e < NPK; ++e) prm.P[(size_t)e * B + b] = smem[e * BSF + fl];
@@ -199,14 +175,148 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 // ------------------------------------------------------------------------------------------------------------------
 // NOMINAL role: owns the nominal state (registers), the streams, and all per-frame decisions
 // ------------------------------------------------------------------------------------------------------------------
+// What a frame will do, decided from the detections alone (filter.cpp:329-341 / 418-430 / 639-675): nothing in here
+// depends on the filter state except `inited`, `prev_id`, `cursor` and the nominal time, none of which the update changes,
+// so the plan of frame w+1 is made while the covariance warp runs frame w's update.
+struct FramePlan {
+    bool do_prop, apply_init, apply_reset;
+    int req;                 // marker index + 1 of the update, 0 = no update
+    uint32_t p_first, p_end;
+    double t_det, t_end;
+    double y[7];             // measurement of the update (p, q of the chosen detection)
+    double qv[4], pv[3];     // vision-only pose for init / reset
+};
+
+template <int BSF>
+__device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts& k, uint32_t w, size_t b, bool live, uint32_t cursor,
+                                           double n_t, int inited, int& prev_id, int& status, FramePlan& pl) {
+    const size_t B = prm.B;
+    const int mode = prm.mode;
+    const bool fused = (mode & M_FUSED) != 0;
+    const bool uses_det = (mode & (M_INIT | M_RESET | M_UPDATE | M_FUSED)) != 0;
+    pl.do_prop = pl.apply_init = pl.apply_reset = false;
+    pl.req = 0;
+    pl.p_first = pl.p_end = 0;
+    pl.t_det = pl.t_end = 0.0;
+    bool do_update = false;
+    int n_det = 0, idx_near = 0, idx_prev = 0;
+    double md = 10.0, prev_dist = 0.0;
+    // ---- scan this frame's detections (filter.cpp:329-341 / 418-430 / 639-658) ----------------
+    if (uses_det) {
+        pl.t_det = prm.det_t[w];
+        for (int s = 0; s < prm.m; ++s) {
+            const size_t slot = (size_t)w * prm.m + s;
+            const int id = prm.det_id[slot * B + b];
+            if (id < 0) continue;
+            const double* pp = prm.det_pose + slot * 7 * B + b;
+            const double px = pp[0], py = pp[B], pz = pp[2 * B];
+            const double dist = sqrt(px * px + py * py + pz * pz);
+            if (n_det == 0) { idx_near = s; idx_prev = s; }  // detectionResult_[0] defaults (min_dist_id = 0)
+            if (dist < md) { md = dist; idx_near = s; }
+            if (id == prev_id) { prev_dist = dist; idx_prev = s; }
+            ++n_det;
+        }
+    }
+    int idx_upd = idx_near;  // nearest, or the previously used marker within the switch threshold (filter.cpp:660-664)
+    {
+        const double dd = prev_dist - md;
+        if ((dd < 0 ? -dd : dd) < k.switch_thres && prev_dist != 0) idx_upd = idx_prev;
+    }
+    bool do_init = false, do_reset = false;
+    uint32_t n_before = prm.n_imu_before;
+    if (fused) {
+        if (n_det == 0) {
+            status |= FBUS_ST_NO_DETECTION;  // filter thread not woken (vision.cpp:136-140)
+        } else if (!inited) {
+            do_init = true;
+            n_before = 0;
+            const uint32_t hi = prm.win_off[w + 1];
+            for (uint32_t i = cursor; i < hi; ++i) n_before += (prm.imu_t[i] <= pl.t_det) ? 1u : 0u;
+        } else {
+            do_reset = pl.do_prop = do_update = true;
+            pl.p_first = cursor;
+            pl.p_end = prm.win_off[w + 1];
+            pl.t_end = pl.t_det;
+        }
+    } else {
+        do_init = (mode & M_INIT) != 0;
+        do_reset = (mode & M_RESET) != 0;
+        do_update = (mode & M_UPDATE) != 0;
+        if (mode & M_PROP) {
+            pl.do_prop = true;
+            pl.p_first = prm.prop_first;
+            pl.p_end = prm.prop_first + prm.prop_count;
+            pl.t_end = prm.prop_t_end;
+        }
+        if ((mode & M_UPDATE) && n_det == 0) status |= FBUS_ST_NO_DETECTION;
+    }
+    // ---- F6b InitializePose (filter.cpp:291-399) / F5 ResetSystemState (filter.cpp:405-477) -------
+    if ((do_init || do_reset) && n_det > 0) {
+        bool ok = !(md > k.max_dist);
+        if (do_init) ok = ok && (n_before > 0);
+        int mk = -1;
+        double dp[3], dq[4];
+        if (ok) {
+            const size_t slot = (size_t)w * prm.m + idx_near;
+            const int did = prm.det_id[slot * B + b];
+            const double* pp = prm.det_pose + slot * 7 * B + b;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dp[c] = pp[(size_t)c * B];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dq[c] = pp[(size_t)(3 + c) * B];
+            mk = find_marker(k, prm.tab, did);
+            ok = mk >= 0;
+        }
+        if (ok) {
+            double Rv[9];
+            const MarkerConst mkc = prm.tab->mk[mk];
+            vision_pose(k, mkc, dp, dq, pl.qv, Rv, pl.pv);
+            double t_now = n_t;
+            int inited_now = inited;
+            if (do_init) { pl.apply_init = true; t_now = pl.t_det; inited_now = 1; }
+            if (do_reset) {
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) prm.nom[(size_t)(F_PV + i) * B + b] = pl.pv[i];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_QV + i) * B + b] = pl.qv[i];
+                }
+                if (pl.t_det - t_now > k.reset_gap && inited_now) {
+                    pl.apply_reset = true;
+                    status |= FBUS_ST_RESET_DONE;  // P, g and the carried R stay untouched
+                }
+            }
+        } else {
+            if (do_init) status |= FBUS_ST_INIT_FAILED;
+            if (do_reset) status |= FBUS_ST_RESET_SKIPPED;
+        }
+    } else if (do_init) {
+        status |= FBUS_ST_INIT_FAILED;
+    }
+    // ---- marker and measurement of this frame's update (filter.cpp:666-675) ---------------------------------
+    if (do_update && n_det > 0) {
+        const size_t slot = (size_t)w * prm.m + idx_upd;
+        const int did = prm.det_id[slot * B + b];
+        const int mk = find_marker(k, prm.tab, did);
+        if (mk >= 0) {
+            prev_id = did;
+            pl.req = mk + 1;
+            const double* pp = prm.det_pose + slot * 7 * B + b;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) pl.y[c] = pp[(size_t)c * B];
+        } else {
+            status |= FBUS_ST_UPDATE_SKIPPED;
+        }
+    }
+}
+
 template <int BSF>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
                                              int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
     constexpr int NT = 2 * BSF, NW = BSF / 32;
     const size_t B = prm.B;
     double* const X = smem + (size_t)NPK * BSF + fl;
-    const int mode = prm.mode;
-    const bool fused = (mode & M_FUSED) != 0;
+    const bool fused = (prm.mode & M_FUSED) != 0;
     const int wq = fl >> 5;  // nominal warp index
     Nominal n;
     n.t = prm.nom[(size_t)F_T * B + b];
@@ -226,154 +336,38 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     int inited = prm.init[b];
     int status = prm.status[b];
     uint32_t cursor = fused ? prm.win_off[prm.w0] : 0u;
-    // prefetched inputs of the NEXT frame (issued while this warp waits for the covariance warp's update): frame time,
-    // detection slot 0, and the first IMU sample of the next window
-    uint32_t pf_w = 0xffffffffu, pf_i = 0xffffffffu;
-    int pf_id = -1;
-    double pf_tdet = 0.0, pf_pose[7], pf_st = 0.0, pf_sd[6];
-    const bool uses_det = (mode & (M_INIT | M_RESET | M_UPDATE | M_FUSED)) != 0;
+    // first IMU sample of the NEXT window, prefetched while this warp waits for the covariance warp's update
+    uint32_t pf_i = 0xffffffffu;
+    double pf_st = 0.0, pf_sd[6];
+
+    FramePlan pl;
+    if (prm.w0 < prm.w1) plan_frame<BSF>(prm, k, prm.w0, b, live, cursor, n.t, inited, prev_id, status, pl);
 
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
-        bool do_prop = false, do_update = false;
-        uint32_t p_first = 0, p_end = 0;
-        double t_end = 0.0;
-        int n_det = 0, idx_upd = 0;
-        double t_det = 0.0;
-        {
-            // ---- scan this frame's detections (filter.cpp:329-341 / 418-430 / 639-658) ----------------
-            int idx_near = 0, idx_prev = 0;
-            double md = 10.0, prev_dist = 0.0;
-            if (uses_det) {
-                const bool pf = (pf_w == w);
-                t_det = pf ? pf_tdet : prm.det_t[w];
-                for (int s = 0; s < prm.m; ++s) {
-                    const size_t slot = (size_t)w * prm.m + s;
-                    const bool use_pf = pf && s == 0;
-                    const int id = use_pf ? pf_id : prm.det_id[slot * B + b];
-                    if (id < 0) continue;
-                    const double* pp = prm.det_pose + slot * 7 * B + b;
-                    const double px = use_pf ? pf_pose[0] : pp[0], py = use_pf ? pf_pose[1] : pp[B], pz = use_pf ? pf_pose[2] : pp[2 * B];
-                    const double dist = sqrt(px * px + py * py + pz * pz);
-                    if (n_det == 0) { idx_near = s; idx_prev = s; }  // detectionResult_[0] defaults (min_dist_id = 0)
-                    if (dist < md) { md = dist; idx_near = s; }
-                    if (id == prev_id) { prev_dist = dist; idx_prev = s; }
-                    ++n_det;
-                }
-            }
-            idx_upd = idx_near;  // nearest, or the previously used marker within the switch threshold (filter.cpp:660-664)
-            {
-                const double dd = prev_dist - md;
-                if ((dd < 0 ? -dd : dd) < k.switch_thres && prev_dist != 0) idx_upd = idx_prev;
-            }
-            bool do_init = false, do_reset = false;
-            uint32_t n_before = prm.n_imu_before;
-            if (fused) {
-                if (n_det == 0) {
-                    status |= FBUS_ST_NO_DETECTION;  // filter thread not woken (vision.cpp:136-140)
-                } else if (!inited) {
-                    do_init = true;
-                    n_before = 0;
-                    const uint32_t hi = prm.win_off[w + 1];
-                    for (uint32_t i = cursor; i < hi; ++i) n_before += (prm.imu_t[i] <= t_det) ? 1u : 0u;
-                } else {
-                    do_reset = do_prop = do_update = true;
-                    p_first = cursor;
-                    p_end = prm.win_off[w + 1];
-                    t_end = t_det;
-                }
-            } else {
-                do_init = (mode & M_INIT) != 0;
-                do_reset = (mode & M_RESET) != 0;
-                do_update = (mode & M_UPDATE) != 0;
-                if (mode & M_PROP) {
-                    do_prop = true;
-                    p_first = prm.prop_first;
-                    p_end = prm.prop_first + prm.prop_count;
-                    t_end = prm.prop_t_end;
-                }
-                if ((mode & M_UPDATE) && n_det == 0) status |= FBUS_ST_NO_DETECTION;
-            }
-            // ---- F6b InitializePose (filter.cpp:291-399) / F5 ResetSystemState (filter.cpp:405-477) -------
-            if ((do_init || do_reset) && n_det > 0) {
-                bool ok = !(md > k.max_dist);
-                if (do_init) ok = ok && (n_before > 0);
-                int mk = -1;
-                double dp[3], dq[4];
-                if (ok) {
-                    const size_t slot = (size_t)w * prm.m + idx_near;
-                    const bool use_pf = (pf_w == w) && idx_near == 0;
-                    const int did = use_pf ? pf_id : prm.det_id[slot * B + b];
-                    const double* pp = prm.det_pose + slot * 7 * B + b;
+        // ---- apply the planned F6b InitializePose / F5 ResetSystemState --------------------------------------
+        if (pl.apply_init) {
+            n.t = pl.t_det;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) dp[c] = use_pf ? pf_pose[c] : pp[(size_t)c * B];
+            for (int i = 0; i < 4; ++i) n.q[i] = pl.qv[i];
+            q2R(pl.qv, n.R);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) dq[c] = use_pf ? pf_pose[3 + c] : pp[(size_t)(3 + c) * B];
-                    mk = find_marker(k, prm.tab, did);
-                    ok = mk >= 0;
-                }
-                if (ok) {
-                    double qv[4], Rv[9], pv[3];
-                    const MarkerConst mkc = prm.tab->mk[mk];
-                    vision_pose(k, mkc, dp, dq, qv, Rv, pv);
-                    if (do_init) {
-                        n.t = t_det;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) n.q[i] = qv[i];
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) n.R[i] = Rv[i];
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) n.p[i] = pv[i];
-                        n.g[0] = 9.8; n.g[1] = 0.0; n.g[2] = 0.0;  // filter.cpp:387
-                        inited = 1;
-                        if (fused) cursor = prm.win_off[w + 1];  // consumed IMU samples erased (filter.cpp:390)
-                    }
-                    if (do_reset) {
-                        if (live) {
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) prm.nom[(size_t)(F_PV + i) * B + b] = pv[i];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_QV + i) * B + b] = qv[i];
-                        }
-                        if (t_det - n.t > k.reset_gap && inited) {
-                            n.t = t_det;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) n.q[i] = qv[i];
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) { n.p[i] = pv[i]; n.v[i] = 0.0; n.ba[i] = 0.0; n.bg[i] = 0.0; }
-                            status |= FBUS_ST_RESET_DONE;  // P, g and the carried R stay untouched
-                        }
-                    }
-                } else {
-                    if (do_init) status |= FBUS_ST_INIT_FAILED;
-                    if (do_reset) status |= FBUS_ST_RESET_SKIPPED;
-                }
-            } else if (do_init) {
-                status |= FBUS_ST_INIT_FAILED;
-            }
+            for (int i = 0; i < 3; ++i) n.p[i] = pl.pv[i];
+            n.g[0] = 9.8; n.g[1] = 0.0; n.g[2] = 0.0;  // filter.cpp:387
+            inited = 1;
+            if (fused) cursor = prm.win_off[w + 1];  // consumed IMU samples erased (filter.cpp:390)
         }
-
-#if FBUS_COOP_UPDATE
-        // ---- marker of this frame's update (filter.cpp:666-675), fetched now so that the loads overlap the propagation ----
-        int req = 0;
-        double yP[3], yQ[4];
-        if (do_update && n_det > 0) {
-            const size_t slot = (size_t)w * prm.m + idx_upd;
-            const int did = prm.det_id[slot * B + b];
-            const int mk = find_marker(k, prm.tab, did);
-            if (mk >= 0) {
-                prev_id = did;
-                req = mk + 1;
-                const double* pp = prm.det_pose + slot * 7 * B + b;
+        if (pl.apply_reset) {
+            n.t = pl.t_det;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) yP[c] = pp[(size_t)c * B];
+            for (int i = 0; i < 4; ++i) n.q[i] = pl.qv[i];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) yQ[c] = pp[(size_t)(3 + c) * B];
-            } else {
-                status |= FBUS_ST_UPDATE_SKIPPED;
-            }
+            for (int i = 0; i < 3; ++i) { n.p[i] = pl.pv[i]; n.v[i] = 0.0; n.ba[i] = 0.0; n.bg[i] = 0.0; }
         }
+        const bool do_prop = pl.do_prop;
+        const uint32_t p_first = pl.p_first, p_end = pl.p_end;
+        const double t_end = pl.t_end;
+        const int req = pl.req;
 
-#endif
         // ---- F3 BatchImuProcessing (filter.cpp:483-531): one sample ahead of the covariance warp -------------
         {
             const uint32_t vlo = __reduce_min_sync(0xffffffffu, do_prop ? p_first : 0xffffffffu);
@@ -384,7 +378,9 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
 #pragma unroll
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
+        int fs = 0;
         if (lo < hi) {
+            fs = (int)((hi - lo) & 1u);
             const double start = n.t;
             bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
             uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
@@ -427,113 +423,46 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                     }
                 }
                 sflag[slot][fl] = valid;
-                step_bar<NT>(fl >> 5);  // publish record (i); also: the covariance warp has finished sample i-1
+                step_bar<NT>(wq);  // publish record (i); also: the covariance warp has finished sample i-1
             }
             if (fused && do_prop) cursor = consumed;
         }
-        cta_bar<NT>();  // (b) the covariance warp is done with the ring
 
-#if FBUS_COOP_UPDATE
-        // ---- F4 ObservationUpdate (filter.cpp:622-739), cooperative: post measurement + pose, the covariance warp
-        //      computes the gain factors, then both warps apply one half-rank factor each --------------------------
+        // ---- F4 ObservationUpdate (filter.cpp:622-739): post the request (into the ring slot the covariance warp is
+        //      not reading), the covariance warp does the algebra ------------------------------------------------
         if (req) {
+            double* rq = X + (size_t)fs * 22 * BSF;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) X[(size_t)c * BSF] = yP[c];
+            for (int c = 0; c < 7; ++c) rq[(size_t)c * BSF] = pl.y[c];  // yP (3), yQ (4)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { X[(size_t)(3 + c) * BSF] = yQ[c]; X[(size_t)(7 + c) * BSF] = n.q[c]; }
+            for (int c = 0; c < 4; ++c) rq[(size_t)(7 + c) * BSF] = n.q[c];
 #pragma unroll
-            for (int c = 0; c < 9; ++c) X[(size_t)(11 + c) * BSF] = n.R[c];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) X[(size_t)(20 + c) * BSF] = n.p[c];
+            for (int c = 0; c < 9; ++c) rq[(size_t)(11 + c) * BSF] = n.R[c];
+            rq[(size_t)20 * BSF] = n.p[0]; rq[(size_t)21 * BSF] = n.p[1]; X[(size_t)RQ_EXTRA * BSF] = n.p[2];
         }
         sflag[2][fl] = req;
         {
             const int wany = __any_sync(0xffffffffu, req != 0);
             if ((fl & 31) == 0) sh.any_upd[wq] = wany;
         }
-        cta_bar<NT>();  // (c)
-        int any = sh.any_upd[0];
-#pragma unroll
-        for (int q = 1; q < NW; ++q) any |= sh.any_upd[q];
-        if (any) {
-            const Cov<BSF> P{smem + fl};
-            double Z[54];
-            double y3 = 0.0, y4 = 0.0, y5 = 0.0;
-            cta_bar<NT>();  // (c2)
-            if (req) {
-                double Cm[21];
-#pragma unroll
-                for (int c = 0; c < 21; ++c) Cm[c] = X[(size_t)c * BSF];
-                y3 = X[(size_t)21 * BSF]; y4 = X[(size_t)22 * BSF]; y5 = X[(size_t)23 * BSF];
-                update_Zb<BSF>(P, Cm, Z);
-            }
-            cta_bar<NT>();  // (d1)
-            if (req) update_sweep<BSF, 5, 18>(P, Z);
-            cta_bar<NT>();  // (d2)
-            if (req) update_sweep<BSF, 0, 5>(P, Z);
-            cta_bar<NT>();  // (e)
-            if (req) {
-                double dx[18];
-#pragma unroll
-                for (int c = 0; c < 18; ++c) dx[c] = X[(size_t)(27 + c) * BSF];
-                update_dx<true>(Z, y3, y4, y5, dx);
-                inject_error_state(n, dx);
-            }
-        }
-#else
-        // ---- F4 ObservationUpdate (filter.cpp:622-739): post the request, the covariance warp does the algebra ----
-        int req_old = 0;
-        if (do_update && n_det > 0) {
-            const size_t slot = (size_t)w * prm.m + idx_upd;
-            const bool use_pf = (pf_w == w) && idx_upd == 0;
-            const int did = use_pf ? pf_id : prm.det_id[slot * B + b];
-            const int mk = find_marker(k, prm.tab, did);
-            if (mk >= 0) {
-                prev_id = did;
-                req_old = mk + 1;
-                const double* pp = prm.det_pose + slot * 7 * B + b;
-#pragma unroll
-                for (int c = 0; c < 7; ++c) X[(size_t)c * BSF] = use_pf ? pf_pose[c] : pp[(size_t)c * B];  // yP (3), yQ (4)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) X[(size_t)(7 + c) * BSF] = n.q[c];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) X[(size_t)(11 + c) * BSF] = n.R[c];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) X[(size_t)(20 + c) * BSF] = n.p[c];
-            } else {
-                status |= FBUS_ST_UPDATE_SKIPPED;
-            }
-        }
-        sflag[2][fl] = req_old;
-        {
-            const int wany = __any_sync(0xffffffffu, req_old != 0);
-            if ((fl & 31) == 0) sh.any_upd[wq] = wany;
-        }
-        // prefetch the next frame's inputs; the loads complete while this warp waits for the update
+        step_bar<NT>(wq);  // (r)
+        const int any = pair_any<NT>(sh, wq);
+        // ---- while the update runs: the next window's first IMU sample and the next frame's plan ---------------
+        FramePlan nx;
+        nx.do_prop = nx.apply_init = nx.apply_reset = false;
+        nx.req = 0;
         if (w + 1 < prm.w1) {
-            if (uses_det) {
-                const size_t slot = (size_t)(w + 1) * prm.m;
-                pf_w = w + 1;
-                pf_tdet = prm.det_t[w + 1];
-                pf_id = prm.det_id[slot * B + b];
-                const double* pp = prm.det_pose + slot * 7 * B + b;
-#pragma unroll
-                for (int c = 0; c < 7; ++c) pf_pose[c] = pp[(size_t)c * B];
-            }
             if (fused && cursor < prm.win_off[prm.w1]) {
                 pf_i = cursor;
                 pf_st = prm.imu_t[cursor];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) pf_sd[c] = prm.imu[((size_t)cursor * 6 + c) * B + b];
             }
+            plan_frame<BSF>(prm, k, w + 1, b, live, cursor, n.t, inited, prev_id, status, nx);
         }
-        cta_bar<NT>();  // (c)
-        int any = sh.any_upd[0];
-#pragma unroll
-        for (int q = 1; q < NW; ++q) any |= sh.any_upd[q];
         if (any) {
-            cta_bar<NT>();  // (d) results posted
-            if (req_old) {
+            step_bar<NT>(wq);  // (d) results posted
+            if (req) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     n.p[c] = X[(size_t)(23 + c) * BSF];
@@ -545,9 +474,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                 for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(26 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
             }
-            cta_bar<NT>();  // (e)
         }
-#endif
         // ---- trace row: the data/fusion.txt record (filter.cpp:241-246) -------------------------
         if (prm.trace && live) {
             double* row = prm.trace + (size_t)(w - prm.w0) * 17 * B + b;
@@ -563,6 +490,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                 row[(size_t)(14 + c) * B] = n.bg[c];
             }
         }
+        pl = nx;
     }
     if (!live) return;
     bool fin = isfinite(n.t);
