@@ -22,6 +22,11 @@
 #ifndef FBUS_TL_REGS
 #define FBUS_TL_REGS 1
 #endif
+// 1: both warps of a filter group share the update: the covariance warp computes the gain factors and applies the first
+//    half-rank factor Za, the nominal warp applies the second (Zb) and injects the error state; 0: covariance warp alone
+#ifndef FBUS_COOP_UPDATE
+#define FBUS_COOP_UPDATE 0  // measured: 6.4e9 vs 7.5e9 filter-steps/s -- the sweeps are shared-memory-bandwidth bound, two warps do not help
+#endif
 // 1: the per-sample ring barrier is private to a warp pair (64 threads); the CTA re-aligns once per frame
 #ifndef FBUS_PAIR_BARRIER
 #define FBUS_PAIR_BARRIER 1
@@ -33,7 +38,7 @@
 
 namespace fbus {
 
-constexpr int XCH = 46;  // doubles of exchange area per filter: ring 2 x 22; reused by the update: Lc 21 + y 6, dx 18
+constexpr int XCH = 54;  // doubles of exchange area per filter: ring 2 x 22 (+ request, results); the update parks 54 doubles of Z here
 
 // CTA-wide named barrier used by both roles (the two roles run different code, so the barrier is issued from
 // different program counters; whole warps take each path, and arrivals are counted per barrier id)
@@ -137,6 +142,51 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
         step_bar<NT>(wq);  // (r) update request posted (normally long before this warp gets here)
         if (pair_any<NT>(sh, wq)) {
             const int req = sflag[2][fl];
+#if FBUS_COOP_UPDATE
+            // Cooperative update.  This warp computes the gain factors from the posted measurement and pose, publishes
+            // the part of Lc the nominal warp needs (rows 3..5) and y[3..5], then both warps take one half-rank factor
+            // each from the OLD covariance (Za here, Zb there) and apply it to disjoint row sets, swapping once.
+            double Z[54];
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+            double Cm[21];
+            if (req) {
+                const double* rq = X + (size_t)fs * 22 * BSF;
+                Nominal t;
+                double yP[3], yQ[4], y[6];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) yP[c] = rq[(size_t)c * BSF];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { yQ[c] = rq[(size_t)(3 + c) * BSF]; t.q[c] = rq[(size_t)(7 + c) * BSF]; }
+#pragma unroll
+                for (int c = 0; c < 9; ++c) t.R[c] = rq[(size_t)(11 + c) * BSF];
+                t.p[0] = rq[(size_t)20 * BSF]; t.p[1] = rq[(size_t)21 * BSF]; t.p[2] = X[(size_t)RQ_EXTRA * BSF];
+                const MarkerConst mkc = prm.tab->mk[req - 1];  // 3 KB table, L2-resident
+                // X = L^-1 Hs (42 doubles) is parked in the exchange area: the request is already in registers
+                update_prologue<BSF, BSF, JOSEPH>(P, t, k, mkc, yP, yQ, Cm, y, X);
+                X[(size_t)0 * BSF] = Cm[9];  X[(size_t)1 * BSF] = Cm[13]; X[(size_t)2 * BSF] = Cm[14];   // C(3,3) C(4,3) C(4,4)
+                X[(size_t)3 * BSF] = Cm[18]; X[(size_t)4 * BSF] = Cm[19]; X[(size_t)5 * BSF] = Cm[20];   // C(5,3) C(5,4) C(5,5)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) X[(size_t)(6 + c) * BSF] = y[3 + c];
+                y0 = y[0]; y1 = y[1]; y2 = y[2];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 21; ++c) Cm[c] = 0.0;
+            }
+            // from here on no divergent regions: lanes without a request run the same code with their stores off
+            step_bar<NT>(wq);  // (u1) gain factors published
+            update_Za<BSF>(P, Cm, Z);
+            step_bar<NT>(wq);  // (u2) both factors taken from the old covariance
+            update_sweep<BSF, 0, 5>(P, Z, req != 0);
+            step_bar<NT>(wq);  // (u3) swap row sets
+            update_sweep<BSF, 5, 18>(P, Z, req != 0);
+            {
+                double dx[18];
+                update_dx<false>(Z, y0, y1, y2, dx);
+#pragma unroll
+                for (int c = 0; c < 18; ++c) X[(size_t)(22 + c) * BSF] = dx[c];
+            }
+            step_bar<NT>(wq);  // (d) covariance updated, first half of dx posted
+#else
             if (req) {
                 const double* rq = X + (size_t)fs * 22 * BSF;
                 Nominal t;
@@ -152,7 +202,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                 for (int c = 0; c < 3; ++c) { t.v[c] = 0.0; t.ba[c] = 0.0; t.bg[c] = 0.0; t.g[c] = 0.0; }
                 t.t = 0.0;
                 const MarkerConst mkc = prm.tab->mk[req - 1];
-                measurement_update<BSF, JOSEPH ? 1 : 0>(P, t, k, mkc, yP, yQ);
+                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X);
                 // hand back: corrected p, q and the increments of v, b_a, b_g, g
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -166,6 +216,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                 for (int c = 0; c < 4; ++c) X[(size_t)(26 + c) * BSF] = t.q[c];
             }
             step_bar<NT>(wq);  // (d) results posted
+#endif
         }
     }
     if (live)
@@ -461,6 +512,37 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             plan_frame<BSF>(prm, k, w + 1, b, live, cursor, n.t, inited, prev_id, status, nx);
         }
         if (any) {
+#if FBUS_COOP_UPDATE
+            const Cov<BSF> P{smem + fl};
+            double Z[54];
+            double y3 = 0.0, y4 = 0.0, y5 = 0.0;
+            step_bar<NT>(wq);  // (u1)
+            {   // no divergent regions below (see cov_role): lanes without a request keep their stores / state changes off
+                const double c33 = X[(size_t)0 * BSF], c43 = X[(size_t)1 * BSF], c44 = X[(size_t)2 * BSF];
+                const double c53 = X[(size_t)3 * BSF], c54 = X[(size_t)4 * BSF], c55 = X[(size_t)5 * BSF];
+                y3 = X[(size_t)6 * BSF]; y4 = X[(size_t)7 * BSF]; y5 = X[(size_t)8 * BSF];
+                update_Zb6<BSF>(P, c33, c43, c44, c53, c54, c55, Z);
+            }
+            step_bar<NT>(wq);  // (u2)
+            update_sweep<BSF, 5, 18>(P, Z, req != 0);
+            step_bar<NT>(wq);  // (u3)
+            update_sweep<BSF, 0, 5>(P, Z, req != 0);
+            step_bar<NT>(wq);  // (d)
+            {
+                double dx[18];
+#pragma unroll
+                for (int c = 0; c < 18; ++c) dx[c] = X[(size_t)(22 + c) * BSF];
+                update_dx<true>(Z, y3, y4, y5, dx);
+                Nominal m = n;
+                inject_error_state(m, dx);  // rotmatI2G deliberately NOT refreshed (A.3-2)
+                if (req) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { n.p[c] = m.p[c]; n.v[c] = m.v[c]; n.ba[c] = m.ba[c]; n.bg[c] = m.bg[c]; n.g[c] = m.g[c]; }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) n.q[c] = m.q[c];
+                }
+            }
+#else
             step_bar<NT>(wq);  // (d) results posted
             if (req) {
 #pragma unroll
@@ -474,6 +556,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                 for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(26 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
             }
+#endif
         }
         // ---- trace row: the data/fusion.txt record (filter.cpp:241-246) -------------------------
         if (prm.trace && live) {

@@ -1005,9 +1005,27 @@ FBUS_HD void update_Zb(const Cov<S> P, const double* Cm, double* Z) {
     }
 }
 #undef FBUS_C
+// same from the six entries of Lc's rows 3..5 alone (what the nominal warp of the split kernel receives)
+template <int S>
+FBUS_HD void update_Zb6(const Cov<S> P, double c33, double c43, double c44, double c53, double c54, double c55, double* Z) {
+    FBUS_UNROLL
+    for (int c = 0; c < 18; ++c) {
+        const double g3 = P.ld(6, c), g4 = P.ld(7, c), g5 = P.ld(8, c);
+        double t3 = c33 * g3;
+        t3 += c43 * g4;
+        t3 += c53 * g5;
+        double t4 = c44 * g4;
+        t4 += c54 * g5;
+        Z[c] = t3;
+        Z[18 + c] = t4;
+        Z[36 + c] = c55 * g5;
+    }
+}
 // P[i][j] -= sum_k Z[k][i] Z[k][j] for rows R0 <= i < R1 (j >= i)
+// `on` = false turns the stores off (predicated stores: the split kernel keeps the code between two barriers free of
+// divergent regions, because ptxas parks values that live across such regions in local memory)
 template <int S, int R0, int R1>
-FBUS_HD void update_sweep(const Cov<S> P, const double* Z) {
+FBUS_HD void update_sweep(const Cov<S> P, const double* Z, bool on = true) {
     FBUS_UNROLL
     for (int i = R0; i < R1; ++i)
         FBUS_UNROLL
@@ -1016,7 +1034,7 @@ FBUS_HD void update_sweep(const Cov<S> P, const double* Z) {
             v -= Z[i] * Z[j];
             v -= Z[18 + i] * Z[18 + j];
             v -= Z[36 + i] * Z[36 + j];
-            P.st(i, j, v);
+            if (on) P.st(i, j, v);
         }
 }
 // dx[c] (+)= y0 Z[0][c] + y1 Z[1][c] + y2 Z[2][c]
@@ -1072,16 +1090,143 @@ FBUS_HD void measurement_update_coop(const Cov<S> P, Nominal& n, const DevConsts
     inject_error_state(n, dx);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// One-pass form of the covariance update (default, FBUS_UPDATE_ONEPASS=1): every entry of P is read once and written
+// once.  Z = Lc^T G (6 x 18) is never held whole: the columns of the p/v/theta block (0..8) stay in registers (54
+// doubles), the columns of the bias/gravity block (9..17) are produced one at a time from the OLD rows of G, used for the
+// 9 cross entries of that column, and parked in `stash` (54 doubles, stride XS: the exchange area of the split kernel)
+// for the bottom-right block.  Shared-memory accesses per update: 495 instead of the two-sweep form's 846, and no
+// rebuild of the old theta rows.  Per entry the six FMAs run in the same order as in the two-sweep form.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef FBUS_UPDATE_ONEPASS
+#define FBUS_UPDATE_ONEPASS 1
+#endif
+template <int S, int XS>
+FBUS_HD void update_onepass(const Cov<S> P, Nominal& n, const double* Cm, const double* y, double* stash) {
+#define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
+#define FBUS_GROW(m) (((m) < 3) ? (m) : (3 + (m)))  // rows of G: 0,1,2,6,7,8
+    double dth[3] = {0.0, 0.0, 0.0};
+    double Z1[54];  // Z[k][c], c = 0..8, at Z1[k * 9 + c]
+    // ---- phase 1: Z columns 0..8 from the top-left block ----------------------------------------------
+    FBUS_UNROLL
+    for (int c = 0; c < 9; ++c) {
+        double g[6];
+        FBUS_UNROLL
+        for (int m = 0; m < 6; ++m) g[m] = P.ld(FBUS_GROW(m), c);
+        FBUS_UNROLL
+        for (int kz = 0; kz < 6; ++kz) {
+            double z = FBUS_C(kz, kz) * g[kz];
+            FBUS_UNROLL
+            for (int m = kz + 1; m < 6; ++m) z += FBUS_C(m, kz) * g[m];
+            Z1[kz * 9 + c] = z;
+        }
+    }
+    // error-state injection (filter.cpp:726-733), columns 0..8: dx[c] = sum_k y[k] Z[k][c]
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        FBUS_UNROLL
+        for (int kz = 0; kz < 6; ++kz) {
+            n.p[i] += y[kz] * Z1[kz * 9 + i];
+            n.v[i] += y[kz] * Z1[kz * 9 + 3 + i];
+            dth[i] += y[kz] * Z1[kz * 9 + 6 + i];
+        }
+    }
+    FBUS_FENCE;
+    // top-left block
+    FBUS_UNROLL
+    for (int i = 0; i < 9; ++i)
+        FBUS_UNROLL
+        for (int j = i; j < 9; ++j) {
+            double v = P.ld(i, j);
+            FBUS_UNROLL
+            for (int kz = 0; kz < 6; ++kz) v -= Z1[kz * 9 + i] * Z1[kz * 9 + j];
+            P.st(i, j, v);
+        }
+    FBUS_FENCE;
+    // ---- phase 2: columns 9..17: Z column from the OLD G entries of that column, cross entries, stash ------
+    FBUS_UNROLL
+    for (int c = 9; c < 18; ++c) {
+        double col[9];
+        FBUS_UNROLL
+        for (int i = 0; i < 9; ++i) col[i] = P.ld(i, c);
+        double z[6];
+        FBUS_UNROLL
+        for (int kz = 0; kz < 6; ++kz) {
+            double t = FBUS_C(kz, kz) * col[FBUS_GROW(kz)];
+            FBUS_UNROLL
+            for (int m = kz + 1; m < 6; ++m) t += FBUS_C(m, kz) * col[FBUS_GROW(m)];
+            z[kz] = t;
+            stash[(size_t)((c - 9) * 6 + kz) * XS] = t;
+        }
+        {
+            double* dst = (c < 12) ? &n.ba[c - 9] : (c < 15) ? &n.bg[c - 12] : &n.g[c - 15];
+            double d = *dst;
+            FBUS_UNROLL
+            for (int kz = 0; kz < 6; ++kz) d += y[kz] * z[kz];
+            *dst = d;
+        }
+        FBUS_UNROLL
+        for (int i = 0; i < 9; ++i) {
+            double v = col[i];
+            FBUS_UNROLL
+            for (int kz = 0; kz < 6; ++kz) v -= Z1[kz * 9 + i] * z[kz];
+            P.st(i, c, v);
+        }
+    }
+    FBUS_FENCE;
+    // ---- phase 3: bottom-right block from the stashed columns -------------------------------------------
+    {
+        double Z2[54];  // Z[k][c], c = 9..17, at Z2[(c - 9) * 6 + k]
+        FBUS_UNROLL
+        for (int e = 0; e < 54; ++e) Z2[e] = stash[(size_t)e * XS];
+        FBUS_UNROLL
+        for (int i = 9; i < 18; ++i)
+            FBUS_UNROLL
+            for (int j = i; j < 18; ++j) {
+                double v = P.ld(i, j);
+                FBUS_UNROLL
+                for (int kz = 0; kz < 6; ++kz) v -= Z2[(i - 9) * 6 + kz] * Z2[(j - 9) * 6 + kz];
+                P.st(i, j, v);
+            }
+    }
+#undef FBUS_GROW
+#undef FBUS_C
+    {   // VectorToQuaterniond (matrix_math.hpp:90-99): v/|v| * sin(|v|/2); NaN at exactly zero, as the reference
+        const double v2 = dth[0] * dth[0] + dth[1] * dth[1] + dth[2] * dth[2];
+        const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
+        const double vn = v2 * iv;
+        double sh, ch;
+        sincos(vn * 0.5, &sh, &ch);
+        const double sc = iv * sh;
+        const double dq[4] = {ch, dth[0] * sc, dth[1] * sc, dth[2] * sc};
+        double qn[4];
+        qmul(n.q, dq, qn);
+        qnormalize(qn);
+        FBUS_UNROLL
+        for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
+    }
+}
+
 // JMODE: 0 = reference form (I-KH)P, 1 = Joseph form, -1 = decided at run time from k.flags (host harness, un-split kernel)
-template <int S, int JMODE = -1>
+// stash: 54 doubles of scratch with stride XS (nullptr: a private array)
+template <int S, int JMODE = -1, int XS = 1>
 FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
-                                const double* yQ) {
+                                const double* yQ, double* stash = nullptr) {
     double Cm[21], y[6];
     {
         double xloc[42];  // single-thread form: X = L^-1 Hs stays private
         if (JMODE == 1 || (JMODE < 0 && (k.flags & 1))) update_prologue<S, 1, true>(P, n, k, mk, yP, yQ, Cm, y, xloc);
         else update_prologue<S, 1, false>(P, n, k, mk, yP, yQ, Cm, y, xloc);
     }
+#if FBUS_UPDATE_ONEPASS
+    if (stash != nullptr) {
+        update_onepass<S, XS>(P, n, Cm, y, stash);
+    } else {
+        double loc[54];
+        update_onepass<S, 1>(P, n, Cm, y, loc);
+    }
+    return;
+#endif
 #define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
     double dth[3];  // attitude part of dx (needed whole before the quaternion injection)
     double Z[54];   // 3 x 18
