@@ -22,6 +22,11 @@
 #ifndef FBUS_TL_REGS
 #define FBUS_TL_REGS 1
 #endif
+// 1: the top-left block stays in the covariance warp's registers for the whole launch (propagation AND update);
+// 0: only while a window is propagated (reloaded from / stored to shared memory around every update)
+#ifndef FBUS_TL_PERSIST
+#define FBUS_TL_PERSIST 0  // measured: 7.47e9 vs 7.96e9 -- block (90 regs) + Z columns (108) + Lc (42) do not fit, the update spills
+#endif
 // 1: both warps of a filter group share the update: the covariance warp computes the gain factors and applies the first
 //    half-rank factor Za, the nominal warp applies the second (Zb) and injects the error state; 0: covariance warp alone
 #ifndef FBUS_COOP_UPDATE
@@ -97,6 +102,14 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
     double* const X = smem + (size_t)NPK * BSF + fl;
     const int wq = fl >> 5;
     for (int e = 0; e < NPK; ++e) smem[e * BSF + fl] = prm.P[(size_t)e * B + b];
+#if FBUS_TL_REGS && FBUS_TL_PERSIST
+#if FBUS_COOP_UPDATE
+#error "FBUS_TL_PERSIST needs FBUS_COOP_UPDATE=0 (the nominal warp cannot see the register-resident block)"
+#endif
+    double TL[NTL];  // top-left 9x9 of P lives in registers for the whole launch
+    tl_load<BSF>(P, TL);
+    const CovX<BSF, true> PT{smem + fl, TL};
+#endif
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
         cta_bar<NT>();  // (a) the nominal warps have posted their IMU ranges
         uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
@@ -105,7 +118,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
         int fs = 0;  // ring slot that carries the update request
         if (lo < hi) {
             fs = (int)((hi - lo) & 1u);
-#if FBUS_TL_REGS
+#if FBUS_TL_REGS && !FBUS_TL_PERSIST
             double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
             tl_load<BSF>(P, TL);
 #endif
@@ -132,7 +145,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #endif
                 }
             }
-#if FBUS_TL_REGS
+#if FBUS_TL_REGS && !FBUS_TL_PERSIST
             tl_store<BSF>(P, TL);
 #endif
 #if FBUS_BR_REGS_SPLIT
@@ -202,7 +215,11 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                 for (int c = 0; c < 3; ++c) { t.v[c] = 0.0; t.ba[c] = 0.0; t.bg[c] = 0.0; t.g[c] = 0.0; }
                 t.t = 0.0;
                 const MarkerConst mkc = prm.tab->mk[req - 1];
+#if FBUS_TL_REGS && FBUS_TL_PERSIST
+                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(PT, t, k, mkc, yP, yQ, X);
+#else
                 measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X);
+#endif
                 // hand back: corrected p, q and the increments of v, b_a, b_g, g
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -219,6 +236,9 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #endif
         }
     }
+#if FBUS_TL_REGS && FBUS_TL_PERSIST
+    tl_store<BSF>(P, TL);
+#endif
     if (live)
         for (int e = 0; e < NPK; ++e) prm.P[(size_t)e * B + b] = smem[e * BSF + fl];
 }

@@ -181,11 +181,23 @@ FBUS_HD double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + 
 // covariance accessor: packed symmetric storage with element stride S (S = block size in shared
 // memory on the device, 1 on the host harness)
 // ------------------------------------------------------------------------------------------------
-template <int S>
-struct Cov {
+// TLR = true: the top-left 9x9 block (rows/cols 0..8: p, v, theta) lives in the caller's registers TL[45] (packed by
+// tlidx) instead of in the strided array; every index is a compile-time constant after unrolling, so the choice is static.
+FBUS_HD constexpr int tlidx(int i, int j) {
+    return (i <= j) ? (i * 9 - (i * (i - 1)) / 2 + (j - i)) : (j * 9 - (j * (j - 1)) / 2 + (i - j));
+}
+template <int S, bool TLR = false>
+struct CovX {
     double* s;
-    FBUS_HD double ld(int i, int j) const { return s[pidx(i, j) * S]; }
-    FBUS_HD void st(int i, int j, double v) const { s[pidx(i, j) * S] = v; }
+    double* TL = nullptr;
+    FBUS_HD double ld(int i, int j) const {
+        if (TLR && i < 9 && j < 9) return TL[tlidx(i, j)];
+        return s[pidx(i, j) * S];
+    }
+    FBUS_HD void st(int i, int j, double v) const {
+        if (TLR && i < 9 && j < 9) TL[tlidx(i, j)] = v;
+        else s[pidx(i, j) * S] = v;
+    }
     // X[r*3+c] = P[3bi+r][3bj+c]  (off-diagonal block, any order of bi,bj)
     FBUS_HD void ldblk(int bi, int bj, double* X) const {
         FBUS_UNROLL
@@ -221,6 +233,8 @@ struct Cov {
             for (int c = r; c < 3; ++c) st(3 * b + r, 3 * b + c, X[r * 3 + c]);
     }
 };
+template <int S>
+using Cov = CovX<S, false>;
 
 // ------------------------------------------------------------------------------------------------
 // F1: covariance propagation  P <- F P F^T + diag(Qbar)   (FILTER::UpdateCovariance, filter.cpp:588-616)
@@ -237,11 +251,7 @@ FBUS_HD constexpr int bridx(int i, int j) {  // any order; i,j in 9..17
     return (i <= j) ? ((i - 9) * 9 - ((i - 9) * (i - 10)) / 2 + (j - i)) : ((j - 9) * 9 - ((j - 9) * (j - 10)) / 2 + (i - j));
 }
 constexpr int NBR = 45;
-// packed index inside the top-left 9x9 (rows/cols 0..8)
-FBUS_HD constexpr int tlidx(int i, int j) {
-    return (i <= j) ? (i * 9 - (i * (i - 1)) / 2 + (j - i)) : (j * 9 - (j * (j - 1)) / 2 + (i - j));
-}
-constexpr int NTL = 45;
+constexpr int NTL = 45;  // packed size of the top-left 9x9 (tlidx)
 template <int S>
 FBUS_HD void tl_load(const Cov<S> P, double* TL) {
     FBUS_UNROLL
@@ -737,8 +747,8 @@ struct CholStep<N, N> {
 // Prologue of the update: everything up to the gain factors.  Reads only the 21 entries of P6 = P[{p,theta},{p,theta}].
 // Outputs Cm = lower-packed Cholesky factor Lc of C = Hs^T S^-1 Hs and y = Lc^-1 u (u = Hs^T S^-1 r), so that
 //   (I-KH)P = P - Z^T Z with Z = Lc^T G, and dx = K r = Z^T y.
-template <int S, int XS, bool JOSEPH = false>
-FBUS_HD void update_prologue(const Cov<S> P, const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+template <int S, int XS, bool JOSEPH = false, bool TLR = false>
+FBUS_HD void update_prologue(const CovX<S, TLR> P, const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
                              const double* yQ, double* Cm, double* y, double* scr) {
     // scr: 42 doubles of scratch with element stride XS (shared memory in the warp-specialised kernel) for X = L^-1 Hs
     // ---- predicted measurement and Hs ------------------------------------------------------
@@ -1101,8 +1111,11 @@ FBUS_HD void measurement_update_coop(const Cov<S> P, Nominal& n, const DevConsts
 #ifndef FBUS_UPDATE_ONEPASS
 #define FBUS_UPDATE_ONEPASS 1
 #endif
-template <int S, int XS>
-FBUS_HD void update_onepass(const Cov<S> P, Nominal& n, const double* Cm, const double* y, double* stash) {
+#ifndef FBUS_PROLOGUE_PARK
+#define FBUS_PROLOGUE_PARK 1
+#endif
+template <int S, int XS, bool TLR = false>
+FBUS_HD void update_onepass(const CovX<S, TLR> P, Nominal& n, const double* Cm, const double* y, double* stash) {
 #define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
 #define FBUS_GROW(m) (((m) < 3) ? (m) : (3 + (m)))  // rows of G: 0,1,2,6,7,8
     double dth[3] = {0.0, 0.0, 0.0};
@@ -1209,11 +1222,15 @@ FBUS_HD void update_onepass(const Cov<S> P, Nominal& n, const double* Cm, const 
 
 // JMODE: 0 = reference form (I-KH)P, 1 = Joseph form, -1 = decided at run time from k.flags (host harness, un-split kernel)
 // stash: 54 doubles of scratch with stride XS (nullptr: a private array)
-template <int S, int JMODE = -1, int XS = 1>
-FBUS_HD void measurement_update(const Cov<S> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+template <int S, int JMODE = -1, int XS = 1, bool TLR = false>
+FBUS_HD void measurement_update(const CovX<S, TLR> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
                                 const double* yQ, double* stash = nullptr) {
     double Cm[21], y[6];
-    {
+    if (TLR && XS > 1 && FBUS_PROLOGUE_PARK) {
+        // the register-resident top-left block leaves no room for X = L^-1 Hs (42 doubles): park it in the stash area
+        if (JMODE == 1 || (JMODE < 0 && (k.flags & 1))) update_prologue<S, XS, true>(P, n, k, mk, yP, yQ, Cm, y, stash);
+        else update_prologue<S, XS, false>(P, n, k, mk, yP, yQ, Cm, y, stash);
+    } else {
         double xloc[42];  // single-thread form: X = L^-1 Hs stays private
         if (JMODE == 1 || (JMODE < 0 && (k.flags & 1))) update_prologue<S, 1, true>(P, n, k, mk, yP, yQ, Cm, y, xloc);
         else update_prologue<S, 1, false>(P, n, k, mk, yP, yQ, Cm, y, xloc);
