@@ -30,7 +30,9 @@ constexpr int WIN_BS = FBUS_WIN_BS;  // filters per CTA of the window kernel (17
 #define FBUS_SPLIT 1
 #endif
 #if FBUS_SPLIT
-constexpr size_t WIN_SMEM = (size_t)(NPK + XCH) * WIN_BS * sizeof(double);
+// the 128-filter CTAs keep P in tensor memory (FBUS_TMEM): shared memory then only holds the exchange area
+constexpr bool WIN_TMEM = (FBUS_TMEM != 0) && WIN_BS == 128 && (FBUS_COOP_UPDATE == 0);
+constexpr size_t WIN_SMEM = (size_t)((WIN_TMEM ? 0 : NPK) + XCH) * WIN_BS * sizeof(double);
 #else
 constexpr size_t WIN_SMEM = (size_t)NPK * WIN_BS * sizeof(double);
 #endif

@@ -17,6 +17,7 @@
 #pragma once
 
 #include "fbus_kernels.cuh"
+#include "fbus_tmem.cuh"
 
 // 1 (default): the covariance warp keeps the top-left 9x9 block of P in registers while it propagates a window
 #ifndef FBUS_TL_REGS
@@ -26,6 +27,11 @@
 // 0: only while a window is propagated (reloaded from / stored to shared memory around every update)
 #ifndef FBUS_TL_PERSIST
 #define FBUS_TL_PERSIST 0  // measured: 7.47e9 vs 7.96e9 -- block (90 regs) + Z columns (108) + Lc (42) do not fit, the update spills
+#endif
+// 1 (default): the 128-filter CTAs keep the covariance in TENSOR MEMORY (one TMEM lane per filter, fbus_tmem.cuh) instead
+// of shared memory; the 32-filter CTAs of small batches (several per SM) always use shared memory
+#ifndef FBUS_TMEM
+#define FBUS_TMEM 1
 #endif
 // 1: both warps of a filter group share the update: the covariance warp computes the gain factors and applies the first
 //    half-rank factor Za, the nominal warp applies the second (Zb) and injects the error state; 0: covariance warp alone
@@ -78,6 +84,45 @@ struct SplitShared {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int RQ_EXTRA = 44;  // the request needs 23 doubles: 22 in the free ring slot + this one
 
+// top-left 9x9 <-> registers, block-wise (six 3x3 blocks) for the tensor-memory accessor
+template <bool TM, class CV>
+__device__ __forceinline__ void tl_load_any(const CV P, double* TL) {
+    if constexpr (TM) {
+        FBUS_UNROLL
+        for (int bj = 0; bj < 3; ++bj)
+            FBUS_UNROLL
+            for (int bi = 0; bi <= bj; ++bi) {
+                double T[9];
+                P.ldraw(bi, bj, T);
+                tm_wait_ld();
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r)
+                    FBUS_UNROLL
+                    for (int c = (bi == bj ? r : 0); c < 3; ++c) TL[tlidx(3 * bi + r, 3 * bj + c)] = T[r * 3 + c];
+            }
+    } else {
+        tl_load<0>(P, TL);
+    }
+}
+template <bool TM, class CV>
+__device__ __forceinline__ void tl_store_any(const CV P, const double* TL) {
+    if constexpr (TM) {
+        FBUS_UNROLL
+        for (int bj = 0; bj < 3; ++bj)
+            FBUS_UNROLL
+            for (int bi = 0; bi <= bj; ++bi) {
+                double T[9];
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r)
+                    FBUS_UNROLL
+                    for (int c = 0; c < 3; ++c) T[r * 3 + c] = TL[tlidx(3 * bi + r, 3 * bj + c)];
+                P.straw(bi, bj, T);
+            }
+    } else {
+        tl_store<0>(P, TL);
+    }
+}
+
 template <int NT>
 __device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) {
 #if FBUS_PAIR_BARRIER
@@ -93,21 +138,40 @@ __device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) {
 // ------------------------------------------------------------------------------------------------------------------
 // COVARIANCE role: owns P (shared memory; top-left 9x9 in registers while propagating)
 // ------------------------------------------------------------------------------------------------------------------
-template <int BSF, bool JOSEPH>
+template <int BSF, bool JOSEPH, bool TM>
 __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh, int32_t (*sflag)[BSF],
-                                         int fl, size_t b, bool live) {
+                                         int fl, size_t b, bool live, uint32_t tm_base) {
     constexpr int NT = 2 * BSF, NW = BSF / 32;
+    constexpr int NPS = TM ? 0 : NPK;  // doubles of P per filter in shared memory
     const size_t B = prm.B;
-    const Cov<BSF> P{smem + fl};
-    double* const X = smem + (size_t)NPK * BSF + fl;
+    using CV = typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type;
+    CV P;
+    if constexpr (TM) P.base = tm_base + ((uint32_t)((threadIdx.x >> 5) & 3) << 21);  // lane 32*(warp%4) in bits 31..16
+    else P.s = smem + fl;
+    double* const X = smem + (size_t)NPS * BSF + fl;
     const int wq = fl >> 5;
-    for (int e = 0; e < NPK; ++e) smem[e * BSF + fl] = prm.P[(size_t)e * B + b];
+    if constexpr (TM) {
+        FBUS_UNROLL
+        for (int bj = 0; bj < 6; ++bj)
+            FBUS_UNROLL
+            for (int bi = 0; bi <= bj; ++bi) {
+                double T[9];
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r)
+                    FBUS_UNROLL
+                    for (int c = 0; c < 3; ++c) T[r * 3 + c] = prm.P[(size_t)pidx(3 * bi + r, 3 * bj + c) * B + b];
+                P.straw(bi, bj, T);
+            }
+        P.fence_st();
+    } else {
+        for (int e = 0; e < NPK; ++e) smem[e * BSF + fl] = prm.P[(size_t)e * B + b];
+    }
 #if FBUS_TL_REGS && FBUS_TL_PERSIST
 #if FBUS_COOP_UPDATE
 #error "FBUS_TL_PERSIST needs FBUS_COOP_UPDATE=0 (the nominal warp cannot see the register-resident block)"
 #endif
     double TL[NTL];  // top-left 9x9 of P lives in registers for the whole launch
-    tl_load<BSF>(P, TL);
+    tl_load_any<TM>(P, TL);
     const CovX<BSF, true> PT{smem + fl, TL};
 #endif
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
@@ -120,7 +184,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             fs = (int)((hi - lo) & 1u);
 #if FBUS_TL_REGS && !FBUS_TL_PERSIST
             double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
-            tl_load<BSF>(P, TL);
+            tl_load_any<TM>(P, TL);
 #endif
 #if FBUS_BR_REGS_SPLIT
             double BR[NBR];
@@ -129,24 +193,35 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             for (uint32_t i = lo; i < hi; ++i) {
                 step_bar<NT>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
                 const int slot = (int)((i - lo) & 1u);
-                if (sflag[slot][fl]) {
+                const int valid = sflag[slot][fl];
+                // tensor-memory accesses are warp-wide: a warp with any valid lane runs the step on all lanes, the
+                // others with F = I and no process noise (every entry of P keeps its value)
+                if (TM ? __any_sync(0xffffffffu, valid) : valid) {
                     const double* rec = X + (size_t)slot * 22 * BSF;
                     double A[9], Bm[9];
 #pragma unroll
                     for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * BSF]; Bm[e] = rec[(size_t)(9 + e) * BSF]; }
-                    const double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
-                    const double dt = rec[(size_t)21 * BSF];
+                    double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
+                    double dt = rec[(size_t)21 * BSF];
+                    double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
+                    if (TM && !valid) {
+#pragma unroll
+                        for (int e = 0; e < 9; ++e) { A[e] = 0.0; Bm[e] = 0.0; }
+                        u0 = u1 = u2 = dt = 0.0;
+                        Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;
+                    }
+                    P.fence_st();  // the previous step's stores
 #if FBUS_TL_REGS && FBUS_BR_REGS_SPLIT
-                    propagate_cov_core<BSF, true, true>(P, A, Bm, u0, u1, u2, dt, k.Qd, BR, TL);
+                    propagate_cov_core<BSF, true, true>(P, A, Bm, u0, u1, u2, dt, Qv, BR, TL);
 #elif FBUS_TL_REGS
-                    propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, k.Qd, nullptr, TL);
+                    propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL);
 #else
-                    propagate_cov_core<BSF>(P, A, Bm, u0, u1, u2, dt, k.Qd);
+                    propagate_cov_core<BSF>(P, A, Bm, u0, u1, u2, dt, Qv);
 #endif
                 }
             }
 #if FBUS_TL_REGS && !FBUS_TL_PERSIST
-            tl_store<BSF>(P, TL);
+            tl_store_any<TM>(P, TL);
 #endif
 #if FBUS_BR_REGS_SPLIT
             br_store_diag<BSF>(P, BR);
@@ -200,7 +275,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             }
             step_bar<NT>(wq);  // (d) covariance updated, first half of dx posted
 #else
-            if (req) {
+            if (TM ? true : (req != 0)) {  // tensor memory: all lanes, the ones without a request with zero gain
                 const double* rq = X + (size_t)fs * 22 * BSF;
                 Nominal t;
                 double yP[3], yQ[4];
@@ -214,12 +289,14 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { t.v[c] = 0.0; t.ba[c] = 0.0; t.bg[c] = 0.0; t.g[c] = 0.0; }
                 t.t = 0.0;
-                const MarkerConst mkc = prm.tab->mk[req - 1];
+                const MarkerConst mkc = prm.tab->mk[(req > 0 ? req : 1) - 1];
+                P.fence_st();
 #if FBUS_TL_REGS && FBUS_TL_PERSIST
-                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(PT, t, k, mkc, yP, yQ, X);
+                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(PT, t, k, mkc, yP, yQ, X, req != 0);
 #else
-                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X);
+                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X, req != 0);
 #endif
+                P.fence_st();
                 // hand back: corrected p, q and the increments of v, b_a, b_g, g
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -237,10 +314,28 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
         }
     }
 #if FBUS_TL_REGS && FBUS_TL_PERSIST
-    tl_store<BSF>(P, TL);
+    tl_store_any<TM>(P, TL);
 #endif
-    if (live)
-        for (int e = 0; e < NPK; ++e) prm.P[(size_t)e * B + b] = smem[e * BSF + fl];
+    if constexpr (TM) {
+        P.fence_st();
+        FBUS_UNROLL
+        for (int bj = 0; bj < 6; ++bj)
+            FBUS_UNROLL
+            for (int bi = 0; bi <= bj; ++bi) {
+                double T[9];
+                P.ldraw(bi, bj, T);
+                tm_wait_ld();
+                if (live) {
+                    FBUS_UNROLL
+                    for (int r = 0; r < 3; ++r)
+                        FBUS_UNROLL
+                        for (int c = (bi == bj ? r : 0); c < 3; ++c) prm.P[(size_t)pidx(3 * bi + r, 3 * bj + c) * B + b] = T[r * 3 + c];
+                }
+            }
+    } else {
+        if (live)
+            for (int e = 0; e < NPK; ++e) prm.P[(size_t)e * B + b] = smem[e * BSF + fl];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -381,12 +476,12 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
     }
 }
 
-template <int BSF>
+template <int BSF, bool TM>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
                                              int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
     constexpr int NT = 2 * BSF, NW = BSF / 32;
     const size_t B = prm.B;
-    double* const X = smem + (size_t)NPK * BSF + fl;
+    double* const X = smem + (size_t)(TM ? 0 : NPK) * BSF + fl;
     const bool fused = (prm.mode & M_FUSED) != 0;
     const int wq = fl >> 5;  // nominal warp index
     Nominal n;
@@ -653,8 +748,15 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
     const size_t b0 = (size_t)blockIdx.x * BSF + fl;
     const bool live = b0 < prm.B;
     const size_t b = live ? b0 : prm.B - 1;  // threads past the batch mirror the last filter and never store
-    if (is_cov) cov_role<BSF, JOSEPH>(prm, k, smem, sh, sflag, fl, b, live);
-    else nominal_role<BSF>(prm, k, smem, sh, sflag, fl, b, live);
+    constexpr bool TM = (FBUS_TMEM != 0) && BSF == 128 && (FBUS_COOP_UPDATE == 0);
+    uint32_t tm_base = 0;
+    if constexpr (TM) {
+        __shared__ uint32_t tm_slot;
+        tm_base = tm_alloc_cta(&tm_slot);
+    }
+    if (is_cov) cov_role<BSF, JOSEPH, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
+    else nominal_role<BSF, TM>(prm, k, smem, sh, sflag, fl, b, live);
+    if constexpr (TM) tm_free_cta(tm_base);
 }
 
 }  // namespace fbus

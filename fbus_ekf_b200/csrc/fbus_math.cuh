@@ -188,8 +188,15 @@ FBUS_HD constexpr int tlidx(int i, int j) {
 }
 template <int S, bool TLR = false>
 struct CovX {
+    static constexpr bool kTLR = TLR;
+    static constexpr bool kBlocked = false;  // element access is as cheap as block access
     double* s;
     double* TL = nullptr;
+    FBUS_HD void fence_st() const {}  // accessors with asynchronous stores (tensor memory) order them here
+    // asynchronous-load API of the tensor-memory accessor (fbus_tmem.cuh); plain loads here
+    FBUS_HD void ldblk_nw(int bi, int bj, double* X) const { ldany(bi, bj, X); }
+    FBUS_HD void wait_ld() const {}
+    FBUS_HD void fix(int, int, double*) const {}
     FBUS_HD double ld(int i, int j) const {
         if (TLR && i < 9 && j < 9) return TL[tlidx(i, j)];
         return s[pidx(i, j) * S];
@@ -252,15 +259,15 @@ FBUS_HD constexpr int bridx(int i, int j) {  // any order; i,j in 9..17
 }
 constexpr int NBR = 45;
 constexpr int NTL = 45;  // packed size of the top-left 9x9 (tlidx)
-template <int S>
-FBUS_HD void tl_load(const Cov<S> P, double* TL) {
+template <int S, class CV = Cov<S>>
+FBUS_HD void tl_load(const CV P, double* TL) {
     FBUS_UNROLL
     for (int i = 0; i < 9; ++i)
         FBUS_UNROLL
         for (int j = i; j < 9; ++j) TL[tlidx(i, j)] = P.ld(i, j);
 }
-template <int S>
-FBUS_HD void tl_store(const Cov<S> P, const double* TL) {
+template <int S, class CV = Cov<S>>
+FBUS_HD void tl_store(const CV P, const double* TL) {
     FBUS_UNROLL
     for (int i = 0; i < 9; ++i)
         FBUS_UNROLL
@@ -300,8 +307,8 @@ FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, dou
 
 // TLR = true: the top-left 9x9 (p, v, theta covariance: read AND written by every step) is held in the caller's
 // registers TL[45] across the IMU samples of a window instead of making a round trip through shared memory per step.
-template <int S, bool BRR = false, bool TLR = false>
-FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B, double u0, double u1, double u2, double dt,
+template <int S, bool BRR = false, bool TLR = false, class CV = Cov<S>>
+FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, double u0, double u1, double u2, double dt,
                                 const double* Qd, double* BR = nullptr, double* TL = nullptr) {
 #define FBUS_TLLD(i, j) (TLR ? TL[tlidx((i), (j))] : P.ld((i), (j)))
 #define FBUS_TLST(i, j, v)                        \
@@ -350,7 +357,8 @@ FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B
         {   // 1c: P'22 (without the -a*M24 term) ; M12 = P12 + A*P22 (+ more below)
             double P22[9], P24[9], U22[9], acc22[9];
             FBUS_TL_LDBLK(2, 2, P22);
-            P.ldblk(2, 4, P24);
+            P.ldblk_nw(2, 4, P24);
+            P.wait_ld();
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -378,8 +386,9 @@ FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B
         FBUS_FENCE_A;
         {   // M12 += B*P23^T + a*P25^T
             double P23[9], P25[9];
-            P.ldblk(2, 3, P23);
-            P.ldblk(2, 5, P25);
+            P.ldblk_nw(2, 3, P23);
+            P.ldblk_nw(2, 5, P25);
+            P.wait_ld();
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -395,8 +404,9 @@ FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B
         {   // 1b: P'11 (without the M13*B^T + a*M15 term), P'12 (without -a*M14)
             double P13[9], P15[9], acc11[9], acc12[9];
             FBUS_TL_LDBLK(1, 1, P11);
-            P.ldblk(1, 3, P13);
-            P.ldblk(1, 5, P15);
+            P.ldblk_nw(1, 3, P13);
+            P.ldblk_nw(1, 5, P15);
+            P.wait_ld();
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -465,11 +475,13 @@ FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B
     FBUS_UNROLL
     for (int kk = 0; kk < 3; ++kk) {
         const int k = (kk == 0) ? 4 : (kk == 1) ? 3 : 5;
-        double X1[9];
-        P.ldblk(1, k, X1);
+        double X1[9], X2[9];
+        P.ldblk_nw(1, k, X1);
         {   // row 0: M0 = P0k + a*P1k
             double M0[9];
-            P.ldblk(0, k, M0);
+            P.ldblk_nw(0, k, M0);
+            P.ldblk_nw(2, k, X2);
+            P.wait_ld();
             FBUS_UNROLL
             for (int e = 0; e < 9; ++e) M0[e] += a * X1[e];
             P.stblk(0, k, M0);
@@ -504,8 +516,7 @@ FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B
             }
         }
         FBUS_FENCE_A;
-        double X2[9];
-        P.ldblk(2, k, X2);
+        double X4[9];
         {   // row 1: M1 = P1k + A*P2k + B*P3k + a*P5k
             double X3[9], X5[9];
             if (BRR) {
@@ -517,8 +528,13 @@ FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B
                         X5[r * 3 + c] = BR[bridx(15 + r, 3 * k + c)];
                     }
             } else {
-                P.ldany(3, k, X3);
-                P.ldany(5, k, X5);
+                P.ldblk_nw(3, k, X3);
+                P.ldblk_nw(5, k, X5);
+                P.ldblk_nw(4, k, X4);
+                P.wait_ld();
+                P.fix(3, k, X3);
+                P.fix(5, k, X5);
+                P.fix(4, k, X4);
             }
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
@@ -571,14 +587,12 @@ FBUS_HD void propagate_cov_core(const Cov<S> P, const double* A, const double* B
         }
         FBUS_FENCE_A;
         {   // row 2: M2 = (I+Wm)*P2k - a*P4k
-            double X4[9], M2[9];
+            double M2[9];
             if (BRR) {
                 FBUS_UNROLL
                 for (int r = 0; r < 3; ++r)
                     FBUS_UNROLL
                     for (int c = 0; c < 3; ++c) X4[r * 3 + c] = BR[bridx(12 + r, 3 * k + c)];
-            } else {
-                P.ldany(4, k, X4);
             }
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
@@ -747,8 +761,8 @@ struct CholStep<N, N> {
 // Prologue of the update: everything up to the gain factors.  Reads only the 21 entries of P6 = P[{p,theta},{p,theta}].
 // Outputs Cm = lower-packed Cholesky factor Lc of C = Hs^T S^-1 Hs and y = Lc^-1 u (u = Hs^T S^-1 r), so that
 //   (I-KH)P = P - Z^T Z with Z = Lc^T G, and dx = K r = Z^T y.
-template <int S, int XS, bool JOSEPH = false, bool TLR = false>
-FBUS_HD void update_prologue(const CovX<S, TLR> P, const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+template <int S, int XS, bool JOSEPH = false, class CV = Cov<S>>
+FBUS_HD void update_prologue(const CV P, const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
                              const double* yQ, double* Cm, double* y, double* scr) {
     // scr: 42 doubles of scratch with element stride XS (shared memory in the warp-specialised kernel) for X = L^-1 Hs
     // ---- predicted measurement and Hs ------------------------------------------------------
@@ -1114,8 +1128,8 @@ FBUS_HD void measurement_update_coop(const Cov<S> P, Nominal& n, const DevConsts
 #ifndef FBUS_PROLOGUE_PARK
 #define FBUS_PROLOGUE_PARK 1
 #endif
-template <int S, int XS, bool TLR = false>
-FBUS_HD void update_onepass(const CovX<S, TLR> P, Nominal& n, const double* Cm, const double* y, double* stash) {
+template <int S, int XS, class CV = Cov<S>>
+FBUS_HD void update_onepass(const CV P, Nominal& n, const double* Cm, const double* y, double* stash) {
 #define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
 #define FBUS_GROW(m) (((m) < 3) ? (m) : (3 + (m)))  // rows of G: 0,1,2,6,7,8
     double dth[3] = {0.0, 0.0, 0.0};
@@ -1156,6 +1170,7 @@ FBUS_HD void update_onepass(const CovX<S, TLR> P, Nominal& n, const double* Cm, 
             P.st(i, j, v);
         }
     FBUS_FENCE;
+    P.fence_st();
     // ---- phase 2: columns 9..17: Z column from the OLD G entries of that column, cross entries, stash ------
     FBUS_UNROLL
     for (int c = 9; c < 18; ++c) {
@@ -1187,6 +1202,7 @@ FBUS_HD void update_onepass(const CovX<S, TLR> P, Nominal& n, const double* Cm, 
         }
     }
     FBUS_FENCE;
+    P.fence_st();
     // ---- phase 3: bottom-right block from the stashed columns -------------------------------------------
     {
         double Z2[54];  // Z[k][c], c = 9..17, at Z2[(c - 9) * 6 + k]
@@ -1221,12 +1237,165 @@ FBUS_HD void update_onepass(const CovX<S, TLR> P, Nominal& n, const double* Cm, 
 }
 
 // JMODE: 0 = reference form (I-KH)P, 1 = Joseph form, -1 = decided at run time from k.flags (host harness, un-split kernel)
+// Block form of the one-pass update for accessors whose natural unit is a 3x3 block (tensor memory): same arithmetic per
+// entry (six FMAs in the same order), the entries are visited block by block.
+//   1. Z columns 0..8 from the blocks (0,0) (0,1) (0,2) (1,2) (2,2); sweep of the six top-left blocks;
+//   2a. Z columns 9..17 from the blocks (0,k), (2,k), k = 3..5 -> stash (Lc is dead afterwards);
+//   2b. sweep of the nine cross blocks (Z columns of block column k re-read from the stash);
+//   3.  sweep of the six bottom-right blocks from the stashed columns.
+template <int S, int XS, class CV>
+FBUS_HD void update_onepass_blk(const CV P, Nominal& n, const double* Cm, const double* y, double* stash) {
+#define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
+    double dth[3] = {0.0, 0.0, 0.0};
+    double Z1[54];  // Z[k][c], c = 0..8, at Z1[k * 9 + c]
+    {
+        double B00[9], B01[9], B02[9], B12[9], B22[9];
+        P.ldblk_nw(0, 0, B00); P.ldblk_nw(0, 1, B01); P.ldblk_nw(0, 2, B02); P.ldblk_nw(1, 2, B12); P.ldblk_nw(2, 2, B22);
+        P.wait_ld();
+        FBUS_UNROLL
+        for (int c = 0; c < 9; ++c) {
+            double g[6];
+            FBUS_UNROLL
+            for (int m = 0; m < 3; ++m) {
+                g[m] = (c < 3) ? B00[m * 3 + c] : (c < 6) ? B01[m * 3 + (c - 3)] : B02[m * 3 + (c - 6)];
+                g[3 + m] = (c < 3) ? B02[c * 3 + m] : (c < 6) ? B12[(c - 3) * 3 + m] : B22[m * 3 + (c - 6)];
+            }
+            FBUS_UNROLL
+            for (int kz = 0; kz < 6; ++kz) {
+                double z = FBUS_C(kz, kz) * g[kz];
+                FBUS_UNROLL
+                for (int m = kz + 1; m < 6; ++m) z += FBUS_C(m, kz) * g[m];
+                Z1[kz * 9 + c] = z;
+            }
+        }
+    }
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        FBUS_UNROLL
+        for (int kz = 0; kz < 6; ++kz) {
+            n.p[i] += y[kz] * Z1[kz * 9 + i];
+            n.v[i] += y[kz] * Z1[kz * 9 + 3 + i];
+            dth[i] += y[kz] * Z1[kz * 9 + 6 + i];
+        }
+    }
+    FBUS_FENCE;
+    FBUS_UNROLL
+    for (int bj = 0; bj < 3; ++bj)
+        FBUS_UNROLL
+        for (int bi = 0; bi <= bj; ++bi) {
+            double T[9];
+            P.ldblk_nw(bi, bj, T);
+            P.wait_ld();
+            FBUS_UNROLL
+            for (int r = 0; r < 3; ++r)
+                FBUS_UNROLL
+                for (int c = (bi == bj ? r : 0); c < 3; ++c) {
+                    double v = T[r * 3 + c];
+                    FBUS_UNROLL
+                    for (int kz = 0; kz < 6; ++kz) v -= Z1[kz * 9 + 3 * bi + r] * Z1[kz * 9 + 3 * bj + c];
+                    T[r * 3 + c] = v;
+                }
+            if (bi == bj) P.stdiag(bi, T);
+            else P.stblk(bi, bj, T);
+        }
+    FBUS_FENCE;
+    // ---- 2a: Z columns 9..17 -> stash ------------------------------------------------------------------
+    FBUS_UNROLL
+    for (int k = 3; k < 6; ++k) {
+        double B0[9], B2[9];
+        P.ldblk_nw(0, k, B0); P.ldblk_nw(2, k, B2);
+        P.wait_ld();
+        FBUS_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            double z[6];
+            FBUS_UNROLL
+            for (int kz = 0; kz < 6; ++kz) {
+                double t = FBUS_C(kz, kz) * ((kz < 3) ? B0[kz * 3 + c] : B2[(kz - 3) * 3 + c]);
+                FBUS_UNROLL
+                for (int m = kz + 1; m < 6; ++m) t += FBUS_C(m, kz) * ((m < 3) ? B0[m * 3 + c] : B2[(m - 3) * 3 + c]);
+                z[kz] = t;
+                stash[(size_t)(((k - 3) * 3 + c) * 6 + kz) * XS] = t;
+            }
+            double* dst = (k == 3) ? &n.ba[c] : (k == 4) ? &n.bg[c] : &n.g[c];
+            double d = *dst;
+            FBUS_UNROLL
+            for (int kz = 0; kz < 6; ++kz) d += y[kz] * z[kz];
+            *dst = d;
+        }
+    }
+#undef FBUS_C
+    FBUS_FENCE;
+    // ---- 2b: cross blocks -----------------------------------------------------------------------------
+    FBUS_UNROLL
+    for (int k = 3; k < 6; ++k) {
+        double zc[18];  // z of columns 3k..3k+2: zc[c * 6 + kz]
+        FBUS_UNROLL
+        for (int e = 0; e < 18; ++e) zc[e] = stash[(size_t)((k - 3) * 18 + e) * XS];
+        FBUS_UNROLL
+        for (int bi = 0; bi < 3; ++bi) {
+            double T[9];
+            P.ldblk_nw(bi, k, T);
+            P.wait_ld();
+            FBUS_UNROLL
+            for (int r = 0; r < 3; ++r)
+                FBUS_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    double v = T[r * 3 + c];
+                    FBUS_UNROLL
+                    for (int kz = 0; kz < 6; ++kz) v -= Z1[kz * 9 + 3 * bi + r] * zc[c * 6 + kz];
+                    T[r * 3 + c] = v;
+                }
+            P.stblk(bi, k, T);
+        }
+    }
+    FBUS_FENCE;
+    // ---- 3: bottom-right blocks -----------------------------------------------------------------------
+    {
+        double Z2[54];  // Z[k][c], c = 9..17, at Z2[(c - 9) * 6 + k]
+        FBUS_UNROLL
+        for (int e = 0; e < 54; ++e) Z2[e] = stash[(size_t)e * XS];
+        FBUS_UNROLL
+        for (int bj = 3; bj < 6; ++bj)
+            FBUS_UNROLL
+            for (int bi = 3; bi <= bj; ++bi) {
+                double T[9];
+                P.ldblk_nw(bi, bj, T);
+                P.wait_ld();
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r)
+                    FBUS_UNROLL
+                    for (int c = (bi == bj ? r : 0); c < 3; ++c) {
+                        double v = T[r * 3 + c];
+                        FBUS_UNROLL
+                        for (int kz = 0; kz < 6; ++kz) v -= Z2[(3 * (bi - 3) + r) * 6 + kz] * Z2[(3 * (bj - 3) + c) * 6 + kz];
+                        T[r * 3 + c] = v;
+                    }
+                if (bi == bj) P.stdiag(bi, T);
+                else P.stblk(bi, bj, T);
+            }
+    }
+    {   // VectorToQuaterniond (matrix_math.hpp:90-99): v/|v| * sin(|v|/2); NaN at exactly zero, as the reference
+        const double v2 = dth[0] * dth[0] + dth[1] * dth[1] + dth[2] * dth[2];
+        const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
+        const double vn = v2 * iv;
+        double sh, ch;
+        sincos(vn * 0.5, &sh, &ch);
+        const double sc = iv * sh;
+        const double dq[4] = {ch, dth[0] * sc, dth[1] * sc, dth[2] * sc};
+        double qn[4];
+        qmul(n.q, dq, qn);
+        qnormalize(qn);
+        FBUS_UNROLL
+        for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
+    }
+}
+
 // stash: 54 doubles of scratch with stride XS (nullptr: a private array)
-template <int S, int JMODE = -1, int XS = 1, bool TLR = false>
-FBUS_HD void measurement_update(const CovX<S, TLR> P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
-                                const double* yQ, double* stash = nullptr) {
+template <int S, int JMODE = -1, int XS = 1, class CV = Cov<S>>
+FBUS_HD void measurement_update(const CV P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+                                const double* yQ, double* stash = nullptr, bool on = true) {
     double Cm[21], y[6];
-    if (TLR && XS > 1 && FBUS_PROLOGUE_PARK) {
+    if (CV::kTLR && XS > 1 && FBUS_PROLOGUE_PARK) {
         // the register-resident top-left block leaves no room for X = L^-1 Hs (42 doubles): park it in the stash area
         if (JMODE == 1 || (JMODE < 0 && (k.flags & 1))) update_prologue<S, XS, true>(P, n, k, mk, yP, yQ, Cm, y, stash);
         else update_prologue<S, XS, false>(P, n, k, mk, yP, yQ, Cm, y, stash);
@@ -1235,8 +1404,16 @@ FBUS_HD void measurement_update(const CovX<S, TLR> P, Nominal& n, const DevConst
         if (JMODE == 1 || (JMODE < 0 && (k.flags & 1))) update_prologue<S, 1, true>(P, n, k, mk, yP, yQ, Cm, y, xloc);
         else update_prologue<S, 1, false>(P, n, k, mk, yP, yQ, Cm, y, xloc);
     }
+    if (!on) {  // lane without an update inside a warp that must stay convergent: zero gain, P and the state keep their values
+        FBUS_UNROLL
+        for (int i = 0; i < 21; ++i) Cm[i] = 0.0;
+        FBUS_UNROLL
+        for (int i = 0; i < 6; ++i) y[i] = 0.0;
+    }
 #if FBUS_UPDATE_ONEPASS
-    if (stash != nullptr) {
+    if (CV::kBlocked) {
+        update_onepass_blk<S, XS>(P, n, Cm, y, stash);
+    } else if (stash != nullptr) {
         update_onepass<S, XS>(P, n, Cm, y, stash);
     } else {
         double loc[54];
