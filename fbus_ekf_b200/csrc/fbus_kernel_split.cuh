@@ -201,15 +201,10 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                     double A[9], Bm[9];
 #pragma unroll
                     for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * BSF]; Bm[e] = rec[(size_t)(9 + e) * BSF]; }
-                    double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
-                    double dt = rec[(size_t)21 * BSF];
+                    const double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
+                    const double dt = rec[(size_t)21 * BSF];
                     double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
-                    if (TM && !valid) {
-#pragma unroll
-                        for (int e = 0; e < 9; ++e) { A[e] = 0.0; Bm[e] = 0.0; }
-                        u0 = u1 = u2 = dt = 0.0;
-                        Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;
-                    }
+                    if (TM && !valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;  // the record of an invalid sample is all zeros
                     P.fence_st();  // the previous step's stores
 #if FBUS_TL_REGS && FBUS_BR_REGS_SPLIT
                     propagate_cov_core<BSF, true, true>(P, A, Bm, u0, u1, u2, dt, Qv, BR, TL);
@@ -587,6 +582,11 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                         propagate_nominal(n, dt, d, d + 3);  // F2 after F1's coefficients were taken (filter.cpp:509-513)
                         n.t = ti;
                     }
+                }
+                if (TM && !valid) {  // tensor-memory mode: the covariance warp runs every lane, invalid ones with F = I
+                    double* rec = X + (size_t)slot * 22 * BSF;
+#pragma unroll
+                    for (int e = 0; e < 22; ++e) rec[(size_t)e * BSF] = 0.0;
                 }
                 sflag[slot][fl] = valid;
                 step_bar<NT>(wq);  // publish record (i); also: the covariance warp has finished sample i-1

@@ -310,6 +310,9 @@ FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, dou
 template <int S, bool BRR = false, bool TLR = false, class CV = Cov<S>>
 FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, double u0, double u1, double u2, double dt,
                                 const double* Qd, double* BR = nullptr, double* TL = nullptr) {
+// element (r, c) of block (bi, bj) loaded with ldblk_nw: a blocked accessor delivers the stored block (min, max), i.e. the
+// transpose when bi > bj (BRR: the register cache is already in the requested orientation)
+#define FBUS_BLK(X, bi, bj, r, c) ((CV::kBlocked && !BRR && (bi) > (bj)) ? X[(c) * 3 + (r)] : X[(r) * 3 + (c)])
 #define FBUS_TLLD(i, j) (TLR ? TL[tlidx((i), (j))] : P.ld((i), (j)))
 #define FBUS_TLST(i, j, v)                        \
     do {                                          \
@@ -531,21 +534,18 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
                 P.ldblk_nw(3, k, X3);
                 P.ldblk_nw(5, k, X5);
                 P.ldblk_nw(4, k, X4);
-                P.wait_ld();
-                P.fix(3, k, X3);
-                P.fix(5, k, X5);
-                P.fix(4, k, X4);
+                P.wait_ld();  // blocks below the diagonal arrive transposed from a blocked accessor: FBUS_BLK indexes them
             }
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
                 for (int j = 0; j < 3; ++j) {
                     double s = X1[i * 3 + j];
-                    s += a * X5[i * 3 + j];
+                    s += a * FBUS_BLK(X5, 5, k, i, j);
                     FBUS_UNROLL
                     for (int c = 0; c < 3; ++c) {
                         s += A[i * 3 + c] * X2[c * 3 + j];
-                        s += B[i * 3 + c] * X3[c * 3 + j];
+                        s += B[i * 3 + c] * FBUS_BLK(X3, 3, k, c, j);
                     }
                     X1[i * 3 + j] = s;  // M1 in place (X1[i][j] is not read again)
                 }
@@ -599,7 +599,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
                 FBUS_UNROLL
                 for (int j = 0; j < 3; ++j) {
                     double t = X2[i * 3 + j];
-                    t -= a * X4[i * 3 + j];
+                    t -= a * FBUS_BLK(X4, 4, k, i, j);
                     FBUS_WX_ACC(t, X2, i, j);
                     M2[i * 3 + j] = t;
                 }
@@ -624,6 +624,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
     }
 #undef FBUS_WX_ACC
 #undef FBUS_XWT_ACC
+#undef FBUS_BLK
 #undef FBUS_TLLD
 #undef FBUS_TLST
 #undef FBUS_TL_LDBLK

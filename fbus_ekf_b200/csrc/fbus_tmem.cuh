@@ -14,6 +14,10 @@
 
 #include "fbus_math.cuh"
 
+#ifndef FBUS_TMEM_WIDE_ST
+#define FBUS_TMEM_WIDE_ST 1  // measured: 8.64e9 (wide) vs 8.57e9 (nine 2-column stores) filter-steps/s
+#endif
+
 namespace fbus {
 
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -96,8 +100,13 @@ struct CovTM {
     }
     __device__ __forceinline__ void straw(int bi, int bj, const double* X) const {
         const uint32_t a = base + tm_blk_col(bi, bj);
-        tm_st8(a, X);
+#if FBUS_TMEM_WIDE_ST
+        tm_st8(a, X);  // one 16-column store: needs the eight values in consecutive registers (ptxas adds moves)
         tm_st1(a + 16u, X[8]);
+#else
+        FBUS_UNROLL
+        for (int e = 0; e < 9; ++e) tm_st1(a + 2u * (uint32_t)e, X[e]);  // nine 2-column stores straight from where the values are
+#endif
     }
     // X[r*3+c] = P[3bi+r][3bj+c], any order of bi, bj
     __device__ __forceinline__ void ldblk(int bi, int bj, double* X) const {
