@@ -33,6 +33,11 @@
 #ifndef FBUS_TMEM
 #define FBUS_TMEM 1
 #endif
+// 1 (tensor-memory kernel only): the nominal warp sweeps the bottom-right blocks of the update (stage 3) while the
+// covariance warp sweeps the cross blocks (stage 2b); both read the same stashed Z columns
+#ifndef FBUS_OFFLOAD3
+#define FBUS_OFFLOAD3 0  // measured: 8.45e9 vs 8.62e9 filter-steps/s (one more hand-over barrier per update, 270 FMA moved)
+#endif
 // 1: both warps of a filter group share the update: the covariance warp computes the gain factors and applies the first
 //    half-rank factor Za, the nominal warp applies the second (Zb) and injects the error state; 0: covariance warp alone
 #ifndef FBUS_COOP_UPDATE
@@ -83,6 +88,10 @@ struct SplitShared {
 // The next frame's (a) doubles as "results consumed".
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int RQ_EXTRA = 44;  // the request needs 23 doubles: 22 in the free ring slot + this one
+// first double of the update's results (19 doubles: p, q, dv, db_a, db_g, dg).  The tensor-memory kernel has shared memory to
+// spare and keeps them clear of the stash (0..53), which the partner warp may still be reading (FBUS_OFFLOAD3)
+constexpr int XCH_TM = 76;
+template <bool TM> struct ResArea { static constexpr int first = TM ? 56 : 23; };
 
 // top-left 9x9 <-> registers, block-wise (six 3x3 blocks) for the tensor-memory accessor
 template <bool TM, class CV>
@@ -123,6 +132,19 @@ __device__ __forceinline__ void tl_store_any(const CV P, const double* TL) {
     }
 }
 
+// hand-over inside the update (see update_onepass_blk): stores of this warp complete, pair barrier, tensor-memory fences
+template <int NT>
+struct PairSync {
+    static constexpr bool kOffload3 = true;
+    int wq;
+    __device__ __forceinline__ void operator()() const {
+        tm_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        step_bar<NT>(wq);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+};
+
 template <int NT>
 __device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) {
 #if FBUS_PAIR_BARRIER
@@ -143,6 +165,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                                          int fl, size_t b, bool live, uint32_t tm_base) {
     constexpr int NT = 2 * BSF, NW = BSF / 32;
     constexpr int NPS = TM ? 0 : NPK;  // doubles of P per filter in shared memory
+    constexpr int RES0 = ResArea<TM>::first;
     const size_t B = prm.B;
     using CV = typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type;
     CV P;
@@ -289,22 +312,25 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #if FBUS_TL_REGS && FBUS_TL_PERSIST
                 measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(PT, t, k, mkc, yP, yQ, X, req != 0);
 #else
-                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X, req != 0);
+                if constexpr (TM && FBUS_OFFLOAD3) measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X, req != 0, PairSync<NT>{wq});
+                else measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X, req != 0);
 #endif
                 P.fence_st();
                 // hand back: corrected p, q and the increments of v, b_a, b_g, g
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    X[(size_t)(23 + c) * BSF] = t.p[c];
-                    X[(size_t)(30 + c) * BSF] = t.v[c];
-                    X[(size_t)(33 + c) * BSF] = t.ba[c];
-                    X[(size_t)(36 + c) * BSF] = t.bg[c];
-                    X[(size_t)(39 + c) * BSF] = t.g[c];
+                    X[(size_t)(RES0 + 0 + c) * BSF] = t.p[c];
+                    X[(size_t)(RES0 + 7 + c) * BSF] = t.v[c];
+                    X[(size_t)(RES0 + 10 + c) * BSF] = t.ba[c];
+                    X[(size_t)(RES0 + 13 + c) * BSF] = t.bg[c];
+                    X[(size_t)(RES0 + 16 + c) * BSF] = t.g[c];
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) X[(size_t)(26 + c) * BSF] = t.q[c];
+                for (int c = 0; c < 4; ++c) X[(size_t)(RES0 + 3 + c) * BSF] = t.q[c];
             }
-            step_bar<NT>(wq);  // (d) results posted
+            if constexpr (TM && FBUS_OFFLOAD3) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            step_bar<NT>(wq);  // (d) results posted (and the partner's bottom-right sweep is complete)
+            if constexpr (TM && FBUS_OFFLOAD3) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #endif
         }
     }
@@ -473,10 +499,11 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
 
 template <int BSF, bool TM>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
-                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
+                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live, uint32_t tm_base) {
     constexpr int NT = 2 * BSF, NW = BSF / 32;
     const size_t B = prm.B;
     double* const X = smem + (size_t)(TM ? 0 : NPK) * BSF + fl;
+    constexpr int RES0 = ResArea<TM>::first;
     const bool fused = (prm.mode & M_FUSED) != 0;
     const int wq = fl >> 5;  // nominal warp index
     Nominal n;
@@ -658,18 +685,28 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                 }
             }
 #else
+            if constexpr (TM && FBUS_OFFLOAD3) {
+                // stage 3 of the update on this warp: the Z columns 9..17 are in the exchange area after the hand-over
+                CovTM<false> PN;
+                PN.base = tm_base + ((uint32_t)((threadIdx.x >> 5) & 3) << 21);
+                step_bar<NT>(wq);  // hand-over (PairSync in the covariance warp)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                update_bottom_right_blk<BSF>(PN, X);
+                tm_wait_st();
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
             step_bar<NT>(wq);  // (d) results posted
             if (req) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    n.p[c] = X[(size_t)(23 + c) * BSF];
-                    n.v[c] += X[(size_t)(30 + c) * BSF];
-                    n.ba[c] += X[(size_t)(33 + c) * BSF];
-                    n.bg[c] += X[(size_t)(36 + c) * BSF];
-                    n.g[c] += X[(size_t)(39 + c) * BSF];
+                    n.p[c] = X[(size_t)(RES0 + 0 + c) * BSF];
+                    n.v[c] += X[(size_t)(RES0 + 7 + c) * BSF];
+                    n.ba[c] += X[(size_t)(RES0 + 10 + c) * BSF];
+                    n.bg[c] += X[(size_t)(RES0 + 13 + c) * BSF];
+                    n.g[c] += X[(size_t)(RES0 + 16 + c) * BSF];
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(26 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
+                for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(RES0 + 3 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
             }
 #endif
         }
@@ -755,7 +792,7 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
         tm_base = tm_alloc_cta(&tm_slot);
     }
     if (is_cov) cov_role<BSF, JOSEPH, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
-    else nominal_role<BSF, TM>(prm, k, smem, sh, sflag, fl, b, live);
+    else nominal_role<BSF, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
     if constexpr (TM) tm_free_cta(tm_base);
 }
 
