@@ -38,6 +38,12 @@
 #ifndef FBUS_OFFLOAD3
 #define FBUS_OFFLOAD3 0  // measured: 8.45e9 vs 8.62e9 filter-steps/s (one more hand-over barrier per update, 270 FMA moved)
 #endif
+// Tensor-memory kernel: depth of the coefficient ring between the nominal and the covariance warp.  0: two slots handed over
+// with one pair barrier per sample (lock-step); D > 0: D slots with mbarrier full/empty pairs, the nominal warp may run up
+// to D samples ahead and neither warp waits for the other sample by sample
+#ifndef FBUS_RING_DEPTH
+#define FBUS_RING_DEPTH 0  // measured: 8.62e9 (lock-step) vs 8.25e9 (D = 2), 8.32e9 (D = 3), 8.25e9 (D = 6) filter-steps/s
+#endif
 // 1: both warps of a filter group share the update: the covariance warp computes the gain factors and applies the first
 //    half-rank factor Za, the nominal warp applies the second (Zb) and injects the error state; 0: covariance warp alone
 #ifndef FBUS_COOP_UPDATE
@@ -71,9 +77,28 @@ __device__ __forceinline__ void step_bar(int pair) {
 #endif
 }
 
+constexpr int RING_REC = 23;  // doubles per ring record in the mbarrier ring: A 9, B 9, w dt 3, dt, valid
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {  // release: everything this thread did before is visible to the waiter
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {  // acquire; the warp reconverges afterwards
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+    __syncwarp();
+}
+
 struct SplitShared {
     uint32_t lo_hi[2][8];   // per nominal warp: min first / max end of the candidate IMU range
     int32_t any_upd[8];     // per nominal warp: some filter requests an update
+    uint64_t mb_full[4][8];   // mbarrier ring (tensor-memory kernel): record written / record consumed, per warp pair and slot
+    uint64_t mb_empty[4][8];
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -166,6 +191,9 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
     constexpr int NT = 2 * BSF, NW = BSF / 32;
     constexpr int NPS = TM ? 0 : NPK;  // doubles of P per filter in shared memory
     constexpr int RES0 = ResArea<TM>::first;
+    constexpr bool RING = TM && (FBUS_RING_DEPTH > 0);
+    const double* const RG = smem + (size_t)XCH_TM * BSF + fl;  // mbarrier ring (RING only)
+    uint32_t cnt = 0;                                           // samples consumed since the launch started
     const size_t B = prm.B;
     using CV = typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type;
     CV P;
@@ -204,7 +232,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
         int fs = 0;  // ring slot that carries the update request
         if (lo < hi) {
-            fs = (int)((hi - lo) & 1u);
+            if (!RING) fs = (int)((hi - lo) & 1u);
 #if FBUS_TL_REGS && !FBUS_TL_PERSIST
             double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
             tl_load_any<TM>(P, TL);
@@ -214,18 +242,32 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             br_load<BSF>(P, BR);
 #endif
             for (uint32_t i = lo; i < hi; ++i) {
-                step_bar<NT>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
-                const int slot = (int)((i - lo) & 1u);
-                const int valid = sflag[slot][fl];
+                const double* rec;
+                int valid;
+                if constexpr (RING) {
+                    const uint32_t slot = cnt % (uint32_t)FBUS_RING_DEPTH, ph = (cnt / (uint32_t)FBUS_RING_DEPTH) & 1u;
+                    ++cnt;
+                    mb_wait(&sh.mb_full[wq][slot], ph);  // record (i) is complete
+                    rec = RG + (size_t)slot * RING_REC * BSF;
+                    valid = rec[(size_t)22 * BSF] != 0.0;
+                } else {
+                    step_bar<NT>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
+                    const int slot = (int)((i - lo) & 1u);
+                    valid = sflag[slot][fl];
+                    rec = X + (size_t)slot * 22 * BSF;
+                }
                 // tensor-memory accesses are warp-wide: a warp with any valid lane runs the step on all lanes, the
                 // others with F = I and no process noise (every entry of P keeps its value)
-                if (TM ? __any_sync(0xffffffffu, valid) : valid) {
-                    const double* rec = X + (size_t)slot * 22 * BSF;
-                    double A[9], Bm[9];
+                const bool run = TM ? (__any_sync(0xffffffffu, valid) != 0) : (valid != 0);
+                double A[9], Bm[9], u0 = 0.0, u1 = 0.0, u2 = 0.0, dt = 0.0;
+                if (run) {
 #pragma unroll
                     for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * BSF]; Bm[e] = rec[(size_t)(9 + e) * BSF]; }
-                    const double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
-                    const double dt = rec[(size_t)21 * BSF];
+                    u0 = rec[(size_t)18 * BSF]; u1 = rec[(size_t)19 * BSF]; u2 = rec[(size_t)20 * BSF];
+                    dt = rec[(size_t)21 * BSF];
+                }
+                if constexpr (RING) mb_arrive(&sh.mb_empty[wq][(cnt - 1u) % (uint32_t)FBUS_RING_DEPTH]);  // record consumed (the loads above are ordered before this release)
+                if (run) {
                     double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
                     if (TM && !valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;  // the record of an invalid sample is all zeros
                     P.fence_st();  // the previous step's stores
@@ -504,6 +546,9 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     const size_t B = prm.B;
     double* const X = smem + (size_t)(TM ? 0 : NPK) * BSF + fl;
     constexpr int RES0 = ResArea<TM>::first;
+    constexpr bool RING = TM && (FBUS_RING_DEPTH > 0);
+    double* const RG = smem + (size_t)XCH_TM * BSF + fl;  // mbarrier ring (RING only)
+    uint32_t cnt = 0;                                     // samples produced since the launch started
     const bool fused = (prm.mode & M_FUSED) != 0;
     const int wq = fl >> 5;  // nominal warp index
     Nominal n;
@@ -568,7 +613,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
         int fs = 0;
         if (lo < hi) {
-            fs = (int)((hi - lo) & 1u);
+            if (!RING) fs = (int)((hi - lo) & 1u);
             const double start = n.t;
             bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
             uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
@@ -586,7 +631,15 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                     for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)(i + 1) * 6 + c) * B + b];
                 }
-                const int slot = (int)((i - lo) & 1u);
+                int slot = (int)((i - lo) & 1u);
+                double* recp = X + (size_t)slot * 22 * BSF;
+                if constexpr (RING) {
+                    slot = (int)(cnt % (uint32_t)FBUS_RING_DEPTH);
+                    const uint32_t ph = (cnt / (uint32_t)FBUS_RING_DEPTH) & 1u;
+                    ++cnt;
+                    mb_wait(&sh.mb_empty[wq][slot], ph ^ 1u);  // the covariance warp has consumed this slot's previous record
+                    recp = RG + (size_t)slot * RING_REC * BSF;
+                }
                 int valid = 0;
                 if (open && i >= p_first && i < p_end) {
                     if (ti < start) {
@@ -601,7 +654,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                         for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
                         cov_coeffs(n.R, av, wv, dt, A, Bm, u);  // F1 uses the CARRIED rotmatI2G (A.3-2,3)
-                        double* rec = X + (size_t)slot * 22 * BSF;
+                        double* rec = recp;
 #pragma unroll
                         for (int e = 0; e < 9; ++e) { rec[(size_t)e * BSF] = A[e]; rec[(size_t)(9 + e) * BSF] = Bm[e]; }
                         rec[(size_t)18 * BSF] = u[0]; rec[(size_t)19 * BSF] = u[1]; rec[(size_t)20 * BSF] = u[2];
@@ -611,12 +664,16 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                     }
                 }
                 if (TM && !valid) {  // tensor-memory mode: the covariance warp runs every lane, invalid ones with F = I
-                    double* rec = X + (size_t)slot * 22 * BSF;
 #pragma unroll
-                    for (int e = 0; e < 22; ++e) rec[(size_t)e * BSF] = 0.0;
+                    for (int e = 0; e < 22; ++e) recp[(size_t)e * BSF] = 0.0;
                 }
-                sflag[slot][fl] = valid;
-                step_bar<NT>(wq);  // publish record (i); also: the covariance warp has finished sample i-1
+                if constexpr (RING) {
+                    recp[(size_t)22 * BSF] = valid ? 1.0 : 0.0;
+                    mb_arrive(&sh.mb_full[wq][slot]);  // publish record (i)
+                } else {
+                    sflag[slot][fl] = valid;
+                    step_bar<NT>(wq);  // publish record (i); also: the covariance warp has finished sample i-1
+                }
             }
             if (fused && do_prop) cursor = consumed;
         }
@@ -787,6 +844,14 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
     const size_t b = live ? b0 : prm.B - 1;  // threads past the batch mirror the last filter and never store
     constexpr bool TM = (FBUS_TMEM != 0) && BSF == 128 && (FBUS_COOP_UPDATE == 0);
     uint32_t tm_base = 0;
+    if constexpr (TM && FBUS_RING_DEPTH > 0) {
+        static_assert(FBUS_RING_DEPTH <= 8, "mbarrier ring: at most 8 slots");
+        if (threadIdx.x < 4 * FBUS_RING_DEPTH) {
+            mb_init(&sh.mb_full[threadIdx.x / FBUS_RING_DEPTH][threadIdx.x % FBUS_RING_DEPTH], 32);
+            mb_init(&sh.mb_empty[threadIdx.x / FBUS_RING_DEPTH][threadIdx.x % FBUS_RING_DEPTH], 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if constexpr (TM) {
         __shared__ uint32_t tm_slot;
         tm_base = tm_alloc_cta(&tm_slot);
