@@ -31,8 +31,8 @@ constexpr int WIN_BS = FBUS_WIN_BS;  // filters per CTA of the window kernel (17
 #endif
 #if FBUS_SPLIT
 // the 128-filter CTAs keep P in tensor memory (FBUS_TMEM): shared memory then only holds the exchange area
-constexpr bool WIN_TMEM = (FBUS_TMEM != 0) && WIN_BS == 128 && (FBUS_COOP_UPDATE == 0);
-constexpr size_t WIN_SMEM = (size_t)(WIN_TMEM ? XCH_TM + FBUS_RING_DEPTH * RING_REC : NPK + XCH) * WIN_BS * sizeof(double);
+constexpr bool WIN_TMEM = (FBUS_TMEM != 0) && WIN_BS == 128;
+constexpr size_t WIN_SMEM = (size_t)((WIN_TMEM ? 0 : NPK) + XCH) * WIN_BS * sizeof(double);
 #else
 constexpr size_t WIN_SMEM = (size_t)NPK * WIN_BS * sizeof(double);
 #endif

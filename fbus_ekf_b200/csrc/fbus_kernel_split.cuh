@@ -4,14 +4,18 @@
 // warp per scheduler with one thread per filter.  A lone warp cannot overlap its shared-memory traffic, integer work
 // and the serial sin/cos/sqrt/div chains of the nominal-state integration with the half-rate FP64 pipe (ncu: FP64 pipe
 // ~33 % busy, "wait"/"short scoreboard" stalls, 1.0 warp per scheduler).  Here every group of 32 filters gets
-//   * a COVARIANCE warp: F1 (P <- F P F^T + Q) and the measurement update's covariance work, P in shared memory;
+//   * a COVARIANCE warp: F1 (P <- F P F^T + Q) and the measurement update's covariance work; P lives in TENSOR MEMORY
+//                        (one TMEM lane per filter, fbus_tmem.cuh) in the 128-filter CTAs, in shared memory in the
+//                        32-filter CTAs used for small batches;
 //   * a NOMINAL warp:    detection scan, F6b init, F5 reset, F2 nominal integration (q,p,v + the carried rotmatI2G),
 //                        the IMU/detection streams, and the error-state injection after an update.
 // so each scheduler holds two warps with complementary instruction mixes.  The nominal warp runs one IMU sample AHEAD
 // and hands the covariance warp the coefficients of F for that sample (A = -R[a]x dt, B = -R dt, w dt, dt: 22 doubles)
-// through a 2-deep ring in shared memory; one __syncthreads per sample orders the ring and also keeps all warps of the
-// CTA on the same instruction-cache lines.  For an update the nominal warp posts (marker, y, q, R, p), the covariance
-// warp runs measurement_update and posts back the injected pose / state increments.
+// through a 2-deep ring in shared memory; one named barrier per sample (private to the warp pair) orders the ring, one
+// CTA-wide barrier per frame keeps all warps on the same instruction-cache lines.  For an update the nominal warp posts
+// (marker, y, q, R, p), the covariance warp runs measurement_update and posts back the injected pose / state increments;
+// meanwhile the nominal warp plans the next frame.  Variants that were measured and dropped (cooperative update, deeper
+// mbarrier ring, register-resident blocks across frames, ...) are listed in DESIGN.md; the git history has their code.
 //
 // Numerically identical to ekf_window_kernel (same device functions, same order of operations per filter).
 #pragma once
@@ -23,39 +27,14 @@
 #ifndef FBUS_TL_REGS
 #define FBUS_TL_REGS 1
 #endif
-// 1: the top-left block stays in the covariance warp's registers for the whole launch (propagation AND update);
-// 0: only while a window is propagated (reloaded from / stored to shared memory around every update)
-#ifndef FBUS_TL_PERSIST
-#define FBUS_TL_PERSIST 0  // measured: 7.47e9 vs 7.96e9 -- block (90 regs) + Z columns (108) + Lc (42) do not fit, the update spills
-#endif
 // 1 (default): the 128-filter CTAs keep the covariance in TENSOR MEMORY (one TMEM lane per filter, fbus_tmem.cuh) instead
 // of shared memory; the 32-filter CTAs of small batches (several per SM) always use shared memory
 #ifndef FBUS_TMEM
 #define FBUS_TMEM 1
 #endif
-// 1 (tensor-memory kernel only): the nominal warp sweeps the bottom-right blocks of the update (stage 3) while the
-// covariance warp sweeps the cross blocks (stage 2b); both read the same stashed Z columns
-#ifndef FBUS_OFFLOAD3
-#define FBUS_OFFLOAD3 0  // measured: 8.45e9 vs 8.62e9 filter-steps/s (one more hand-over barrier per update, 270 FMA moved)
-#endif
-// Tensor-memory kernel: depth of the coefficient ring between the nominal and the covariance warp.  0: two slots handed over
-// with one pair barrier per sample (lock-step); D > 0: D slots with mbarrier full/empty pairs, the nominal warp may run up
-// to D samples ahead and neither warp waits for the other sample by sample
-#ifndef FBUS_RING_DEPTH
-#define FBUS_RING_DEPTH 0  // measured: 8.62e9 (lock-step) vs 8.25e9 (D = 2), 8.32e9 (D = 3), 8.25e9 (D = 6) filter-steps/s
-#endif
-// 1: both warps of a filter group share the update: the covariance warp computes the gain factors and applies the first
-//    half-rank factor Za, the nominal warp applies the second (Zb) and injects the error state; 0: covariance warp alone
-#ifndef FBUS_COOP_UPDATE
-#define FBUS_COOP_UPDATE 0  // measured: 6.4e9 vs 7.5e9 filter-steps/s -- the sweeps are shared-memory-bandwidth bound, two warps do not help
-#endif
 // 1: the per-sample ring barrier is private to a warp pair (64 threads); the CTA re-aligns once per frame
 #ifndef FBUS_PAIR_BARRIER
 #define FBUS_PAIR_BARRIER 1
-#endif
-// 1: additionally keep the bottom-right 9x9 block (bias / gravity covariance) in the covariance warp's registers
-#ifndef FBUS_BR_REGS_SPLIT
-#define FBUS_BR_REGS_SPLIT 0
 #endif
 
 namespace fbus {
@@ -77,28 +56,9 @@ __device__ __forceinline__ void step_bar(int pair) {
 #endif
 }
 
-constexpr int RING_REC = 23;  // doubles per ring record in the mbarrier ring: A 9, B 9, w dt 3, dt, valid
-__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mb_arrive(uint64_t* bar) {  // release: everything this thread did before is visible to the waiter
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {  // acquire; the warp reconverges afterwards
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    } while (!ok);
-    __syncwarp();
-}
-
 struct SplitShared {
     uint32_t lo_hi[2][8];   // per nominal warp: min first / max end of the candidate IMU range
     int32_t any_upd[8];     // per nominal warp: some filter requests an update
-    uint64_t mb_full[4][8];   // mbarrier ring (tensor-memory kernel): record written / record consumed, per warp pair and slot
-    uint64_t mb_empty[4][8];
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -113,10 +73,6 @@ struct SplitShared {
 // The next frame's (a) doubles as "results consumed".
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int RQ_EXTRA = 44;  // the request needs 23 doubles: 22 in the free ring slot + this one
-// first double of the update's results (19 doubles: p, q, dv, db_a, db_g, dg).  The tensor-memory kernel has shared memory to
-// spare and keeps them clear of the stash (0..53), which the partner warp may still be reading (FBUS_OFFLOAD3)
-constexpr int XCH_TM = 76;
-template <bool TM> struct ResArea { static constexpr int first = TM ? 56 : 23; };
 
 // top-left 9x9 <-> registers, block-wise (six 3x3 blocks) for the tensor-memory accessor
 template <bool TM, class CV>
@@ -157,19 +113,6 @@ __device__ __forceinline__ void tl_store_any(const CV P, const double* TL) {
     }
 }
 
-// hand-over inside the update (see update_onepass_blk): stores of this warp complete, pair barrier, tensor-memory fences
-template <int NT>
-struct PairSync {
-    static constexpr bool kOffload3 = true;
-    int wq;
-    __device__ __forceinline__ void operator()() const {
-        tm_wait_st();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        step_bar<NT>(wq);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-};
-
 template <int NT>
 __device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) {
 #if FBUS_PAIR_BARRIER
@@ -190,10 +133,6 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                                          int fl, size_t b, bool live, uint32_t tm_base) {
     constexpr int NT = 2 * BSF, NW = BSF / 32;
     constexpr int NPS = TM ? 0 : NPK;  // doubles of P per filter in shared memory
-    constexpr int RES0 = ResArea<TM>::first;
-    constexpr bool RING = TM && (FBUS_RING_DEPTH > 0);
-    const double* const RG = smem + (size_t)XCH_TM * BSF + fl;  // mbarrier ring (RING only)
-    uint32_t cnt = 0;                                           // samples consumed since the launch started
     const size_t B = prm.B;
     using CV = typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type;
     CV P;
@@ -217,14 +156,6 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
     } else {
         for (int e = 0; e < NPK; ++e) smem[e * BSF + fl] = prm.P[(size_t)e * B + b];
     }
-#if FBUS_TL_REGS && FBUS_TL_PERSIST
-#if FBUS_COOP_UPDATE
-#error "FBUS_TL_PERSIST needs FBUS_COOP_UPDATE=0 (the nominal warp cannot see the register-resident block)"
-#endif
-    double TL[NTL];  // top-left 9x9 of P lives in registers for the whole launch
-    tl_load_any<TM>(P, TL);
-    const CovX<BSF, true> PT{smem + fl, TL};
-#endif
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
         cta_bar<NT>();  // (a) the nominal warps have posted their IMU ranges
         uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
@@ -232,109 +163,41 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
         int fs = 0;  // ring slot that carries the update request
         if (lo < hi) {
-            if (!RING) fs = (int)((hi - lo) & 1u);
-#if FBUS_TL_REGS && !FBUS_TL_PERSIST
+            fs = (int)((hi - lo) & 1u);
+#if FBUS_TL_REGS
             double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
             tl_load_any<TM>(P, TL);
 #endif
-#if FBUS_BR_REGS_SPLIT
-            double BR[NBR];
-            br_load<BSF>(P, BR);
-#endif
             for (uint32_t i = lo; i < hi; ++i) {
-                const double* rec;
-                int valid;
-                if constexpr (RING) {
-                    const uint32_t slot = cnt % (uint32_t)FBUS_RING_DEPTH, ph = (cnt / (uint32_t)FBUS_RING_DEPTH) & 1u;
-                    ++cnt;
-                    mb_wait(&sh.mb_full[wq][slot], ph);  // record (i) is complete
-                    rec = RG + (size_t)slot * RING_REC * BSF;
-                    valid = rec[(size_t)22 * BSF] != 0.0;
-                } else {
-                    step_bar<NT>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
-                    const int slot = (int)((i - lo) & 1u);
-                    valid = sflag[slot][fl];
-                    rec = X + (size_t)slot * 22 * BSF;
-                }
+                step_bar<NT>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
+                const int slot = (int)((i - lo) & 1u);
+                const int valid = sflag[slot][fl];
                 // tensor-memory accesses are warp-wide: a warp with any valid lane runs the step on all lanes, the
                 // others with F = I and no process noise (every entry of P keeps its value)
-                const bool run = TM ? (__any_sync(0xffffffffu, valid) != 0) : (valid != 0);
-                double A[9], Bm[9], u0 = 0.0, u1 = 0.0, u2 = 0.0, dt = 0.0;
-                if (run) {
+                if (TM ? __any_sync(0xffffffffu, valid) : valid) {
+                    const double* rec = X + (size_t)slot * 22 * BSF;
+                    double A[9], Bm[9];
 #pragma unroll
                     for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * BSF]; Bm[e] = rec[(size_t)(9 + e) * BSF]; }
-                    u0 = rec[(size_t)18 * BSF]; u1 = rec[(size_t)19 * BSF]; u2 = rec[(size_t)20 * BSF];
-                    dt = rec[(size_t)21 * BSF];
-                }
-                if constexpr (RING) mb_arrive(&sh.mb_empty[wq][(cnt - 1u) % (uint32_t)FBUS_RING_DEPTH]);  // record consumed (the loads above are ordered before this release)
-                if (run) {
+                    const double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
+                    const double dt = rec[(size_t)21 * BSF];
                     double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
                     if (TM && !valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;  // the record of an invalid sample is all zeros
                     P.fence_st();  // the previous step's stores
-#if FBUS_TL_REGS && FBUS_BR_REGS_SPLIT
-                    propagate_cov_core<BSF, true, true>(P, A, Bm, u0, u1, u2, dt, Qv, BR, TL);
-#elif FBUS_TL_REGS
+#if FBUS_TL_REGS
                     propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL);
 #else
                     propagate_cov_core<BSF>(P, A, Bm, u0, u1, u2, dt, Qv);
 #endif
                 }
             }
-#if FBUS_TL_REGS && !FBUS_TL_PERSIST
+#if FBUS_TL_REGS
             tl_store_any<TM>(P, TL);
-#endif
-#if FBUS_BR_REGS_SPLIT
-            br_store_diag<BSF>(P, BR);
 #endif
         }
         step_bar<NT>(wq);  // (r) update request posted (normally long before this warp gets here)
         if (pair_any<NT>(sh, wq)) {
             const int req = sflag[2][fl];
-#if FBUS_COOP_UPDATE
-            // Cooperative update.  This warp computes the gain factors from the posted measurement and pose, publishes
-            // the part of Lc the nominal warp needs (rows 3..5) and y[3..5], then both warps take one half-rank factor
-            // each from the OLD covariance (Za here, Zb there) and apply it to disjoint row sets, swapping once.
-            double Z[54];
-            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-            double Cm[21];
-            if (req) {
-                const double* rq = X + (size_t)fs * 22 * BSF;
-                Nominal t;
-                double yP[3], yQ[4], y[6];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) yP[c] = rq[(size_t)c * BSF];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { yQ[c] = rq[(size_t)(3 + c) * BSF]; t.q[c] = rq[(size_t)(7 + c) * BSF]; }
-#pragma unroll
-                for (int c = 0; c < 9; ++c) t.R[c] = rq[(size_t)(11 + c) * BSF];
-                t.p[0] = rq[(size_t)20 * BSF]; t.p[1] = rq[(size_t)21 * BSF]; t.p[2] = X[(size_t)RQ_EXTRA * BSF];
-                const MarkerConst mkc = prm.tab->mk[req - 1];  // 3 KB table, L2-resident
-                // X = L^-1 Hs (42 doubles) is parked in the exchange area: the request is already in registers
-                update_prologue<BSF, BSF, JOSEPH>(P, t, k, mkc, yP, yQ, Cm, y, X);
-                X[(size_t)0 * BSF] = Cm[9];  X[(size_t)1 * BSF] = Cm[13]; X[(size_t)2 * BSF] = Cm[14];   // C(3,3) C(4,3) C(4,4)
-                X[(size_t)3 * BSF] = Cm[18]; X[(size_t)4 * BSF] = Cm[19]; X[(size_t)5 * BSF] = Cm[20];   // C(5,3) C(5,4) C(5,5)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) X[(size_t)(6 + c) * BSF] = y[3 + c];
-                y0 = y[0]; y1 = y[1]; y2 = y[2];
-            } else {
-#pragma unroll
-                for (int c = 0; c < 21; ++c) Cm[c] = 0.0;
-            }
-            // from here on no divergent regions: lanes without a request run the same code with their stores off
-            step_bar<NT>(wq);  // (u1) gain factors published
-            update_Za<BSF>(P, Cm, Z);
-            step_bar<NT>(wq);  // (u2) both factors taken from the old covariance
-            update_sweep<BSF, 0, 5>(P, Z, req != 0);
-            step_bar<NT>(wq);  // (u3) swap row sets
-            update_sweep<BSF, 5, 18>(P, Z, req != 0);
-            {
-                double dx[18];
-                update_dx<false>(Z, y0, y1, y2, dx);
-#pragma unroll
-                for (int c = 0; c < 18; ++c) X[(size_t)(22 + c) * BSF] = dx[c];
-            }
-            step_bar<NT>(wq);  // (d) covariance updated, first half of dx posted
-#else
             if (TM ? true : (req != 0)) {  // tensor memory: all lanes, the ones without a request with zero gain
                 const double* rq = X + (size_t)fs * 22 * BSF;
                 Nominal t;
@@ -351,34 +214,23 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                 t.t = 0.0;
                 const MarkerConst mkc = prm.tab->mk[(req > 0 ? req : 1) - 1];
                 P.fence_st();
-#if FBUS_TL_REGS && FBUS_TL_PERSIST
-                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(PT, t, k, mkc, yP, yQ, X, req != 0);
-#else
-                if constexpr (TM && FBUS_OFFLOAD3) measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X, req != 0, PairSync<NT>{wq});
-                else measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X, req != 0);
-#endif
+                measurement_update<BSF, JOSEPH ? 1 : 0, BSF>(P, t, k, mkc, yP, yQ, X, req != 0);
                 P.fence_st();
                 // hand back: corrected p, q and the increments of v, b_a, b_g, g
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    X[(size_t)(RES0 + 0 + c) * BSF] = t.p[c];
-                    X[(size_t)(RES0 + 7 + c) * BSF] = t.v[c];
-                    X[(size_t)(RES0 + 10 + c) * BSF] = t.ba[c];
-                    X[(size_t)(RES0 + 13 + c) * BSF] = t.bg[c];
-                    X[(size_t)(RES0 + 16 + c) * BSF] = t.g[c];
+                    X[(size_t)(23 + c) * BSF] = t.p[c];
+                    X[(size_t)(30 + c) * BSF] = t.v[c];
+                    X[(size_t)(33 + c) * BSF] = t.ba[c];
+                    X[(size_t)(36 + c) * BSF] = t.bg[c];
+                    X[(size_t)(39 + c) * BSF] = t.g[c];
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) X[(size_t)(RES0 + 3 + c) * BSF] = t.q[c];
+                for (int c = 0; c < 4; ++c) X[(size_t)(26 + c) * BSF] = t.q[c];
             }
-            if constexpr (TM && FBUS_OFFLOAD3) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            step_bar<NT>(wq);  // (d) results posted (and the partner's bottom-right sweep is complete)
-            if constexpr (TM && FBUS_OFFLOAD3) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#endif
+            step_bar<NT>(wq);  // (d) results posted
         }
     }
-#if FBUS_TL_REGS && FBUS_TL_PERSIST
-    tl_store_any<TM>(P, TL);
-#endif
     if constexpr (TM) {
         P.fence_st();
         FBUS_UNROLL
@@ -541,14 +393,10 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
 
 template <int BSF, bool TM>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
-                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live, uint32_t tm_base) {
+                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
     constexpr int NT = 2 * BSF, NW = BSF / 32;
     const size_t B = prm.B;
     double* const X = smem + (size_t)(TM ? 0 : NPK) * BSF + fl;
-    constexpr int RES0 = ResArea<TM>::first;
-    constexpr bool RING = TM && (FBUS_RING_DEPTH > 0);
-    double* const RG = smem + (size_t)XCH_TM * BSF + fl;  // mbarrier ring (RING only)
-    uint32_t cnt = 0;                                     // samples produced since the launch started
     const bool fused = (prm.mode & M_FUSED) != 0;
     const int wq = fl >> 5;  // nominal warp index
     Nominal n;
@@ -613,7 +461,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
         int fs = 0;
         if (lo < hi) {
-            if (!RING) fs = (int)((hi - lo) & 1u);
+            fs = (int)((hi - lo) & 1u);
             const double start = n.t;
             bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
             uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
@@ -631,15 +479,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                     for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)(i + 1) * 6 + c) * B + b];
                 }
-                int slot = (int)((i - lo) & 1u);
-                double* recp = X + (size_t)slot * 22 * BSF;
-                if constexpr (RING) {
-                    slot = (int)(cnt % (uint32_t)FBUS_RING_DEPTH);
-                    const uint32_t ph = (cnt / (uint32_t)FBUS_RING_DEPTH) & 1u;
-                    ++cnt;
-                    mb_wait(&sh.mb_empty[wq][slot], ph ^ 1u);  // the covariance warp has consumed this slot's previous record
-                    recp = RG + (size_t)slot * RING_REC * BSF;
-                }
+                const int slot = (int)((i - lo) & 1u);
                 int valid = 0;
                 if (open && i >= p_first && i < p_end) {
                     if (ti < start) {
@@ -654,7 +494,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                         for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
                         cov_coeffs(n.R, av, wv, dt, A, Bm, u);  // F1 uses the CARRIED rotmatI2G (A.3-2,3)
-                        double* rec = recp;
+                        double* rec = X + (size_t)slot * 22 * BSF;
 #pragma unroll
                         for (int e = 0; e < 9; ++e) { rec[(size_t)e * BSF] = A[e]; rec[(size_t)(9 + e) * BSF] = Bm[e]; }
                         rec[(size_t)18 * BSF] = u[0]; rec[(size_t)19 * BSF] = u[1]; rec[(size_t)20 * BSF] = u[2];
@@ -664,16 +504,12 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                     }
                 }
                 if (TM && !valid) {  // tensor-memory mode: the covariance warp runs every lane, invalid ones with F = I
+                    double* rec = X + (size_t)slot * 22 * BSF;
 #pragma unroll
-                    for (int e = 0; e < 22; ++e) recp[(size_t)e * BSF] = 0.0;
+                    for (int e = 0; e < 22; ++e) rec[(size_t)e * BSF] = 0.0;
                 }
-                if constexpr (RING) {
-                    recp[(size_t)22 * BSF] = valid ? 1.0 : 0.0;
-                    mb_arrive(&sh.mb_full[wq][slot]);  // publish record (i)
-                } else {
-                    sflag[slot][fl] = valid;
-                    step_bar<NT>(wq);  // publish record (i); also: the covariance warp has finished sample i-1
-                }
+                sflag[slot][fl] = valid;
+                step_bar<NT>(wq);  // publish record (i); also: the covariance warp has finished sample i-1
             }
             if (fused && do_prop) cursor = consumed;
         }
@@ -711,61 +547,19 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             plan_frame<BSF>(prm, k, w + 1, b, live, cursor, n.t, inited, prev_id, status, nx);
         }
         if (any) {
-#if FBUS_COOP_UPDATE
-            const Cov<BSF> P{smem + fl};
-            double Z[54];
-            double y3 = 0.0, y4 = 0.0, y5 = 0.0;
-            step_bar<NT>(wq);  // (u1)
-            {   // no divergent regions below (see cov_role): lanes without a request keep their stores / state changes off
-                const double c33 = X[(size_t)0 * BSF], c43 = X[(size_t)1 * BSF], c44 = X[(size_t)2 * BSF];
-                const double c53 = X[(size_t)3 * BSF], c54 = X[(size_t)4 * BSF], c55 = X[(size_t)5 * BSF];
-                y3 = X[(size_t)6 * BSF]; y4 = X[(size_t)7 * BSF]; y5 = X[(size_t)8 * BSF];
-                update_Zb6<BSF>(P, c33, c43, c44, c53, c54, c55, Z);
-            }
-            step_bar<NT>(wq);  // (u2)
-            update_sweep<BSF, 5, 18>(P, Z, req != 0);
-            step_bar<NT>(wq);  // (u3)
-            update_sweep<BSF, 0, 5>(P, Z, req != 0);
-            step_bar<NT>(wq);  // (d)
-            {
-                double dx[18];
-#pragma unroll
-                for (int c = 0; c < 18; ++c) dx[c] = X[(size_t)(22 + c) * BSF];
-                update_dx<true>(Z, y3, y4, y5, dx);
-                Nominal m = n;
-                inject_error_state(m, dx);  // rotmatI2G deliberately NOT refreshed (A.3-2)
-                if (req) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) { n.p[c] = m.p[c]; n.v[c] = m.v[c]; n.ba[c] = m.ba[c]; n.bg[c] = m.bg[c]; n.g[c] = m.g[c]; }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) n.q[c] = m.q[c];
-                }
-            }
-#else
-            if constexpr (TM && FBUS_OFFLOAD3) {
-                // stage 3 of the update on this warp: the Z columns 9..17 are in the exchange area after the hand-over
-                CovTM<false> PN;
-                PN.base = tm_base + ((uint32_t)((threadIdx.x >> 5) & 3) << 21);
-                step_bar<NT>(wq);  // hand-over (PairSync in the covariance warp)
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                update_bottom_right_blk<BSF>(PN, X);
-                tm_wait_st();
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            }
             step_bar<NT>(wq);  // (d) results posted
             if (req) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    n.p[c] = X[(size_t)(RES0 + 0 + c) * BSF];
-                    n.v[c] += X[(size_t)(RES0 + 7 + c) * BSF];
-                    n.ba[c] += X[(size_t)(RES0 + 10 + c) * BSF];
-                    n.bg[c] += X[(size_t)(RES0 + 13 + c) * BSF];
-                    n.g[c] += X[(size_t)(RES0 + 16 + c) * BSF];
+                    n.p[c] = X[(size_t)(23 + c) * BSF];
+                    n.v[c] += X[(size_t)(30 + c) * BSF];
+                    n.ba[c] += X[(size_t)(33 + c) * BSF];
+                    n.bg[c] += X[(size_t)(36 + c) * BSF];
+                    n.g[c] += X[(size_t)(39 + c) * BSF];
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(RES0 + 3 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
+                for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(26 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
             }
-#endif
         }
         // ---- trace row: the data/fusion.txt record (filter.cpp:241-246) -------------------------
         if (prm.trace && live) {
@@ -842,22 +636,14 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
     const size_t b0 = (size_t)blockIdx.x * BSF + fl;
     const bool live = b0 < prm.B;
     const size_t b = live ? b0 : prm.B - 1;  // threads past the batch mirror the last filter and never store
-    constexpr bool TM = (FBUS_TMEM != 0) && BSF == 128 && (FBUS_COOP_UPDATE == 0);
+    constexpr bool TM = (FBUS_TMEM != 0) && BSF == 128;
     uint32_t tm_base = 0;
-    if constexpr (TM && FBUS_RING_DEPTH > 0) {
-        static_assert(FBUS_RING_DEPTH <= 8, "mbarrier ring: at most 8 slots");
-        if (threadIdx.x < 4 * FBUS_RING_DEPTH) {
-            mb_init(&sh.mb_full[threadIdx.x / FBUS_RING_DEPTH][threadIdx.x % FBUS_RING_DEPTH], 32);
-            mb_init(&sh.mb_empty[threadIdx.x / FBUS_RING_DEPTH][threadIdx.x % FBUS_RING_DEPTH], 32);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     if constexpr (TM) {
         __shared__ uint32_t tm_slot;
         tm_base = tm_alloc_cta(&tm_slot);
     }
     if (is_cov) cov_role<BSF, JOSEPH, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
-    else nominal_role<BSF, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
+    else nominal_role<BSF, TM>(prm, k, smem, sh, sflag, fl, b, live);
     if constexpr (TM) tm_free_cta(tm_base);
 }
 

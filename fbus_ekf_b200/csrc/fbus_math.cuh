@@ -1126,9 +1126,6 @@ FBUS_HD void measurement_update_coop(const Cov<S> P, Nominal& n, const DevConsts
 #ifndef FBUS_UPDATE_ONEPASS
 #define FBUS_UPDATE_ONEPASS 1
 #endif
-#ifndef FBUS_PROLOGUE_PARK
-#define FBUS_PROLOGUE_PARK 1
-#endif
 template <int S, int XS, class CV = Cov<S>>
 FBUS_HD void update_onepass(const CV P, Nominal& n, const double* Cm, const double* y, double* stash) {
 #define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
@@ -1244,39 +1241,8 @@ FBUS_HD void update_onepass(const CV P, Nominal& n, const double* Cm, const doub
 //   2a. Z columns 9..17 from the blocks (0,k), (2,k), k = 3..5 -> stash (Lc is dead afterwards);
 //   2b. sweep of the nine cross blocks (Z columns of block column k re-read from the stash);
 //   3.  sweep of the six bottom-right blocks from the stashed columns.
-// Hand-over point after stage 2a (all Z columns 9..17 are in the stash, the bottom-right blocks still hold their OLD
-// values): `sync()` lets a partner warp run stage 3 (update_bottom_right_blk) while this one does stage 2b.
-struct NoSync {
-    static constexpr bool kOffload3 = false;
-    FBUS_HD void operator()() const {}
-};
-template <int XS, class CV>
-FBUS_HD void update_bottom_right_blk(const CV P, const double* stash) {
-    double Z2[54];  // Z[k][c], c = 9..17, at Z2[(c - 9) * 6 + k]
-    FBUS_UNROLL
-    for (int e = 0; e < 54; ++e) Z2[e] = stash[(size_t)e * XS];
-    FBUS_UNROLL
-    for (int bj = 3; bj < 6; ++bj)
-        FBUS_UNROLL
-        for (int bi = 3; bi <= bj; ++bi) {
-            double T[9];
-            P.ldblk_nw(bi, bj, T);
-            P.wait_ld();
-            FBUS_UNROLL
-            for (int r = 0; r < 3; ++r)
-                FBUS_UNROLL
-                for (int c = (bi == bj ? r : 0); c < 3; ++c) {
-                    double v = T[r * 3 + c];
-                    FBUS_UNROLL
-                    for (int kz = 0; kz < 6; ++kz) v -= Z2[(3 * (bi - 3) + r) * 6 + kz] * Z2[(3 * (bj - 3) + c) * 6 + kz];
-                    T[r * 3 + c] = v;
-                }
-            if (bi == bj) P.stdiag(bi, T);
-            else P.stblk(bi, bj, T);
-        }
-}
-template <int S, int XS, class CV, class SyncF = NoSync>
-FBUS_HD void update_onepass_blk(const CV P, Nominal& n, const double* Cm, const double* y, double* stash, SyncF sync = SyncF()) {
+template <int S, int XS, class CV>
+FBUS_HD void update_onepass_blk(const CV P, Nominal& n, const double* Cm, const double* y, double* stash) {
 #define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
     double dth[3] = {0.0, 0.0, 0.0};
     double Z1[54];  // Z[k][c], c = 0..8, at Z1[k * 9 + c]
@@ -1357,7 +1323,6 @@ FBUS_HD void update_onepass_blk(const CV P, Nominal& n, const double* Cm, const 
     }
 #undef FBUS_C
     FBUS_FENCE;
-    sync();
     // ---- 2b: cross blocks -----------------------------------------------------------------------------
     FBUS_UNROLL
     for (int k = 3; k < 6; ++k) {
@@ -1382,8 +1347,31 @@ FBUS_HD void update_onepass_blk(const CV P, Nominal& n, const double* Cm, const 
         }
     }
     FBUS_FENCE;
-    // ---- 3: bottom-right blocks (here, or by the partner warp) ---------------------------------------------
-    if (!SyncF::kOffload3) update_bottom_right_blk<XS>(P, stash);
+    // ---- 3: bottom-right blocks -----------------------------------------------------------------------
+    {
+        double Z2[54];  // Z[k][c], c = 9..17, at Z2[(c - 9) * 6 + k]
+        FBUS_UNROLL
+        for (int e = 0; e < 54; ++e) Z2[e] = stash[(size_t)e * XS];
+        FBUS_UNROLL
+        for (int bj = 3; bj < 6; ++bj)
+            FBUS_UNROLL
+            for (int bi = 3; bi <= bj; ++bi) {
+                double T[9];
+                P.ldblk_nw(bi, bj, T);
+                P.wait_ld();
+                FBUS_UNROLL
+                for (int r = 0; r < 3; ++r)
+                    FBUS_UNROLL
+                    for (int c = (bi == bj ? r : 0); c < 3; ++c) {
+                        double v = T[r * 3 + c];
+                        FBUS_UNROLL
+                        for (int kz = 0; kz < 6; ++kz) v -= Z2[(3 * (bi - 3) + r) * 6 + kz] * Z2[(3 * (bj - 3) + c) * 6 + kz];
+                        T[r * 3 + c] = v;
+                    }
+                if (bi == bj) P.stdiag(bi, T);
+                else P.stblk(bi, bj, T);
+            }
+    }
     {   // VectorToQuaterniond (matrix_math.hpp:90-99): v/|v| * sin(|v|/2); NaN at exactly zero, as the reference
         const double v2 = dth[0] * dth[0] + dth[1] * dth[1] + dth[2] * dth[2];
         const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
@@ -1401,16 +1389,12 @@ FBUS_HD void update_onepass_blk(const CV P, Nominal& n, const double* Cm, const 
 }
 
 // stash: 54 doubles of scratch with stride XS (nullptr: a private array)
-template <int S, int JMODE = -1, int XS = 1, class CV = Cov<S>, class SyncF = NoSync>
+template <int S, int JMODE = -1, int XS = 1, class CV = Cov<S>>
 FBUS_HD void measurement_update(const CV P, Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
-                                const double* yQ, double* stash = nullptr, bool on = true, SyncF sync = SyncF()) {
+                                const double* yQ, double* stash = nullptr, bool on = true) {
     double Cm[21], y[6];
-    if (CV::kTLR && XS > 1 && FBUS_PROLOGUE_PARK) {
-        // the register-resident top-left block leaves no room for X = L^-1 Hs (42 doubles): park it in the stash area
-        if (JMODE == 1 || (JMODE < 0 && (k.flags & 1))) update_prologue<S, XS, true>(P, n, k, mk, yP, yQ, Cm, y, stash);
-        else update_prologue<S, XS, false>(P, n, k, mk, yP, yQ, Cm, y, stash);
-    } else {
-        double xloc[42];  // single-thread form: X = L^-1 Hs stays private
+    {
+        double xloc[42];  // X = L^-1 Hs stays private
         if (JMODE == 1 || (JMODE < 0 && (k.flags & 1))) update_prologue<S, 1, true>(P, n, k, mk, yP, yQ, Cm, y, xloc);
         else update_prologue<S, 1, false>(P, n, k, mk, yP, yQ, Cm, y, xloc);
     }
@@ -1422,7 +1406,7 @@ FBUS_HD void measurement_update(const CV P, Nominal& n, const DevConsts& k, cons
     }
 #if FBUS_UPDATE_ONEPASS
     if (CV::kBlocked) {
-        update_onepass_blk<S, XS>(P, n, Cm, y, stash, sync);
+        update_onepass_blk<S, XS>(P, n, Cm, y, stash);
     } else if (stash != nullptr) {
         update_onepass<S, XS>(P, n, Cm, y, stash);
     } else {
