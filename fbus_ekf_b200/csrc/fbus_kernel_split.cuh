@@ -36,6 +36,11 @@
 #ifndef FBUS_PAIR_BARRIER
 #define FBUS_PAIR_BARRIER 1
 #endif
+// 1: one CTA-wide barrier per frame (all warps loop over the CTA's common IMU range and re-align on the same code);
+// 0: warp pairs are fully independent (needs FBUS_PAIR_BARRIER), each loops over its own range
+#ifndef FBUS_FRAME_CTA_BARRIER
+#define FBUS_FRAME_CTA_BARRIER 1
+#endif
 
 namespace fbus {
 
@@ -157,10 +162,15 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
         for (int e = 0; e < NPK; ++e) smem[e * BSF + fl] = prm.P[(size_t)e * B + b];
     }
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
+#if FBUS_FRAME_CTA_BARRIER || !FBUS_PAIR_BARRIER
         cta_bar<NT>();  // (a) the nominal warps have posted their IMU ranges
         uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
 #pragma unroll
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
+#else
+        step_bar<NT>(wq);  // (a) this pair's nominal warp has posted its IMU range
+        const uint32_t lo = sh.lo_hi[0][wq], hi = sh.lo_hi[1][wq];
+#endif
         int fs = 0;  // ring slot that carries the update request
         if (lo < hi) {
             fs = (int)((hi - lo) & 1u);
@@ -455,10 +465,15 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             const uint32_t vhi = __reduce_max_sync(0xffffffffu, do_prop ? p_end : 0u);
             if ((fl & 31) == 0) { sh.lo_hi[0][wq] = vlo; sh.lo_hi[1][wq] = vhi; }
         }
+#if FBUS_FRAME_CTA_BARRIER || !FBUS_PAIR_BARRIER
         cta_bar<NT>();  // (a)
         uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
 #pragma unroll
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
+#else
+        step_bar<NT>(wq);  // (a)
+        const uint32_t lo = sh.lo_hi[0][wq], hi = sh.lo_hi[1][wq];
+#endif
         int fs = 0;
         if (lo < hi) {
             fs = (int)((hi - lo) & 1u);
