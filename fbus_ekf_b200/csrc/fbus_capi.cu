@@ -240,7 +240,10 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     {
         cudaDeviceProp prop;
         if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
-        h->small_batch = WIN_BS > 32 && (batch + WIN_BS - 1) / WIN_BS < (size_t)prop.multiProcessorCount;
+        // 32-filter CTAs (covariance in shared memory) only while at most two of them land on an SM: measured with
+        // profiles/probes/batch_sweep.py they beat the 128-filter tensor-memory CTAs by ~5 % up to 8 192 filters and fall
+        // to ~3e9 filter-steps/s beyond (three small CTAs per SM), where the large CTAs keep scaling with the SMs they fill
+        h->small_batch = WIN_BS > 32 && (batch + 31) / 32 <= 2 * (size_t)prop.multiProcessorCount;
         if (const char* sb = getenv("FBUS_SMALL_BATCH")) h->small_batch = atoi(sb) != 0;
         const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
         e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
