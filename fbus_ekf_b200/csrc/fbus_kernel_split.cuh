@@ -141,7 +141,11 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
     const size_t B = prm.B;
     using CV = typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type;
     CV P;
-    if constexpr (TM) P.base = tm_base + ((uint32_t)((threadIdx.x >> 5) & 3) << 21);  // lane 32*(warp%4) in bits 31..16
+    if constexpr (TM) {
+        // lane 32*(warp%4) in bits 31..16; broadcast from lane 0 so that the compiler knows the address is warp-uniform and
+        // keeps it (and the block offsets added to it) in uniform registers instead of converting for every tcgen05 access
+        P.base = __shfl_sync(0xffffffffu, tm_base + ((uint32_t)((threadIdx.x >> 5) & 3) << 21), 0);
+    }
     else P.s = smem + fl;
     double* const X = smem + (size_t)NPS * BSF + fl;
     const int wq = fl >> 5;
