@@ -153,6 +153,7 @@ def lib() -> C.CDLL:
         "fbus_set_state": (C.c_int, [H, C.POINTER(StateSoa)]),
         "fbus_clear_status": (C.c_int, [H]),
         "fbus_stats": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_int32, c_double_p, C.c_void_p]),
+        "fbus_stats_combine": (C.c_int, [c_double_p, C.c_size_t, c_double_p]),
         "fbus_synth_streams": (C.c_int, [H, C.POINTER(SynthSpec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "fbus_quat_from_rotmat": (None, [c_double_p, c_double_p]),
         "fbus_measure_fp64_peak": (C.c_int, [H, c_double_p]),
@@ -169,7 +170,7 @@ EXPORTED_SYMBOLS = (
     "fbus_config_default", "fbus_create", "fbus_destroy", "fbus_last_error", "fbus_abi_version", "fbus_synchronize",
     "fbus_batch", "fbus_stream", "fbus_init_gravity_gyrobias", "fbus_init_position_quaternion", "fbus_propagate",
     "fbus_reset_state", "fbus_update", "fbus_step_windows", "fbus_refract_solve", "fbus_inair_solve", "fbus_undistort_fisheye", "fbus_solve_to_detections", "fbus_refract_solve_gn", "fbus_marker_pose", "fbus_get_state",
-    "fbus_set_state", "fbus_clear_status", "fbus_stats", "fbus_synth_streams", "fbus_quat_from_rotmat",
+    "fbus_set_state", "fbus_clear_status", "fbus_stats", "fbus_stats_combine", "fbus_synth_streams", "fbus_quat_from_rotmat",
     "fbus_measure_fp64_peak")
 
 

@@ -651,6 +651,20 @@ int fbus_clear_status(fbus_handle* h) {
     return FBUS_OK;
 }
 
+int fbus_stats_combine(const double* parts, size_t n_parts, double* out) {
+    if (!parts || !out || n_parts == 0) {
+        g_last_error = "fbus_stats_combine: bad argument";
+        return FBUS_E_BADARG;
+    }
+    for (int i = 0; i < FBUS_NSTATS; ++i) out[i] = 0.0;
+    for (size_t p = 0; p < n_parts; ++p) {
+        const double* v = parts + p * FBUS_NSTATS;
+        for (int i = 0; i < 5; ++i) out[i] += v[i];
+        out[5] = (p == 0 || v[5] > out[5]) ? v[5] : out[5];
+    }
+    return FBUS_OK;
+}
+
 int fbus_stats(fbus_handle* h, const double* truth_p, const double* truth_q, int32_t mem, double* out_host, double* out_dev) {
     if (!h || !truth_p || !truth_q) return fail(h, FBUS_E_BADARG, "fbus_stats: bad argument");
     CUDA_TRY(h, cudaSetDevice(h->device));

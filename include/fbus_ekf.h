@@ -277,6 +277,10 @@ int fbus_clear_status(fbus_handle* h);
    without a host round trip; out_host (optional) is HOST. */
 int fbus_stats(fbus_handle* h, const double* truth_p, const double* truth_q, int32_t mem,
                double* out_host, double* out_dev);
+/* Combine rule of the per-shard vectors (what the multi-GPU driver applies with its all-reduce; here for callers
+   that gather the vectors themselves -- several handles in one process, MPI): parts is [n_parts][FBUS_NSTATS] on the HOST;
+   out[0..4] = sums over the parts, out[5] = maximum, out[6..7] = 0.  Pure host code, needs no handle. */
+int fbus_stats_combine(const double* parts, size_t n_parts, double* out);
 
 /* ---- synthetic Monte-Carlo streams (benchmark workload generator) ---- */
 

@@ -82,3 +82,17 @@ def test_two_ranks_equal_one(built, tmp_path):
     assert np.array_equal(p, state["p"])
     summ = shard.summarize_stats(s0)
     assert summ["filters_finite"] == B and summ["rmse_pos_m"] < 0.05
+
+
+def test_stats_combine_c_abi(built):
+    """the host-side combine rule exported by the C ABI equals shard.combine_stats' rule (sums for [0..4], max for [5])"""
+    import ctypes as C
+    from fbus_ekf_b200 import capi
+    rng = np.random.default_rng(5)
+    parts = np.ascontiguousarray(rng.uniform(0.0, 10.0, (3, capi.FBUS_NSTATS)))
+    out = np.full(capi.FBUS_NSTATS, -1.0)
+    rc = capi.lib().fbus_stats_combine(capi.dptr(parts), 3, capi.dptr(out))
+    assert rc == 0
+    assert np.allclose(out[:5], parts[:, :5].sum(axis=0), rtol=0, atol=1e-12)
+    assert out[5] == parts[:, 5].max() and out[6] == 0.0 and out[7] == 0.0
+    assert capi.lib().fbus_stats_combine(None, 0, capi.dptr(out)) != 0
