@@ -386,7 +386,10 @@ __global__ void ctor_kernel(double* nom, double* P, int32_t* prev_id, int32_t* i
 }
 
 // K3+K4: one thread per marker.  corners [16][n] float32 -> pose [7][n], corners3d [12][n], valid [n]
-__global__ void __launch_bounds__(128) refract_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ corners, size_t n,
+#ifndef FBUS_REFRACT_MINB
+#define FBUS_REFRACT_MINB 6  // measured: 9.72e9 solves/s with 6 CTAs/SM (80 regs) vs 9.39e9 with 5 (82 regs), 9.06e9 with 8 (64 regs, spills)
+#endif
+__global__ void __launch_bounds__(128, FBUS_REFRACT_MINB) refract_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ corners, size_t n,
                                                       double* __restrict__ pose, double* __restrict__ c3d, int32_t* __restrict__ valid) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
