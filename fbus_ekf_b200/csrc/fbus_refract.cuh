@@ -15,7 +15,8 @@ constexpr double REF_M_PI = 3.1415926;
 //   r' = alpha*r + beta*nv, beta = sqrt(1-alpha^2(1-v^2)) - alpha*v  (or its negation, see `rule`)
 FBUS_HD void refract_ray(const double* r, const double* nv, double alpha, int rule, double* out, double* v_out) {
     const double v = r[0] * nv[0] + r[1] * nv[1] + r[2] * nv[2];
-    const double root = sqrt(1 - alpha * alpha * (1 - v * v));
+    const double arg = 1 - alpha * alpha * (1 - v * v);
+    const double root = arg * rsqrt_d(arg);  // sqrt to ~1 ulp without the correctly-rounded sequence (NaN for arg <= 0: total reflection)
     const double beta = rule ? (root - alpha * v) : (alpha * v - root);
     FBUS_UNROLL
     for (int j = 0; j < 3; ++j) out[j] = alpha * r[j] + beta * nv[j];
@@ -64,7 +65,8 @@ FBUS_HD double triangulate_corner(const DevConsts& k, double xl, double yl, doub
     FBUS_UNROLL
     for (int j = 0; j < 3; ++j) P[j] = 0.5 * (P1L[j] + t1 * r2L[j] + pR[j] + t2 * rR[j]);
     Pout[0] = -P[0]; Pout[1] = -P[1]; Pout[2] = P[2];
-    return norm3(P);
+    const double n2 = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+    return n2 * rsqrt_d(n2);  // |P|, only compared with the detection-distance threshold
 }
 
 // unit eigenvector of the smallest eigenvalue of a symmetric 3x3 (stands in for EigenSolver<Matrix3d>,
