@@ -89,20 +89,19 @@ FBUS_HD void null_vec(const double* M, double lam, double* v) {
     v[0] = b0 * inv; v[1] = b1 * inv; v[2] = b2 * inv;
 }
 FBUS_HD void smallest_eigvec_sym3(const double* M, double* z) {
-    const double q = (M[0] + M[4] + M[8]) * (1.0 / 3.0);
-    const double p1 = M[1] * M[1] + M[2] * M[2] + M[5] * M[5];
-    const double a = M[0] - q, b = M[4] - q, c = M[8] - q;
-    const double p2 = a * a + b * b + c * c + 2.0 * p1;
-    const double ip0 = rsqrt_d(p2 * (1.0 / 6.0));
-    const double p = p2 * (1.0 / 6.0) * ip0;
-    double lam = q;
-    if (p > 0.0) {
-        const double ip = ip0;
-        const double B0 = a * ip, B4 = b * ip, B8 = c * ip, B1 = M[1] * ip, B2 = M[2] * ip, B5 = M[5] * ip;
-        double r = 0.5 * (B0 * (B4 * B8 - B5 * B5) - B1 * (B1 * B8 - B5 * B2) + B2 * (B1 * B5 - B4 * B2));
-        r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-        const double phi = acos(r) * (1.0 / 3.0);
-        lam = q + 2.0 * p * cos(phi + 2.0943951023931953);  // smallest eigenvalue
+    // Smallest root of the characteristic polynomial f(l) = l^3 - c2 l^2 + c1 l - c0 by Newton from l = 0: M is positive
+    // semi-definite, so f(0) = -det M <= 0 and f is increasing and concave left of its smallest root -- the iterates rise
+    // monotonically to it and never overshoot.  For the corner scatter matrix (smallest eigenvalue ~ noise^2, the other two
+    // ~ side^2) the first step already has a relative error of ~l_min/l_2; the Rayleigh polish below removes what is left.
+    const double c2 = M[0] + M[4] + M[8];
+    const double c1 = (M[0] * M[4] - M[1] * M[1]) + (M[0] * M[8] - M[2] * M[2]) + (M[4] * M[8] - M[5] * M[5]);
+    const double c0 = M[0] * (M[4] * M[8] - M[5] * M[5]) - M[1] * (M[1] * M[8] - M[5] * M[2]) + M[2] * (M[1] * M[5] - M[4] * M[2]);
+    double lam = 0.0;
+    FBUS_UNROLL
+    for (int it = 0; it < 3; ++it) {
+        const double f = ((lam - c2) * lam + c1) * lam - c0;
+        const double df = (3.0 * lam - 2.0 * c2) * lam + c1;
+        lam -= f * rcp_d(df);
     }
     double v[3];
     null_vec(M, lam, v);
