@@ -6,6 +6,14 @@
 
 #include "fbus_math.cuh"
 
+// Newton steps on the characteristic polynomial / Rayleigh-quotient polish of the plane normal (smallest_eigvec_sym3)
+#ifndef FBUS_EIG_NEWTON
+#define FBUS_EIG_NEWTON 4
+#endif
+#ifndef FBUS_EIG_POLISH
+#define FBUS_EIG_POLISH 0
+#endif
+
 namespace fbus {
 
 // common.hpp:14 -- the reference overrides M_PI; R2's -pi/4 rotation must use this value (A.3-1)
@@ -44,7 +52,9 @@ FBUS_HD double triangulate_corner(const DevConsts& k, double xl, double yl, doub
     refract_ray(r1R, k.normal, k.a1, k.glass_gt_water, r2R, &v1R);
     double P1L[3], P1R[3];
     {
-        const double s0L = k.d_air * rcp_d(v0L), s0R = k.d_air * rcp_d(v0R), s1L = k.d_glass * rcp_d(v1L), s1R = k.d_glass * rcp_d(v1R);
+        // d_air / v0 and d_glass / v1 from ONE reciprocal per ray: 1 / (v0 v1)
+        const double iL = rcp_d(v0L * v1L), iR = rcp_d(v0R * v1R);
+        const double s0L = k.d_air * (v1L * iL), s0R = k.d_air * (v1R * iR), s1L = k.d_glass * (v0L * iL), s1R = k.d_glass * (v0R * iR);
         FBUS_UNROLL
         for (int j = 0; j < 3; ++j) {
             P1L[j] = s0L * r0L[j] + s1L * r1L[j];
@@ -58,7 +68,7 @@ FBUS_HD double triangulate_corner(const DevConsts& k, double xl, double yl, doub
     for (int j = 0; j < 3; ++j) pR[j] += k.P_LR[j];
     const double c[3] = {r2L[1] * rR[2] - r2L[2] * rR[1], r2L[2] * rR[0] - r2L[0] * rR[2], r2L[0] * rR[1] - r2L[1] * rR[0]};
     const double d[3] = {pR[0] - P1L[0], pR[1] - P1L[1], pR[2] - P1L[2]};
-    const double inv3 = rcp_d(det3_cols(c, r2L, rR));
+    const double inv3 = rcp_d(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);  // det[c, rL, rR] = c . (rL x rR) = |c|^2
     const double t1 = det3_cols(c, d, rR) * inv3;
     const double t2 = -det3_cols(c, r2L, d) * inv3;
     double P[3];
@@ -98,17 +108,19 @@ FBUS_HD void smallest_eigvec_sym3(const double* M, double* z) {
     const double c0 = M[0] * (M[4] * M[8] - M[5] * M[5]) - M[1] * (M[1] * M[8] - M[5] * M[2]) + M[2] * (M[1] * M[5] - M[4] * M[2]);
     double lam = 0.0;
     FBUS_UNROLL
-    for (int it = 0; it < 3; ++it) {
+    for (int it = 0; it < FBUS_EIG_NEWTON; ++it) {
         const double f = ((lam - c2) * lam + c1) * lam - c0;
         const double df = (3.0 * lam - 2.0 * c2) * lam + c1;
         lam -= f * rcp_d(df);
     }
+#if FBUS_EIG_POLISH
     double v[3];
     null_vec(M, lam, v);
     // Rayleigh-quotient polish
     double Mv[3];
     mat3_vec(M, v, Mv);
     lam = v[0] * Mv[0] + v[1] * Mv[1] + v[2] * Mv[2];
+#endif
     null_vec(M, lam, z);
 }
 
