@@ -72,6 +72,7 @@ struct fbus_handle {
     uint32_t* d_ticket = nullptr;
     uint32_t stagger_cycles = 0;
     bool small_batch = false;
+    bool tri_warp = false;  // large batches: three-warp window kernel (FBUS_TRI_WARP=1) instead of the two-warp one
     double* d_nom = nullptr;
     double* d_P = nullptr;
     int32_t* d_prev = nullptr;
@@ -136,6 +137,10 @@ int launch_window(fbus_handle* h, WinParams& prm) {
         const size_t smem32 = (size_t)(NPK + XCH) * 32 * sizeof(double);
         if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_split_kernel<32, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
         else ekf_window_split_kernel<32, false><<<g32, 64, smem32, h->stream>>>(prm, h->k);
+    } else if (WIN_TMEM && h->tri_warp) {
+        // three warps per 32 filters (top-left / nominal / cross blocks), covariance in tensor memory
+        if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_tri_kernel<true><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
+        else ekf_window_tri_kernel<false><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
     } else if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_split_kernel<WIN_BS, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
     else ekf_window_split_kernel<WIN_BS, false><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
 #else
@@ -245,6 +250,12 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         // to ~3e9 filter-steps/s beyond (three small CTAs per SM), where the large CTAs keep scaling with the SMs they fill
         h->small_batch = WIN_BS > 32 && (batch + 31) / 32 <= 2 * (size_t)prop.multiProcessorCount;
         if (const char* sb = getenv("FBUS_SMALL_BATCH")) h->small_batch = atoi(sb) != 0;
+        if (const char* tw = getenv("FBUS_TRI_WARP")) h->tri_warp = atoi(tw) != 0;
+        if (WIN_TMEM) {
+            e = cudaFuncSetAttribute(ekf_window_tri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_tri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+            if (e != cudaSuccess) return bail("cudaFuncSetAttribute(tri)", e);
+        }
         const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
         e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);

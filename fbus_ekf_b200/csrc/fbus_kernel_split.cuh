@@ -51,15 +51,18 @@ constexpr int XCH = 54;  // doubles of exchange area per filter: ring 2 x 22 (+ 
 template <int NT>
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 // per-sample barrier: either the whole CTA or only the covariance + nominal warp of one filter group (ids 2..9)
-template <int NT>
+template <int NT, int GS = 64>
 __device__ __forceinline__ void step_bar(int pair) {
 #if FBUS_PAIR_BARRIER
-    asm volatile("bar.sync %0, 64;" ::"r"(pair + 2) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(pair + 2), "n"(GS) : "memory");
 #else
     (void)pair;
     cta_bar<NT>();
 #endif
 }
+// three-warp kernel: "new cross blocks stored" -- the cross warp arrives, the top-left warp waits (ids 6..9, 64 threads)
+__device__ __forceinline__ void cross_done_arrive(int grp) { asm volatile("bar.arrive %0, 64;" ::"r"(grp + 6) : "memory"); }
+__device__ __forceinline__ void cross_done_wait(int grp) { asm volatile("bar.sync %0, 64;" ::"r"(grp + 6) : "memory"); }
 
 struct SplitShared {
     uint32_t lo_hi[2][8];   // per nominal warp: min first / max end of the candidate IMU range
@@ -130,16 +133,77 @@ __device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) {
 #endif
 }
 
+// three-warp kernel: hand-over inside a propagate step (see propagate_cov_core PART 1 / 2)
+struct CrossWait {
+    int grp;
+    __device__ __forceinline__ void operator()() const {
+        cross_done_wait(grp);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// CROSS role (three-warp kernel only): the cross blocks P[0:9, 9:18] of every propagate step and the process noise on
+// the bias diagonals; everything else of the frame is done by the other two warps, this one only keeps their barriers.
+// ------------------------------------------------------------------------------------------------------------------
+template <int BSF>
+__device__ __forceinline__ void cross_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh, int32_t (*sflag)[BSF],
+                                           int fl, uint32_t tm_base) {
+    constexpr int NT = 3 * BSF, NW = BSF / 32, GS = 96;
+    CovTM2 P;
+    P.base = __shfl_sync(0xffffffffu, tm_base + ((uint32_t)((threadIdx.x >> 5) & 3) << 21), 0);
+    const double* const X = smem + fl;
+    const int wq = fl >> 5;
+    for (uint32_t w = prm.w0; w < prm.w1; ++w) {
+#if FBUS_FRAME_CTA_BARRIER || !FBUS_PAIR_BARRIER
+        cta_bar<NT>();  // (a)
+        uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
+#else
+        step_bar<NT, GS>(wq);  // (a)
+        const uint32_t lo = sh.lo_hi[0][wq], hi = sh.lo_hi[1][wq];
+#endif
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");  // the update of the previous frame rewrote the blocks
+        for (uint32_t i = lo; i < hi; ++i) {
+            step_bar<NT, GS>(wq);  // record (i) is complete
+            const int slot = (int)((i - lo) & 1u);
+            const int valid = sflag[slot][fl];
+            if (__any_sync(0xffffffffu, valid)) {
+                const double* rec = X + (size_t)slot * 22 * BSF;
+                double A[9], Bm[9];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * BSF]; Bm[e] = rec[(size_t)(9 + e) * BSF]; }
+                const double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
+                const double dt = rec[(size_t)21 * BSF];
+                double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
+                if (!valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;
+                propagate_cov_core<BSF, false, false, CovTM2, 2>(P, A, Bm, u0, u1, u2, dt, Qv);
+                tm_wait_st();
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                cross_done_arrive(wq);  // the top-left warp may fold the new blocks
+                P.cur ^= 1u;
+            }
+        }
+        P.tr_home();  // the update works on the home positions
+        tm_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        step_bar<NT, GS>(wq);  // (r)
+        if (pair_any<NT>(sh, wq)) step_bar<NT, GS>(wq);  // (d)
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // COVARIANCE role: owns P (shared memory; top-left 9x9 in registers while propagating)
 // ------------------------------------------------------------------------------------------------------------------
-template <int BSF, bool JOSEPH, bool TM>
+template <int BSF, bool JOSEPH, bool TM, int WPG = 2>
 __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh, int32_t (*sflag)[BSF],
                                          int fl, size_t b, bool live, uint32_t tm_base) {
-    constexpr int NT = 2 * BSF, NW = BSF / 32;
+    constexpr int NT = WPG * BSF, NW = BSF / 32, GS = WPG * 32;  // WPG warps per group of 32 filters
     constexpr int NPS = TM ? 0 : NPK;  // doubles of P per filter in shared memory
     const size_t B = prm.B;
-    using CV = typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type;
+    static_assert(WPG == 2 || TM, "the three-warp kernel keeps the covariance in tensor memory");
+    using CV = typename std::conditional<WPG == 3, CovTM2, typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type>::type;
     CV P;
     if constexpr (TM) {
         // lane 32*(warp%4) in bits 31..16; broadcast from lane 0 so that the compiler knows the address is warp-uniform and
@@ -172,7 +236,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #pragma unroll
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
 #else
-        step_bar<NT>(wq);  // (a) this pair's nominal warp has posted its IMU range
+        step_bar<NT, GS>(wq);  // (a) this pair's nominal warp has posted its IMU range
         const uint32_t lo = sh.lo_hi[0][wq], hi = sh.lo_hi[1][wq];
 #endif
         int fs = 0;  // ring slot that carries the update request
@@ -183,7 +247,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
             tl_load_any<TM>(P, TL);
 #endif
             for (uint32_t i = lo; i < hi; ++i) {
-                step_bar<NT>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
+                step_bar<NT, GS>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
                 const int slot = (int)((i - lo) & 1u);
                 const int valid = sflag[slot][fl];
                 // tensor-memory accesses are warp-wide: a warp with any valid lane runs the step on all lanes, the
@@ -198,18 +262,28 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                     double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
                     if (TM && !valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;  // the record of an invalid sample is all zeros
                     P.fence_st();  // the previous step's stores
+                    if constexpr (WPG == 3) {
+                        // three-warp kernel: this warp does the top-left block (phase 1 from the old cross blocks, then the
+                        // fold of the NEW cross blocks, which the cross warp computes meanwhile)
+                        static_assert(FBUS_TL_REGS, "three-warp kernel: top-left block in registers");
+                        propagate_cov_core<BSF, false, true, CV, 1>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL, CrossWait{wq});
+                        P.cur ^= 1u;
+                    } else {
 #if FBUS_TL_REGS
-                    propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL);
+                        propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL);
 #else
-                    propagate_cov_core<BSF>(P, A, Bm, u0, u1, u2, dt, Qv);
+                        propagate_cov_core<BSF>(P, A, Bm, u0, u1, u2, dt, Qv);
 #endif
+                    }
                 }
             }
 #if FBUS_TL_REGS
             tl_store_any<TM>(P, TL);
 #endif
         }
-        step_bar<NT>(wq);  // (r) update request posted (normally long before this warp gets here)
+        if constexpr (WPG == 3) P.cur = 0;  // the cross warp moves its blocks home before (r)
+        step_bar<NT, GS>(wq);  // (r) update request posted (normally long before this warp gets here)
+        if constexpr (WPG == 3) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (pair_any<NT>(sh, wq)) {
             const int req = sflag[2][fl];
             if (TM ? true : (req != 0)) {  // tensor memory: all lanes, the ones without a request with zero gain
@@ -242,7 +316,8 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #pragma unroll
                 for (int c = 0; c < 4; ++c) X[(size_t)(26 + c) * BSF] = t.q[c];
             }
-            step_bar<NT>(wq);  // (d) results posted
+            if constexpr (WPG == 3) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            step_bar<NT, GS>(wq);  // (d) results posted
         }
     }
     if constexpr (TM) {
@@ -305,7 +380,7 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
             if (id < 0) continue;
             const double* pp = prm.det_pose + slot * 7 * B + b;
             const double px = pp[0], py = pp[B], pz = pp[2 * B];
-            const double dist = sqrt(px * px + py * py + pz * pz);
+            const double dist = sqrt_d(px * px + py * py + pz * pz);
             if (n_det == 0) { idx_near = s; idx_prev = s; }  // detectionResult_[0] defaults (min_dist_id = 0)
             if (dist < md) { md = dist; idx_near = s; }
             if (id == prev_id) { prev_dist = dist; idx_prev = s; }
@@ -405,10 +480,10 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
     }
 }
 
-template <int BSF, bool TM>
+template <int BSF, bool TM, int WPG = 2>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
                                              int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
-    constexpr int NT = 2 * BSF, NW = BSF / 32;
+    constexpr int NT = WPG * BSF, NW = BSF / 32, GS = WPG * 32;  // WPG warps per group of 32 filters
     const size_t B = prm.B;
     double* const X = smem + (size_t)(TM ? 0 : NPK) * BSF + fl;
     const bool fused = (prm.mode & M_FUSED) != 0;
@@ -475,7 +550,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
 #else
-        step_bar<NT>(wq);  // (a)
+        step_bar<NT, GS>(wq);  // (a)
         const uint32_t lo = sh.lo_hi[0][wq], hi = sh.lo_hi[1][wq];
 #endif
         int fs = 0;
@@ -528,7 +603,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                     for (int e = 0; e < 22; ++e) rec[(size_t)e * BSF] = 0.0;
                 }
                 sflag[slot][fl] = valid;
-                step_bar<NT>(wq);  // publish record (i); also: the covariance warp has finished sample i-1
+                step_bar<NT, GS>(wq);  // publish record (i); also: the covariance warp has finished sample i-1
             }
             if (fused && do_prop) cursor = consumed;
         }
@@ -550,7 +625,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             const int wany = __any_sync(0xffffffffu, req != 0);
             if ((fl & 31) == 0) sh.any_upd[wq] = wany;
         }
-        step_bar<NT>(wq);  // (r)
+        step_bar<NT, GS>(wq);  // (r)
         const int any = pair_any<NT>(sh, wq);
         // ---- while the update runs: the next window's first IMU sample and the next frame's plan ---------------
         FramePlan nx;
@@ -566,7 +641,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             plan_frame<BSF>(prm, k, w + 1, b, live, cursor, n.t, inited, prev_id, status, nx);
         }
         if (any) {
-            step_bar<NT>(wq);  // (d) results posted
+            step_bar<NT, GS>(wq);  // (d) results posted
             if (req) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -664,6 +739,50 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
     if (is_cov) cov_role<BSF, JOSEPH, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
     else nominal_role<BSF, TM>(prm, k, smem, sh, sflag, fl, b, live);
     if constexpr (TM) tm_free_cta(tm_base);
+}
+
+#ifndef FBUS_TRI_SETMAXNREG
+#define FBUS_TRI_SETMAXNREG 1
+#endif
+// Three warps per 32 filters (covariance in tensor memory, 128 filters per CTA): top-left warp, nominal warp, cross warp.
+// 384 threads would get 168 registers each; setmaxnreg gives the top-left warps 232 and leaves 136 to the others.
+template <bool JOSEPH>
+__global__ void __launch_bounds__(384, 1) ekf_window_tri_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
+    constexpr int BSF = 128;
+    extern __shared__ double smem[];
+    __shared__ SplitShared sh;
+    __shared__ int32_t sflag[3][BSF];
+    __shared__ uint32_t tm_slot;
+    const int wi = threadIdx.x >> 5;
+    const int role = wi >> 2;  // 0: top-left / update, 1: nominal, 2: cross blocks
+    const int fl = (wi & 3) * 32 + (threadIdx.x & 31);
+    const size_t b0 = (size_t)blockIdx.x * BSF + fl;
+    const bool live = b0 < prm.B;
+    const size_t b = live ? b0 : prm.B - 1;
+    const uint32_t tm_base = tm_alloc_cta(&tm_slot);
+    if (role == 0) {
+#if FBUS_TRI_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+#endif
+#ifndef FBUS_TRI_STUB_COV
+        cov_role<BSF, JOSEPH, true, 3>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
+#endif
+    } else if (role == 1) {
+#if FBUS_TRI_SETMAXNREG
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+#endif
+#ifndef FBUS_TRI_STUB_NOM
+        nominal_role<BSF, true, 3>(prm, k, smem, sh, sflag, fl, b, live);
+#endif
+    } else {
+#if FBUS_TRI_SETMAXNREG
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+#endif
+#ifndef FBUS_TRI_STUB_CROSS
+        cross_role<BSF>(prm, k, smem, sh, sflag, fl, tm_base);
+#endif
+    }
+    tm_free_cta(tm_base);
 }
 
 }  // namespace fbus

@@ -107,11 +107,58 @@ FBUS_HD void qmul_conjb(const double* a, const double* b, double* o) {  // a * c
 }
 // reciprocal square root: one MUFU.RSQ64H + Newton steps on the device (1-2 ulp) instead of a correctly rounded
 // sqrt followed by a correctly rounded division (~4x the instructions); the host build keeps 1/sqrt
+// Device versions are call-free on purpose (hardware seed + Newton steps, no out-of-line slow path): the three-warp window
+// kernel gives its warpgroups different register budgets (setmaxnreg), and ptxas cannot share a library subroutine between
+// them.  Arguments on these paths are far inside the normal range; 0 gives NaN (the callers treat 0 separately or want it).
 FBUS_HD double rsqrt_d(double x) {
 #ifdef __CUDA_ARCH__
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);  // y += y (1/2 - x y^2 / 2)
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return y;
 #else
     return 1.0 / sqrt(x);
+#endif
+}
+// sqrt to ~1 ulp: x * rsqrt(x), exactly 0 at 0
+FBUS_HD double sqrt_d(double x) {
+#ifdef __CUDA_ARCH__
+    return x > 0.0 ? x * rsqrt_d(x) : (x == 0.0 ? 0.0 : x * rsqrt_d(x));
+#else
+    return sqrt(x);
+#endif
+}
+// sin and cos together, call-free: two-term Cody-Waite reduction by pi/2 with FMA (exact enough for |x| < ~1e5; the angles
+// here are half rotation increments, << 1) and the fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp)
+FBUS_HD void sincos_d(double x, double* sn, double* cs) {
+#ifdef __CUDA_ARCH__
+    const double kf = rint(x * 0.63661977236758138);  // 2/pi
+    double r = fma(-kf, 1.5707963267948966, x);
+    r = fma(-kf, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double s0 = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int q = (int)kf & 3;
+    const double sv = (q & 1) ? c0 : s0, cv = (q & 1) ? s0 : c0;
+    *sn = (q & 2) ? -sv : sv;
+    *cs = ((q + 1) & 2) ? -cv : cv;
+#else
+    *sn = sin(x);
+    *cs = cos(x);
 #endif
 }
 // reciprocal: hardware seed (~20 bits) + two Newton steps (~1 ulp), without the slow-path call of a correctly rounded
@@ -195,6 +242,10 @@ struct CovX {
     FBUS_HD void fence_st() const {}  // accessors with asynchronous stores (tensor memory) order them here
     // asynchronous-load API of the tensor-memory accessor (fbus_tmem.cuh); plain loads here
     FBUS_HD void ldblk_nw(int bi, int bj, double* X) const { ldany(bi, bj, X); }
+    // cross blocks of rows 1, 2 (bi in {1,2}, k in 3..5): a double-buffering accessor distinguishes the values before /
+    // after the current step; here there is one copy
+    FBUS_HD void ldtr_nw(int bi, int k, double* X, bool) const { ldany(bi, k, X); }
+    FBUS_HD void sttr(int bi, int k, const double* X) const { stblk(bi, k, X); }
     FBUS_HD void wait_ld() const {}
     FBUS_HD void fix(int, int, double*) const {}
     FBUS_HD double ld(int i, int j) const {
@@ -307,9 +358,12 @@ FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, dou
 
 // TLR = true: the top-left 9x9 (p, v, theta covariance: read AND written by every step) is held in the caller's
 // registers TL[45] across the IMU samples of a window instead of making a round trip through shared memory per step.
-template <int S, bool BRR = false, bool TLR = false, class CV = Cov<S>>
+struct NoMid {
+    FBUS_HD void operator()() const {}
+};
+template <int S, bool BRR = false, bool TLR = false, class CV = Cov<S>, int PART = 0, class MidF = NoMid>
 FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, double u0, double u1, double u2, double dt,
-                                const double* Qd, double* BR = nullptr, double* TL = nullptr) {
+                                const double* Qd, double* BR = nullptr, double* TL = nullptr, MidF mid = MidF()) {
 // element (r, c) of block (bi, bj) loaded with ldblk_nw: a blocked accessor delivers the stored block (min, max), i.e. the
 // transpose when bi > bj (BRR: the register cache is already in the requested orientation)
 #define FBUS_BLK(X, bi, bj, r, c) ((CV::kBlocked && !BRR && (bi) > (bj)) ? X[(c) * 3 + (r)] : X[(r) * 3 + (c)])
@@ -353,14 +407,14 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
     // ---------------- phase 1: top-left blocks from old values -------------------------------
     // Staged so that few blocks are live at a time (FBUS_FENCE stops the scheduler hoisting every
     // shared-memory load to the top, which would blow the 255-register budget).
-    {
+    if (PART != 2) {
         double P11[9], P12[9];
         FBUS_TL_LDBLK(1, 2, P12);
         double M12[9];
         {   // 1c: P'22 (without the -a*M24 term) ; M12 = P12 + A*P22 (+ more below)
             double P22[9], P24[9], U22[9], acc22[9];
             FBUS_TL_LDBLK(2, 2, P22);
-            P.ldblk_nw(2, 4, P24);
+            P.ldtr_nw(2, 4, P24, false);
             P.wait_ld();
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
@@ -389,8 +443,8 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
         FBUS_FENCE_A;
         {   // M12 += B*P23^T + a*P25^T
             double P23[9], P25[9];
-            P.ldblk_nw(2, 3, P23);
-            P.ldblk_nw(2, 5, P25);
+            P.ldtr_nw(2, 3, P23, false);
+            P.ldtr_nw(2, 5, P25, false);
             P.wait_ld();
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
@@ -407,8 +461,8 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
         {   // 1b: P'11 (without the M13*B^T + a*M15 term), P'12 (without -a*M14)
             double P13[9], P15[9], acc11[9], acc12[9];
             FBUS_TL_LDBLK(1, 1, P11);
-            P.ldblk_nw(1, 3, P13);
-            P.ldblk_nw(1, 5, P15);
+            P.ldtr_nw(1, 3, P13, false);
+            P.ldtr_nw(1, 5, P15, false);
             P.wait_ld();
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
@@ -474,20 +528,31 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
     }
     FBUS_FENCE_B;
     // ---------------- phase 2: block columns 4, 3, 5 of rows 0..2 -----------------------------
+    // PART 0: compute the new cross blocks and fold them into the top-left block (one warp does everything).
+    // PART 2: compute and store the cross blocks only (the "cross" warp of the three-warp kernel).
+    // PART 1: phase 1 above, then mid(), then LOAD the new cross blocks written by the PART-2 warp and fold them.
+    mid();
     double d01[9], d11[9];
     FBUS_UNROLL
     for (int kk = 0; kk < 3; ++kk) {
         const int k = (kk == 0) ? 4 : (kk == 1) ? 3 : 5;
-        double X1[9], X2[9];
-        P.ldblk_nw(1, k, X1);
-        {   // row 0: M0 = P0k + a*P1k
-            double M0[9];
+        double X1[9], X2[9], M0[9], M2[9];
+        if (PART == 1) {
             P.ldblk_nw(0, k, M0);
-            P.ldblk_nw(2, k, X2);
+            P.ldtr_nw(1, k, X1, true);
+            P.ldtr_nw(2, k, M2, true);
             P.wait_ld();
+        } else {
+            P.ldtr_nw(1, k, X1, false);
+            P.ldblk_nw(0, k, M0);
+            P.ldtr_nw(2, k, X2, false);
+            P.wait_ld();
+            // row 0: M0 = P0k + a*P1k
             FBUS_UNROLL
             for (int e = 0; e < 9; ++e) M0[e] += a * X1[e];
             P.stblk(0, k, M0);
+        }
+        if (PART != 2) {
             if (k == 4) {  // P'02 -= a*M04
                 FBUS_UNROLL
                 for (int i = 0; i < 3; ++i)
@@ -520,7 +585,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
         }
         FBUS_FENCE_A;
         double X4[9];
-        {   // row 1: M1 = P1k + A*P2k + B*P3k + a*P5k
+        if (PART != 1) {   // row 1: M1 = P1k + A*P2k + B*P3k + a*P5k
             double X3[9], X5[9];
             if (BRR) {
                 FBUS_UNROLL
@@ -549,7 +614,16 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
                     }
                     X1[i * 3 + j] = s;  // M1 in place (X1[i][j] is not read again)
                 }
-            P.stblk(1, k, X1);
+            P.sttr(1, k, X1);
+            if (k == 3) {  // accel-bias process noise on P33's diagonal
+                FBUS_UNROLL
+                for (int i = 0; i < 3; ++i) {
+                    if (BRR) BR[bridx(9 + i, 9 + i)] = X3[i * 3 + i] + Qd[2];
+                    else P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);
+                }
+            }
+        }
+        if (PART != 2) {
             if (k == 4) {  // P'12 -= a*M14
                 FBUS_UNROLL
                 for (int i = 0; i < 3; ++i)
@@ -559,7 +633,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
                         t -= a * X1[i * 3 + j];
                         FBUS_TLST(3 + i, 6 + j, t);
                     }
-            } else if (k == 3) {  // d11 = M13*B^T (upper) ; accel-bias process noise on P33's diagonal
+            } else if (k == 3) {  // d11 = M13*B^T (upper)
                 FBUS_UNROLL
                 for (int i = 0; i < 3; ++i)
                     FBUS_UNROLL
@@ -569,11 +643,6 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
                         s += X1[i * 3 + 2] * B[j * 3 + 2];
                         d11[i * 3 + j] = s;
                     }
-                FBUS_UNROLL
-                for (int i = 0; i < 3; ++i) {
-                    if (BRR) BR[bridx(9 + i, 9 + i)] = X3[i * 3 + i] + Qd[2];
-                    else P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);
-                }
             } else {  // P'11 += d11 + a*M15 (upper)
                 FBUS_UNROLL
                 for (int i = 0; i < 3; ++i)
@@ -586,8 +655,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
             }
         }
         FBUS_FENCE_A;
-        {   // row 2: M2 = (I+Wm)*P2k - a*P4k
-            double M2[9];
+        if (PART != 1) {   // row 2: M2 = (I+Wm)*P2k - a*P4k
             if (BRR) {
                 FBUS_UNROLL
                 for (int r = 0; r < 3; ++r)
@@ -603,22 +671,24 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
                     FBUS_WX_ACC(t, X2, i, j);
                     M2[i * 3 + j] = t;
                 }
-            P.stblk(2, k, M2);
-            if (k == 4) {  // P'22 -= a*M24 (upper) ; gyro-bias process noise on P44's diagonal
-                FBUS_UNROLL
-                for (int i = 0; i < 3; ++i)
-                    FBUS_UNROLL
-                    for (int j = i; j < 3; ++j) {
-                        double t = FBUS_TLLD(6 + i, 6 + j);
-                        t -= a * M2[i * 3 + j];
-                        FBUS_TLST(6 + i, 6 + j, t);
-                    }
+            P.sttr(2, k, M2);
+            if (k == 4) {  // gyro-bias process noise on P44's diagonal
                 FBUS_UNROLL
                 for (int i = 0; i < 3; ++i) {
                     if (BRR) BR[bridx(12 + i, 12 + i)] = X4[i * 3 + i] + Qd[3];
                     else P.st(12 + i, 12 + i, X4[i * 3 + i] + Qd[3]);
                 }
             }
+        }
+        if (PART != 2 && k == 4) {  // P'22 -= a*M24 (upper)
+            FBUS_UNROLL
+            for (int i = 0; i < 3; ++i)
+                FBUS_UNROLL
+                for (int j = i; j < 3; ++j) {
+                    double t = FBUS_TLLD(6 + i, 6 + j);
+                    t -= a * M2[i * 3 + j];
+                    FBUS_TLST(6 + i, 6 + j, t);
+                }
         }
         FBUS_FENCE_B;
     }
@@ -656,7 +726,7 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
         // one sincos: the half-interval quaternion needs angle/2 = wn*dt/4, the full one twice that
         // (double-angle identities; ~1 ulp from evaluating sin/cos of wn*dt/2 directly)
         double sh, ch;
-        sincos(wn * dt * 0.25, &sh, &ch);
+        sincos_d(wn * dt * 0.25, &sh, &ch);
         const double sf = 2.0 * sh * ch, cf = 1.0 - 2.0 * sh * sh;
         const double dqh[4] = {ch, sh * ax[0], sh * ax[1], sh * ax[2]};
         const double dq[4] = {cf, sf * ax[0], sf * ax[1], sf * ax[2]};
@@ -1089,7 +1159,7 @@ FBUS_HD void inject_error_state(Nominal& n, const double* dx) {
     const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
     const double vn = v2 * iv;
     double sh, ch;
-    sincos(vn * 0.5, &sh, &ch);
+    sincos_d(vn * 0.5, &sh, &ch);
     const double sc = iv * sh;
     const double dq[4] = {ch, dx[6] * sc, dx[7] * sc, dx[8] * sc};
     double qn[4];
@@ -1223,7 +1293,7 @@ FBUS_HD void update_onepass(const CV P, Nominal& n, const double* Cm, const doub
         const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
         const double vn = v2 * iv;
         double sh, ch;
-        sincos(vn * 0.5, &sh, &ch);
+        sincos_d(vn * 0.5, &sh, &ch);
         const double sc = iv * sh;
         const double dq[4] = {ch, dth[0] * sc, dth[1] * sc, dth[2] * sc};
         double qn[4];
@@ -1377,7 +1447,7 @@ FBUS_HD void update_onepass_blk(const CV P, Nominal& n, const double* Cm, const 
         const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
         const double vn = v2 * iv;
         double sh, ch;
-        sincos(vn * 0.5, &sh, &ch);
+        sincos_d(vn * 0.5, &sh, &ch);
         const double sc = iv * sh;
         const double dq[4] = {ch, dth[0] * sc, dth[1] * sc, dth[2] * sc};
         double qn[4];
@@ -1517,7 +1587,7 @@ FBUS_HD void measurement_update(const CV P, Nominal& n, const DevConsts& k, cons
         const double iv = rsqrt_d(v2);  // inf at exactly zero -> NaN below, as the reference's 0/0
         const double vn = v2 * iv;
         double sh, ch;
-        sincos(vn * 0.5, &sh, &ch);
+        sincos_d(vn * 0.5, &sh, &ch);
         const double sc = iv * sh;
         const double dq[4] = {ch, dth[0] * sc, dth[1] * sc, dth[2] * sc};
         double qn[4];
