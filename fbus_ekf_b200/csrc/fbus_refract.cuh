@@ -443,54 +443,70 @@ FBUS_HD double gn_normal_eq(const GnConsts& g, const double* c, const double* Rm
     double cost = 0.0;
     FBUS_GN_UNROLL
     for (int i = 0; i < 4; ++i) {
-        const double cm[3] = {(i == 1 || i == 2) ? g.size : 0.0, (i >= 2) ? g.size : 0.0, 0.0};  // (0,0),(s,0),(s,s),(0,s)
-        double Rc[3];
-        mat3_vec(Rm, cm, Rc);
-        const double XL[3] = {-(p[0] + Rc[0]), -(p[1] + Rc[1]), p[2] + Rc[2]};  // un-flip: F = diag(-1,-1,1)
-        // d XL / d(dp) = F ; d XL / d(dphi) = -F Rm [cm]x
-        double D[18];  // 3 x 6
+        const double cx = (i == 1 || i == 2) ? g.size : 0.0, cy = (i >= 2) ? g.size : 0.0;  // corners (0,0),(s,0),(s,s),(0,s), z = 0
+        const double XL[3] = {-(p[0] + Rm[0] * cx + Rm[1] * cy), -(p[1] + Rm[3] * cx + Rm[4] * cy), p[2] + Rm[6] * cx + Rm[7] * cy};  // un-flip: F = diag(-1,-1,1)
+        // d XL / d(dp) = F ; d XL / d(dphi) = -F Rm [cm]x, and with cm = (cx, cy, 0):
+        //   (Rm [cm]x)[r][:] = (-Rm[r][2] cy, Rm[r][2] cx, Rm[r][0] cy - Rm[r][1] cx)
+        double Dr[9];  // rotation part of D (3 x 3); the translation part is F itself
         FBUS_UNROLL
         for (int r = 0; r < 3; ++r) {
             const double fs = (r < 2) ? -1.0 : 1.0;
-            D[r * 6 + 0] = (r == 0) ? fs : 0.0; D[r * 6 + 1] = (r == 1) ? fs : 0.0; D[r * 6 + 2] = (r == 2) ? fs : 0.0;
-            // (Rm [cm]x)[r][:] = (Rm[r][1]cm2 - Rm[r][2]cm1, Rm[r][2]cm0 - Rm[r][0]cm2, Rm[r][0]cm1 - Rm[r][1]cm0)
-            D[r * 6 + 3] = -fs * (Rm[r * 3 + 1] * cm[2] - Rm[r * 3 + 2] * cm[1]);
-            D[r * 6 + 4] = -fs * (Rm[r * 3 + 2] * cm[0] - Rm[r * 3 + 0] * cm[2]);
-            D[r * 6 + 5] = -fs * (Rm[r * 3 + 0] * cm[1] - Rm[r * 3 + 1] * cm[0]);
+            Dr[r * 3 + 0] = fs * (Rm[r * 3 + 2] * cy);
+            Dr[r * 3 + 1] = -fs * (Rm[r * 3 + 2] * cx);
+            Dr[r * 3 + 2] = -fs * (Rm[r * 3 + 0] * cy - Rm[r * 3 + 1] * cx);
         }
         FBUS_GN_UNROLL
         for (int cam = 0; cam < 2; ++cam) {
-            double X[3], DX[18];
+            double X[3];
             if (cam == 0) {
                 FBUS_UNROLL
                 for (int r = 0; r < 3; ++r) X[r] = XL[r];
-                FBUS_UNROLL
-                for (int e = 0; e < 18; ++e) DX[e] = D[e];
             } else {
                 const double dL[3] = {XL[0] - g.P_LR[0], XL[1] - g.P_LR[1], XL[2] - g.P_LR[2]};
                 mat3_vec(g.R_RL_inv, dL, X);
-                FBUS_UNROLL
-                for (int r = 0; r < 3; ++r)
-                    FBUS_UNROLL
-                    for (int e = 0; e < 6; ++e)
-                        DX[r * 6 + e] = g.R_RL_inv[r * 3] * D[e] + g.R_RL_inv[r * 3 + 1] * D[6 + e] + g.R_RL_inv[r * 3 + 2] * D[12 + e];
             }
             double uv[2], Jp[6];
             project_refr<JAC, true>(g, X, uv, Jp, sw[cam * 4 + i]);
             const double ru = uv[0] - c[cam * 8 + 2 * i], rv = uv[1] - c[cam * 8 + 2 * i + 1];
-            cost += ru * ru + rv * rv;
+            cost += ru * ru;
+            cost += rv * rv;
             if (!JAC) continue;
+            // G = d(uv)/d(XL) (2 x 3): Jp for the left camera, Jp R_RL^-1 for the right one
+            double G[6];
+            if (cam == 0) {
+                FBUS_UNROLL
+                for (int e = 0; e < 6; ++e) G[e] = Jp[e];
+            } else {
+                FBUS_UNROLL
+                for (int r = 0; r < 2; ++r)
+                    FBUS_UNROLL
+                    for (int e = 0; e < 3; ++e) {
+                        double t = Jp[r * 3] * g.R_RL_inv[e];
+                        t += Jp[r * 3 + 1] * g.R_RL_inv[3 + e];
+                        t += Jp[r * 3 + 2] * g.R_RL_inv[6 + e];
+                        G[r * 3 + e] = t;
+                    }
+            }
+            // J = G [F | Dr]
             double Ju[6], Jv[6];
+            Ju[0] = -G[0]; Ju[1] = -G[1]; Ju[2] = G[2];
+            Jv[0] = -G[3]; Jv[1] = -G[4]; Jv[2] = G[5];
             FBUS_UNROLL
-            for (int e = 0; e < 6; ++e) {
-                Ju[e] = Jp[0] * DX[e] + Jp[1] * DX[6 + e] + Jp[2] * DX[12 + e];
-                Jv[e] = Jp[3] * DX[e] + Jp[4] * DX[6 + e] + Jp[5] * DX[12 + e];
+            for (int e = 0; e < 3; ++e) {
+                double tu = G[0] * Dr[e], tv = G[3] * Dr[e];
+                tu += G[1] * Dr[3 + e]; tv += G[4] * Dr[3 + e];
+                tu += G[2] * Dr[6 + e]; tv += G[5] * Dr[6 + e];
+                Ju[3 + e] = tu; Jv[3 + e] = tv;
             }
             FBUS_UNROLL
             for (int a = 0; a < 6; ++a) {
-                gvec[a] += Ju[a] * ru + Jv[a] * rv;
+                gvec[a] += Ju[a] * ru;
+                gvec[a] += Jv[a] * rv;
                 FBUS_UNROLL
-                for (int b = 0; b <= a; ++b) H[a * (a + 1) / 2 + b] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+                for (int b = 0; b <= a; ++b) {
+                    H[a * (a + 1) / 2 + b] += Ju[a] * Ju[b];
+                    H[a * (a + 1) / 2 + b] += Jv[a] * Jv[b];
+                }
             }
         }
     }
