@@ -351,7 +351,7 @@ FBUS_HD double triangulate_corner_inair(const DevConsts& k, double xl, double yl
 #define FBUS_GN_UNROLL_ON 0  // 1: inline all 8 projections of a Gauss-Newton iteration (warm starts in registers)
 #endif
 #ifndef FBUS_GN_NEWTON_TOL
-#define FBUS_GN_NEWTON_TOL 1e-9
+#define FBUS_GN_NEWTON_TOL 1e-7
 #endif
 #if FBUS_GN_UNROLL_ON
 #define FBUS_GN_UNROLL FBUS_UNROLL
@@ -401,8 +401,8 @@ FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double
         if (!(sn < 1.0)) sn = 0.5 * (s + 1.0);
         if (!(sn > 0.0)) sn = 0.5 * s;
         ds = sn - s;
-        // |ds| <= 1e-9 s: the Newton step that follows would move s by ~ds^2 (1e-18 s): sn is the root to rounding.
-        // r0..gs were evaluated at s = sn - ds; tau below is corrected to first order (error ~ t'' ds^2 / 2 < 1e-16),
+        // |ds| <= 1e-7 s: the Newton step that follows would move s by ~ds^2 (1e-14 s): sn is the root to rounding.
+        // r0..gs were evaluated at s = sn - ds; tau below is corrected to first order (error ~ t'' ds^2 / 2 < 1e-12),
         // the Jacobian keeps a 1e-9 relative error, which only perturbs the GN step by 1e-9 of its length.
         if ((ds < 0 ? -ds : ds) <= (FAST ? FBUS_GN_NEWTON_TOL : 4.5e-16) * s) break;
         s = sn;
