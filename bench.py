@@ -293,6 +293,10 @@ def run_ours(args):
                 "peak_source": "DFMA-saturating microbenchmark measured live on this GPU (fbus_measure_fp64_peak, burst); "
                                "MEASURED_PEAKS.json has no FP64 entry; nominal 37.2 TFLOP/s",
                 "algorithmic_flop_per_launch": flop_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                "fp64_pipe_busy_pct_ncu": prof.get("fp64_pipe_busy_pct_ncu"),
+                "note": "frac uses SURVEY 8d's algorithmic flop count (dense-structure count, FMA = 2); the kernel executes fewer "
+                        "FP64 instructions than that count, so the pipe-busy figure from ncu (same launch shape, "
+                        "profiles/r1_window_kernel_ncu_full.md) is lower than frac",
                 "traffic": (prof["ekf_window_dram_bytes_per_filter_per_launch"] * B) if "ekf_window_dram_bytes_per_filter_per_launch" in prof else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at %d filters, scaled per filter "
                                   "(profiles/roofline_inputs.json)" % prof.get("measured_at_filters", 0) if prof else None,
