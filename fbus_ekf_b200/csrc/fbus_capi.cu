@@ -476,29 +476,49 @@ static int stereo_solve(fbus_handle* h, const float* corners, size_t n, double* 
     if (!h || !corners || !pose) return fail(h, FBUS_E_BADARG, "fbus_refract_solve / fbus_inair_solve: bad argument");
     if (n == 0) return FBUS_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    const float* dc;
-    int rc = stage(h, h->scratch_in, corners, 16 * n, mem, &dc);
-    if (rc) return rc;
-    double* dpose = pose;
-    double* dc3 = corners3d;
-    int32_t* dvalid = valid;
-    if (mem == FBUS_MEM_HOST) {
-        CUDA_TRY(h, h->scratch_out.reserve((7 + 12) * n * sizeof(double)));
-        CUDA_TRY(h, h->scratch_aux.reserve(n * sizeof(int32_t)));
-        dpose = (double*)h->scratch_out.p;
-        dc3 = dpose + 7 * n;
-        dvalid = (int32_t*)h->scratch_aux.p;
+    if (mem != FBUS_MEM_HOST) {
+        const unsigned grid = (unsigned)((n + 127) / 128);
+        if (underwater) refract_kernel<<<grid, 128, 0, h->stream>>>(h->k, corners, n, n, pose, corners3d, valid);
+        else inair_kernel<<<grid, 128, 0, h->stream>>>(h->k, corners, n, n, pose, corners3d, valid);
+        CUDA_TRY(h, cudaGetLastError());
+        return FBUS_OK;
     }
-    const unsigned grid = (unsigned)((n + 127) / 128);
-    if (underwater) refract_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc, n, dpose, dc3, dvalid);
-    else inair_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc, n, dpose, dc3, dvalid);
-    CUDA_TRY(h, cudaGetLastError());
-    if (mem == FBUS_MEM_HOST) {
-        CUDA_TRY(h, cudaMemcpyAsync(pose, dpose, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (corners3d) CUDA_TRY(h, cudaMemcpyAsync(corners3d, dc3, 12 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (valid) CUDA_TRY(h, cudaMemcpyAsync(valid, dvalid, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    // Host arrays: the [16][n] / [7][n] / [12][n] arrays are cut into column chunks; the H2D copy of chunk c+1 (second stream)
+    // overlaps the kernel and the D2H copy of chunk c (PCIe is full duplex), so a call costs about one direction's transfer.
+    CUDA_TRY(h, h->scratch_in.reserve(16 * n * sizeof(float)));
+    CUDA_TRY(h, h->scratch_out.reserve((7 + 12) * n * sizeof(double)));
+    CUDA_TRY(h, h->scratch_aux.reserve(n * sizeof(int32_t)));
+    float* dc = (float*)h->scratch_in.p;
+    double* dpose = (double*)h->scratch_out.p;
+    double* dc3 = dpose + 7 * n;
+    int32_t* dvalid = (int32_t*)h->scratch_aux.p;
+    const bool piped = h->copy_stream != nullptr && n >= 65536;
+    const size_t nch = piped ? 4 : 1;  // few chunks: at ~1 ms per call the API calls per chunk (~30 us) matter
+    const size_t step = ((n + nch - 1) / nch + 127) / 128 * 128;
+    cudaStream_t cs = piped ? h->copy_stream : h->stream;
+    if (piped) {  // the staging buffers may still be read by earlier work on the main stream
+        CUDA_TRY(h, cudaEventRecord(h->ev_done[0], h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(cs, h->ev_done[0], 0));
     }
+    int c = 0;
+    for (size_t a = 0; a < n; a += step, ++c) {
+        const size_t m = (a + step <= n) ? step : n - a;
+        CUDA_TRY(h, cudaMemcpy2DAsync(dc + a, n * sizeof(float), corners + a, n * sizeof(float), m * sizeof(float), 16, cudaMemcpyHostToDevice, cs));
+        if (piped) {
+            CUDA_TRY(h, cudaEventRecord(h->ev_copied[c & 1], cs));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[c & 1], 0));
+        }
+        const unsigned grid = (unsigned)((m + 127) / 128);
+        if (underwater) refract_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc + a, m, n, dpose + a, dc3 + a, dvalid + a);
+        else inair_kernel<<<grid, 128, 0, h->stream>>>(h->k, dc + a, m, n, dpose + a, dc3 + a, dvalid + a);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaMemcpy2DAsync(pose + a, n * sizeof(double), dpose + a, n * sizeof(double), m * sizeof(double), 7, cudaMemcpyDeviceToHost, h->stream));
+        if (corners3d)
+            CUDA_TRY(h, cudaMemcpy2DAsync(corners3d + a, n * sizeof(double), dc3 + a, n * sizeof(double), m * sizeof(double), 12, cudaMemcpyDeviceToHost,
+                                          h->stream));
+        if (valid) CUDA_TRY(h, cudaMemcpyAsync(valid + a, dvalid + a, m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return FBUS_OK;
 }
 

@@ -389,13 +389,14 @@ __global__ void ctor_kernel(double* nom, double* P, int32_t* prev_id, int32_t* i
 #ifndef FBUS_REFRACT_MINB
 #define FBUS_REFRACT_MINB 6  // measured: 9.72e9 solves/s with 6 CTAs/SM (80 regs) vs 9.39e9 with 5 (82 regs), 9.06e9 with 8 (64 regs, spills)
 #endif
-__global__ void __launch_bounds__(128, FBUS_REFRACT_MINB) refract_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ corners, size_t n,
+__global__ void __launch_bounds__(128, FBUS_REFRACT_MINB) refract_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ corners, size_t n, size_t ld,
                                                       double* __restrict__ pose, double* __restrict__ c3d, int32_t* __restrict__ valid) {
+    // n markers of arrays whose rows are ld apart (ld = n for a whole array; a chunk of a larger one otherwise)
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float c[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) c[e] = corners[(size_t)e * n + i];
+    for (int e = 0; e < 16; ++e) c[e] = corners[(size_t)e * ld + i];
     double C[12];
     bool dead = false;
 #pragma unroll
@@ -411,12 +412,12 @@ __global__ void __launch_bounds__(128, FBUS_REFRACT_MINB) refract_kernel(const _
     double p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0};
     if (!dead) marker_pose(C, k.rod_s, k.rod_c, p, q);
 #pragma unroll
-    for (int e = 0; e < 3; ++e) pose[(size_t)e * n + i] = p[e];
+    for (int e = 0; e < 3; ++e) pose[(size_t)e * ld + i] = p[e];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) pose[(size_t)(3 + e) * n + i] = q[e];
+    for (int e = 0; e < 4; ++e) pose[(size_t)(3 + e) * ld + i] = q[e];
     if (c3d) {
 #pragma unroll
-        for (int e = 0; e < 12; ++e) c3d[(size_t)e * n + i] = C[e];
+        for (int e = 0; e < 12; ++e) c3d[(size_t)e * ld + i] = C[e];
     }
     if (valid) valid[i] = dead ? 0 : 1;
 }
@@ -437,13 +438,13 @@ __global__ void __launch_bounds__(128) undistort_kernel(const __grid_constant__ 
 }
 
 // N3+K4: in-air stereo DLT triangulation (VISION::NormalTriangulation, vision.cpp:395-466) + ComputeMarkerPose
-__global__ void __launch_bounds__(128) inair_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ corners, size_t n,
+__global__ void __launch_bounds__(128) inair_kernel(const __grid_constant__ DevConsts k, const float* __restrict__ corners, size_t n, size_t ld,
                                                     double* __restrict__ pose, double* __restrict__ c3d, int32_t* __restrict__ valid) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float c[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) c[e] = corners[(size_t)e * n + i];
+    for (int e = 0; e < 16; ++e) c[e] = corners[(size_t)e * ld + i];
     double C[12];
     bool dead = false;
 #pragma unroll
@@ -458,12 +459,12 @@ __global__ void __launch_bounds__(128) inair_kernel(const __grid_constant__ DevC
     double p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0};
     if (!dead) marker_pose(C, k.rod_s, k.rod_c, p, q);
 #pragma unroll
-    for (int e = 0; e < 3; ++e) pose[(size_t)e * n + i] = p[e];
+    for (int e = 0; e < 3; ++e) pose[(size_t)e * ld + i] = p[e];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) pose[(size_t)(3 + e) * n + i] = q[e];
+    for (int e = 0; e < 4; ++e) pose[(size_t)(3 + e) * ld + i] = q[e];
     if (c3d) {
 #pragma unroll
-        for (int e = 0; e < 12; ++e) c3d[(size_t)e * n + i] = C[e];
+        for (int e = 0; e < 12; ++e) c3d[(size_t)e * ld + i] = C[e];
     }
     if (valid) valid[i] = dead ? 0 : 1;
 }
