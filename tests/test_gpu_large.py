@@ -64,3 +64,17 @@ def test_half_million_refractive_solves(cfg):
     assert np.array_equal(valid[sel], vo)
     good = vo == 1
     assert np.abs(pose[:, sel][:, good] - po[:, good]).max() <= 1e-8
+    # host arrays go through the chunked, pipelined path (column chunks, two streams); device arrays through one launch:
+    # same kernel, same inputs -> identical bits (a ragged size so that the last chunk is partial)
+    import torch
+    m = n - 1000
+    ch = np.ascontiguousarray(corners[:, :m])
+    ph, c3h, vh = f.RefractSolve(ch)
+    cd = torch.from_numpy(ch).cuda()
+    pd = torch.empty((7, m), dtype=torch.float64, device="cuda")
+    c3d = torch.empty((12, m), dtype=torch.float64, device="cuda")
+    vd = torch.empty(m, dtype=torch.int32, device="cuda")
+    f.RefractSolveDevice(cd.data_ptr(), m, pd.data_ptr(), c3d.data_ptr(), vd.data_ptr())
+    f.Synchronize()
+    assert np.array_equal(ph, pd.cpu().numpy(), equal_nan=True) and np.array_equal(c3h, c3d.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(vh, vd.cpu().numpy())
