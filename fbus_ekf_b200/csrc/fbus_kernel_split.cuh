@@ -764,23 +764,17 @@ __global__ void __launch_bounds__(384, 1) ekf_window_tri_kernel(const __grid_con
 #if FBUS_TRI_SETMAXNREG
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
 #endif
-#ifndef FBUS_TRI_STUB_COV
         cov_role<BSF, JOSEPH, true, 3>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
-#endif
     } else if (role == 1) {
 #if FBUS_TRI_SETMAXNREG
         asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
 #endif
-#ifndef FBUS_TRI_STUB_NOM
         nominal_role<BSF, true, 3>(prm, k, smem, sh, sflag, fl, b, live);
-#endif
     } else {
 #if FBUS_TRI_SETMAXNREG
         asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
 #endif
-#ifndef FBUS_TRI_STUB_CROSS
         cross_role<BSF>(prm, k, smem, sh, sflag, fl, tm_base);
-#endif
     }
     tm_free_cta(tm_base);
 }
