@@ -60,13 +60,29 @@ __device__ __forceinline__ void step_bar(int pair) {
     cta_bar<NT>();
 #endif
 }
-// three-warp kernel: "new cross blocks stored" -- the cross warp arrives, the top-left warp waits (ids 6..9, 64 threads)
-__device__ __forceinline__ void cross_done_arrive(int grp) { asm volatile("bar.arrive %0, 64;" ::"r"(grp + 6) : "memory"); }
-__device__ __forceinline__ void cross_done_wait(int grp) { asm volatile("bar.sync %0, 64;" ::"r"(grp + 6) : "memory"); }
+// three-warp kernel: "new cross blocks of block column kk stored" -- one mbarrier per filter group and column (32 arrivals
+// from the cross warp, the top-left warp waits on the phase parity = parity of the step count); the per-sample rendezvous of
+// the three warps keeps the producer at most one phase ahead
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {  // release: everything this thread did before is visible to the waiter
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {  // acquire; the warp reconverges afterwards
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+    __syncwarp();
+}
 
 struct SplitShared {
     uint32_t lo_hi[2][8];   // per nominal warp: min first / max end of the candidate IMU range
     int32_t any_upd[8];     // per nominal warp: some filter requests an update
+    uint64_t col_done[4][3];  // three-warp kernel: mbarriers "cross blocks of block column kk stored", per filter group
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -134,11 +150,22 @@ __device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) {
 }
 
 // three-warp kernel: hand-over inside a propagate step (see propagate_cov_core PART 1 / 2)
-struct CrossWait {
-    int grp;
-    __device__ __forceinline__ void operator()() const {
-        cross_done_wait(grp);
+struct CrossWait {   // top-left warp: wait for a block column of the step with parity `par`
+    uint64_t* bars;
+    uint32_t par;
+    __device__ __forceinline__ void begin(int kk) const {
+        mb_wait(bars + kk, par);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    __device__ __forceinline__ void end(int) const {}
+};
+struct CrossSignal {  // cross warp: a block column is stored
+    uint64_t* bars;
+    __device__ __forceinline__ void begin(int) const {}
+    __device__ __forceinline__ void end(int kk) const {
+        tm_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mb_arrive(bars + kk);
     }
 };
 
@@ -178,10 +205,7 @@ __device__ __forceinline__ void cross_role(const WinParams& prm, const DevConsts
                 const double dt = rec[(size_t)21 * BSF];
                 double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
                 if (!valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;
-                propagate_cov_core<BSF, false, false, CovTM2, 2>(P, A, Bm, u0, u1, u2, dt, Qv);
-                tm_wait_st();
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                cross_done_arrive(wq);  // the top-left warp may fold the new blocks
+                propagate_cov_core<BSF, false, false, CovTM2, 2>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, nullptr, CrossSignal{&sh.col_done[wq][0]});
                 P.cur ^= 1u;
             }
         }
@@ -213,6 +237,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
     else P.s = smem + fl;
     double* const X = smem + (size_t)NPS * BSF + fl;
     const int wq = fl >> 5;
+    uint32_t nstep = 0;  // three-warp kernel: propagate steps executed so far (phase parity of the column mbarriers)
     if constexpr (TM) {
         FBUS_UNROLL
         for (int bj = 0; bj < 6; ++bj)
@@ -266,8 +291,9 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                         // three-warp kernel: this warp does the top-left block (phase 1 from the old cross blocks, then the
                         // fold of the NEW cross blocks, which the cross warp computes meanwhile)
                         static_assert(FBUS_TL_REGS, "three-warp kernel: top-left block in registers");
-                        propagate_cov_core<BSF, false, true, CV, 1>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL, CrossWait{wq});
+                        propagate_cov_core<BSF, false, true, CV, 1>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL, CrossWait{&sh.col_done[wq][0], nstep & 1u});
                         P.cur ^= 1u;
+                        ++nstep;
                     } else {
 #if FBUS_TL_REGS
                         propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL);
@@ -759,6 +785,8 @@ __global__ void __launch_bounds__(384, 1) ekf_window_tri_kernel(const __grid_con
     const size_t b0 = (size_t)blockIdx.x * BSF + fl;
     const bool live = b0 < prm.B;
     const size_t b = live ? b0 : prm.B - 1;
+    if (threadIdx.x < 12) mb_init(&sh.col_done[threadIdx.x / 3][threadIdx.x % 3], 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t tm_base = tm_alloc_cta(&tm_slot);
     if (role == 0) {
 #if FBUS_TRI_SETMAXNREG
