@@ -358,8 +358,11 @@ FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, dou
 
 // TLR = true: the top-left 9x9 (p, v, theta covariance: read AND written by every step) is held in the caller's
 // registers TL[45] across the IMU samples of a window instead of making a round trip through shared memory per step.
+// hooks of propagate_cov_core around each block column of phase 2 (kk = 0, 1, 2 for columns 4, 3, 5): the three-warp kernel
+// synchronises its two covariance warps column by column through them
 struct NoMid {
-    FBUS_HD void operator()() const {}
+    FBUS_HD void begin(int) const {}
+    FBUS_HD void end(int) const {}
 };
 template <int S, bool BRR = false, bool TLR = false, class CV = Cov<S>, int PART = 0, class MidF = NoMid>
 FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, double u0, double u1, double u2, double dt,
@@ -530,12 +533,13 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
     // ---------------- phase 2: block columns 4, 3, 5 of rows 0..2 -----------------------------
     // PART 0: compute the new cross blocks and fold them into the top-left block (one warp does everything).
     // PART 2: compute and store the cross blocks only (the "cross" warp of the three-warp kernel).
-    // PART 1: phase 1 above, then mid(), then LOAD the new cross blocks written by the PART-2 warp and fold them.
-    mid();
+    // PART 1: phase 1 above, then per block column: mid.begin(kk) (wait for the PART-2 warp), LOAD the new cross blocks, fold.
+    // PART 2 calls mid.end(kk) after the stores of a block column (signal).
     double d01[9], d11[9];
     FBUS_UNROLL
     for (int kk = 0; kk < 3; ++kk) {
         const int k = (kk == 0) ? 4 : (kk == 1) ? 3 : 5;
+        mid.begin(kk);
         double X1[9], X2[9], M0[9], M2[9];
         if (PART == 1) {
             P.ldblk_nw(0, k, M0);
@@ -691,6 +695,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
                 }
         }
         FBUS_FENCE_B;
+        mid.end(kk);
     }
 #undef FBUS_WX_ACC
 #undef FBUS_XWT_ACC
