@@ -14,8 +14,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBUS_EKF_LIB", os.path.join(HERE, "libfbus_ekf.so"))
 
+FBUS_OK, FBUS_E_BADARG, FBUS_E_CUDA, FBUS_E_NOMEM, FBUS_E_STATE = 0, -1, -2, -3, -4
 FBUS_MEM_HOST = 0
 FBUS_MEM_DEVICE = 1
+# per-filter status bits (fbus_state_soa.status)
+FBUS_ST_INIT_FAILED, FBUS_ST_RESET_SKIPPED, FBUS_ST_RESET_DONE, FBUS_ST_UPDATE_SKIPPED = 0x1, 0x2, 0x4, 0x8
+FBUS_ST_NONFINITE, FBUS_ST_NO_DETECTION, FBUS_ST_MARKER_REJECTED = 0x10, 0x20, 0x40
+FBUS_FLAG_JOSEPH = 0x1
 FBUS_MAX_MARKERS = 16
 FBUS_NSTATS = 8
 
