@@ -335,6 +335,31 @@ def run_ours(args):
                  "ms_per_launch": s0.elapsed_time(s1) / reps}
         fs.close()
 
+    # ---- the live use of the reference: ONE filter, one detection frame per call with host arrays (what the C++ shim does
+    #      in SetDetectionResultUpdated): latency of a frame, H2D of its ~8 IMU samples and the synchronisation included ----
+    single = None
+    if not args.no_solves and rank == 0:
+        f1 = BatchFilter(cfg, batch=1, device=local)
+        imu1 = np.ascontiguousarray(traj["base_imu"][:, :, None])
+        id1 = np.zeros((W, 1, 1), dtype=np.int32)
+        pose1 = np.ascontiguousarray(traj["base_pose"][:, None, :, None])
+        lat = []
+        for kk in range(4):
+            ti, tf = shifted(traj, kk)
+            imu_v = capi.make_imu_stream(ti, imu1, 1)
+            det_v = capi.make_det_frames(tf, id1, pose1, 1, 1)
+            for w in range(W):
+                t0 = time.perf_counter()
+                f1.StepWindows(imu_v, det_v, traj["win_off"], w, w + 1)
+                f1.Synchronize()
+                if kk > 0:
+                    lat.append(time.perf_counter() - t0)
+        lat = np.sort(np.array(lat)) * 1e6
+        single = {"workload": "one filter, one detection frame (8 IMU samples + 1 marker pose) per fbus_step_windows call, host arrays, "
+                              "synchronised after every frame", "frames": int(lat.size), "median_us": float(np.median(lat)),
+                  "p95_us": float(lat[int(0.95 * (lat.size - 1))]), "frame_period_of_the_camera_us": 1e6 / FRAME_RATE}
+        f1.close()
+
     # ---- refractive solves/sec (second half of the metric): K3+K4 on 524,288 markers per launch ---------------------
     solves = bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak) if not args.no_solves else None
 
@@ -352,7 +377,7 @@ def run_ours(args):
                 "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(B, world), "e2e": e2e, "gpu_launches": K,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "stats": stats, "solves": solves,
-                "small_batch": small, "config4": config4,
+                "small_batch": small, "single_filter": single, "config4": config4,
                 "timing": "CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks"}
         print(json.dumps(line), flush=True)
     if world > 1:
