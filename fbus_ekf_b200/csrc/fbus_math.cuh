@@ -122,6 +122,16 @@ FBUS_HD double rsqrt_d(double x) {
     return 1.0 / sqrt(x);
 #endif
 }
+// one Newton step only: relative error ~1e-13, for iterations that correct themselves (the inner Newton of the GN projection)
+FBUS_HD double rsqrt_d1(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return fma(y, fma(-0.5 * x * y, y, 0.5), y);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 // sqrt to ~1 ulp: x * rsqrt(x), exactly 0 at 0
 FBUS_HD double sqrt_d(double x) {
 #ifdef __CUDA_ARCH__

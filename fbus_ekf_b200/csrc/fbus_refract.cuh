@@ -394,7 +394,11 @@ FBUS_HD void project_refr(const GnConsts& g, const double* X, double* uv, double
     double r0, r1, r2, gs, ds = 0.0;
     for (int it = 0; it < 50; ++it) {
         const double s2 = s * s;
-        r0 = rsqrt_d(1.0 - s2); r1 = rsqrt_d(1.0 - k1s * s2); r2 = rsqrt_d(1.0 - k2s * s2);
+        if (FAST) {  // 1e-13-accurate reciprocal roots are enough inside the GN loop (tau inherits that error, parity needs 1e-8)
+            r0 = rsqrt_d1(1.0 - s2); r1 = rsqrt_d1(1.0 - k1s * s2); r2 = rsqrt_d1(1.0 - k2s * s2);
+        } else {
+            r0 = rsqrt_d(1.0 - s2); r1 = rsqrt_d(1.0 - k1s * s2); r2 = rsqrt_d(1.0 - k2s * s2);
+        }
         gs = g.d0 * (r0 * r0) * r0 + a1 * (r1 * r1) * r1 + a2 * (r2 * r2) * r2;
         const double f = s * (g.d0 * r0 + a1 * r1 + a2 * r2) - rho;
         double sn = s - f * rcp_d(gs);
