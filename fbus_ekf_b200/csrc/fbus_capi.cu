@@ -70,7 +70,12 @@ struct fbus_handle {
     GnConsts gn;
     MarkerTable* d_tab = nullptr;
     uint32_t* d_ticket = nullptr;
+    uint32_t* d_cursor = nullptr;  // [B] first unconsumed IMU sample per filter after the last fused call
+    // identity of the last fused call, for the continuation rule of fbus_step_windows
+    const void* last_imu_data = nullptr;
+    size_t last_n_samples = 0, last_w1 = 0;
     uint32_t stagger_cycles = 0;
+    size_t pipeline_min_bytes = (size_t)64 << 20;  // host streams smaller than this are staged and processed in one go
     bool small_batch = false;
     bool tri_warp = false;  // large batches: three-warp window kernel (FBUS_TRI_WARP=1) instead of the two-warp one
     double* d_nom = nullptr;
@@ -80,7 +85,6 @@ struct fbus_handle {
     int32_t* d_status = nullptr;
     DevBuf imu_t, det_t, win_off, imu_data, det_id, det_pose, trace, scratch_in, scratch_out, scratch_aux, stats_partial, stats_out;
     // second staging set + copy stream: host-resident streams are copied chunk c+1 while chunk c is computed
-    DevBuf imu_data2, det_id2, det_pose2;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     size_t pipeline_frames = 2;  // frames per chunk of the host-stream pipeline (FBUS_PIPELINE_FRAMES, 0 = off)
@@ -127,6 +131,7 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.B = h->B;
     prm.tab = h->d_tab;
     prm.sm_ticket = h->d_ticket;
+    prm.cursor_io = h->d_cursor;
     prm.stagger_cycles = (prm.mode & M_FUSED) ? h->stagger_cycles : 0u;
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
 #if FBUS_SPLIT
@@ -150,8 +155,7 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     return FBUS_OK;
 }
 
-int stage_det(fbus_handle* h, const fbus_det_frames* det, size_t w0, size_t w1, WinParams& prm, int bufset = 0,
-              cudaStream_t big_stream = nullptr) {
+int stage_det(fbus_handle* h, const fbus_det_frames* det, size_t w0, size_t w1, WinParams& prm, cudaStream_t big_stream = nullptr) {
     if (!det || det->batch != h->B || w1 > det->n_frames || w0 > w1 || det->max_markers == 0 || !det->t || !det->id || !det->pose)
         return fail(h, FBUS_E_BADARG, "bad detection frames");
     const size_t m = det->max_markers, B = h->B, nw = w1 - w0;
@@ -162,9 +166,9 @@ int stage_det(fbus_handle* h, const fbus_det_frames* det, size_t w0, size_t w1, 
     const int32_t* did;
     const double* dpose;
     cudaStream_t bs = big_stream ? big_stream : h->stream;
-    rc = stage_on(h, bufset ? h->det_id2 : h->det_id, det->id + w0 * m * B, nw * m * B, det->mem, &did, bs);
+    rc = stage_on(h, h->det_id, det->id + w0 * m * B, nw * m * B, det->mem, &did, bs);
     if (rc) return rc;
-    rc = stage_on(h, bufset ? h->det_pose2 : h->det_pose, det->pose + w0 * m * 7 * B, nw * m * 7 * B, det->mem, &dpose, bs);
+    rc = stage_on(h, h->det_pose, det->pose + w0 * m * 7 * B, nw * m * 7 * B, det->mem, &dpose, bs);
     if (rc) return rc;
     prm.det_t = dt;
     prm.det_id = did;
@@ -221,6 +225,7 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         if ((e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     if (const char* pf = getenv("FBUS_PIPELINE_FRAMES")) h->pipeline_frames = (size_t)strtoul(pf, nullptr, 10);
+    if (const char* pm = getenv("FBUS_PIPELINE_MIN_MB")) h->pipeline_min_bytes = (size_t)strtoul(pm, nullptr, 10) << 20;
     if ((e = cudaMalloc(&h->d_nom, sizeof(double) * NOM_FIELDS * batch)) != cudaSuccess) return bail("cudaMalloc nom", e);
     if ((e = cudaMalloc(&h->d_P, sizeof(double) * NPK * batch)) != cudaSuccess) return bail("cudaMalloc P", e);
     if ((e = cudaMalloc(&h->d_prev, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc prev", e);
@@ -228,6 +233,8 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     if ((e = cudaMalloc(&h->d_status, sizeof(int32_t) * batch)) != cudaSuccess) return bail("cudaMalloc status", e);
     if ((e = cudaMalloc(&h->d_ticket, 256 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc tickets", e);
     if ((e = cudaMemset(h->d_ticket, 0, 256 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset tickets", e);
+    if ((e = cudaMalloc(&h->d_cursor, batch * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc cursor", e);
+    if ((e = cudaMemset(h->d_cursor, 0, batch * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset cursor", e);
     {
         const char* sc = getenv("FBUS_STAGGER_CYCLES");
         h->stagger_cycles = sc ? (uint32_t)strtoul(sc, nullptr, 10) : 0u;  // measured: no benefit, off by default
@@ -284,13 +291,13 @@ int fbus_destroy(fbus_handle* h) {
     if (!h) return FBUS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_nom); cudaFree(h->d_P); cudaFree(h->d_prev); cudaFree(h->d_init); cudaFree(h->d_status); cudaFree(h->d_tab); cudaFree(h->d_ticket);
+    cudaFree(h->d_nom); cudaFree(h->d_P); cudaFree(h->d_prev); cudaFree(h->d_init); cudaFree(h->d_status); cudaFree(h->d_tab); cudaFree(h->d_ticket); cudaFree(h->d_cursor);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
-    DevBuf* bufs[] = {&h->imu_data2, &h->det_id2, &h->det_pose2, &h->imu_t, &h->det_t, &h->win_off, &h->imu_data, &h->det_id, &h->det_pose, &h->trace,
+    DevBuf* bufs[] = {&h->imu_t, &h->det_t, &h->win_off, &h->imu_data, &h->det_id, &h->det_pose, &h->trace,
                       &h->scratch_in, &h->scratch_out, &h->scratch_aux, &h->stats_partial, &h->stats_out};
     for (DevBuf* b : bufs) b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -378,44 +385,45 @@ int fbus_update(fbus_handle* h, const fbus_det_frames* det, size_t frame) {
     return launch_window(h, prm);
 }
 
-// one launch of the fused window kernel for frames [w0, w1).  With a copy stream the bulky host arrays of this
-// chunk are copied on that stream into staging set `bufset` and the kernel waits for them through an event, so the
-// copy of the next chunk overlaps this chunk's kernel.
-static int step_windows_chunk(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det_frames* det, const uint32_t* win_off,
-                              size_t w0, size_t w1, double* trace, int32_t trace_mem, int bufset, cudaStream_t copy_stream) {
-    const size_t B = h->B, nw = w1 - w0;
+// Fused frames [w0, w1) of a stream.  The kernel indexes the stream with absolute sample / frame numbers (the small host arrays
+// t, win_off, det_t are staged in full up to the end of the range; device-resident bulk arrays are used in place), so that a
+// continuation can reach samples a filter has not consumed yet.
+//   host-resident bulk arrays, one launch : samples [win_off[w0], win_off[w1]) and frames [w0, w1) are staged (no continuation)
+//   host-resident, pipelined             : device buffers for the whole range, filled chunk by chunk on the copy stream while the
+//                                          previous chunk is computed; chunks after the first continue (cursor_resume)
+static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det_frames* det, const uint32_t* win_off,
+                              size_t w0, size_t w1, double* trace, int32_t trace_mem, bool resume, size_t chunk_frames) {
+    const size_t B = h->B, nw = w1 - w0, m = det->max_markers;
+    if (det->batch != B || w1 > det->n_frames || m == 0 || !det->t || !det->id || !det->pose) return fail(h, FBUS_E_BADARG, "bad detection frames");
     const size_t s0 = win_off[w0], s1 = win_off[w1];
+    const bool imu_host = imu->mem == FBUS_MEM_HOST, det_host = det->mem == FBUS_MEM_HOST;
     WinParams prm;
     memset(&prm, 0, sizeof prm);
-    if (copy_stream) CUDA_TRY(h, cudaStreamWaitEvent(copy_stream, h->ev_done[bufset], 0));  // staging set free again
-    int rc = stage_det(h, det, w0, w1, prm, bufset, copy_stream);
-    if (rc) return rc;
-    // IMU samples of this call, re-based to index 0
+    // small host arrays, staged in full so that absolute indices work: t[0, s1), win_off[0, w1], det_t[0, w1)
     const double* dt;
-    const double* dd;
-    const size_t ns = s1 - s0;
-    rc = stage(h, h->imu_t, imu->t + s0, ns ? ns : 1, FBUS_MEM_HOST, &dt);
-    if (rc) return rc;
-    if (imu->mem == FBUS_MEM_HOST && ns == 0) dd = nullptr;
-    else {
-        rc = stage_on(h, bufset ? h->imu_data2 : h->imu_data, imu->data + s0 * 6 * B, ns * 6 * B, imu->mem, &dd,
-                      copy_stream ? copy_stream : h->stream);
-        if (rc) return rc;
-    }
-    if (copy_stream) {
-        CUDA_TRY(h, cudaEventRecord(h->ev_copied[bufset], copy_stream));
-        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[bufset], 0));
-    }
-    std::vector<uint32_t> off(nw + 1);
-    for (size_t w = 0; w <= nw; ++w) off[w] = (uint32_t)(win_off[w0 + w] - s0);
+    const double* ddt;
     const uint32_t* doff;
-    rc = stage(h, h->win_off, off.data(), nw + 1, FBUS_MEM_HOST, &doff);
+    int rc = stage(h, h->imu_t, imu->t, s1 ? s1 : 1, FBUS_MEM_HOST, &dt);
     if (rc) return rc;
-    // `off` is pageable host memory: cudaMemcpyAsync has staged it before returning
-    prm.imu_t = dt;
-    prm.imu = dd;
-    prm.win_off = doff;
-    prm.mode = M_FUSED;
+    rc = stage(h, h->win_off, win_off, w1 + 1, FBUS_MEM_HOST, &doff);
+    if (rc) return rc;
+    rc = stage(h, h->det_t, det->t, w1, FBUS_MEM_HOST, &ddt);
+    if (rc) return rc;
+    // bulk arrays: device-resident ones in place; host-resident ones into buffers that hold the range [s0, s1) / [w0, w1),
+    // addressed through base pointers shifted back to index 0 (never dereferenced below the range)
+    const double* dimu = imu->data;
+    const int32_t* did = det->id;
+    const double* dpose = det->pose;
+    if (imu_host) {
+        CUDA_TRY(h, h->imu_data.reserve((s1 - s0 ? s1 - s0 : 1) * 6 * B * sizeof(double)));
+        dimu = (const double*)h->imu_data.p - s0 * 6 * B;
+    }
+    if (det_host) {
+        CUDA_TRY(h, h->det_id.reserve(nw * m * B * sizeof(int32_t)));
+        CUDA_TRY(h, h->det_pose.reserve(nw * m * 7 * B * sizeof(double)));
+        did = (const int32_t*)h->det_id.p - w0 * m * B;
+        dpose = (const double*)h->det_pose.p - w0 * m * 7 * B;
+    }
     double* dtrace = nullptr;
     if (trace) {
         if (trace_mem == FBUS_MEM_DEVICE) dtrace = trace;
@@ -424,10 +432,45 @@ static int step_windows_chunk(fbus_handle* h, const fbus_imu_stream* imu, const 
             dtrace = (double*)h->trace.p;
         }
     }
-    prm.trace = dtrace;
-    rc = launch_window(h, prm);
-    if (rc) return rc;
-    if (copy_stream) CUDA_TRY(h, cudaEventRecord(h->ev_done[bufset], h->stream));
+    prm.imu_t = dt;
+    prm.imu = dimu;
+    prm.win_off = doff;
+    prm.det_t = ddt;
+    prm.det_id = did;
+    prm.det_pose = dpose;
+    prm.m = (int32_t)m;
+    prm.mode = M_FUSED;
+    const bool piped = chunk_frames > 0 && h->copy_stream != nullptr;
+    cudaStream_t cs = piped ? h->copy_stream : h->stream;
+    if (piped) {  // the range buffers may still be read by earlier work on the main stream
+        CUDA_TRY(h, cudaEventRecord(h->ev_done[0], h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(cs, h->ev_done[0], 0));
+    }
+    const size_t step = piped ? chunk_frames : nw;
+    int c = 0;
+    for (size_t a = w0; a < w1; a += step, ++c) {
+        const size_t e = (a + step < w1) ? a + step : w1;
+        const size_t sa = win_off[a], se = win_off[e];
+        if (imu_host && se > sa)
+            CUDA_TRY(h, cudaMemcpyAsync((double*)h->imu_data.p + (sa - s0) * 6 * B, imu->data + sa * 6 * B, (se - sa) * 6 * B * sizeof(double),
+                                        cudaMemcpyHostToDevice, cs));
+        if (det_host) {
+            CUDA_TRY(h, cudaMemcpyAsync((int32_t*)h->det_id.p + (a - w0) * m * B, det->id + a * m * B, (e - a) * m * B * sizeof(int32_t),
+                                        cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(h, cudaMemcpyAsync((double*)h->det_pose.p + (a - w0) * m * 7 * B, det->pose + a * m * 7 * B,
+                                        (e - a) * m * 7 * B * sizeof(double), cudaMemcpyHostToDevice, cs));
+        }
+        if (piped) {
+            CUDA_TRY(h, cudaEventRecord(h->ev_copied[c & 1], cs));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[c & 1], 0));
+        }
+        prm.w0 = (uint32_t)a;
+        prm.w1 = (uint32_t)e;
+        prm.cursor_resume = (resume || c > 0) ? 1 : 0;
+        prm.trace = dtrace ? dtrace + (a - w0) * 17 * B : nullptr;
+        rc = launch_window(h, prm);
+        if (rc) return rc;
+    }
     if (trace && trace_mem == FBUS_MEM_HOST) {
         CUDA_TRY(h, cudaMemcpyAsync(trace, dtrace, nw * 17 * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -445,22 +488,21 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
         if (win_off[w + 1] < win_off[w]) return fail(h, FBUS_E_BADARG, "fbus_step_windows: win_off must be non-decreasing");
     if (win_off[w1] > imu->n_samples) return fail(h, FBUS_E_BADARG, "fbus_step_windows: win_off beyond the IMU stream");
     const size_t nw = w1 - w0, B = h->B;
+    // Continuation (see the header): the call picks up where the previous one on this handle stopped -- same device-resident
+    // IMU array, w0 equal to the previous w1 -- so samples a filter has not consumed yet stay buffered across the two calls.
+    const bool device_streams = imu->mem == FBUS_MEM_DEVICE && det->mem == FBUS_MEM_DEVICE;
+    const bool resume = device_streams && w0 > 0 && w0 == h->last_w1 && imu->data == h->last_imu_data && imu->n_samples == h->last_n_samples;
     // Host-resident streams that are large enough to matter: pipeline the frames in chunks so that the PCIe copy of
     // chunk c+1 runs while chunk c is computed (the state makes one extra HBM round trip per chunk).
     const size_t ch = h->pipeline_frames;
     const bool host_streams = imu->mem == FBUS_MEM_HOST && det->mem == FBUS_MEM_HOST;
     const size_t bytes = (size_t)(win_off[w1] - win_off[w0]) * 48 * B;
-    if (host_streams && ch > 0 && nw >= 2 * ch && bytes >= ((size_t)64 << 20) && h->copy_stream) {
-        int c = 0;
-        for (size_t a = w0; a < w1; a += ch, ++c) {
-            const size_t e = (a + ch < w1) ? a + ch : w1;
-            double* tr = trace ? trace + (a - w0) * 17 * B : nullptr;
-            int rc = step_windows_chunk(h, imu, det, win_off, a, e, tr, trace_mem, c & 1, h->copy_stream);
-            if (rc) return rc;
-        }
-        return FBUS_OK;
-    }
-    return step_windows_chunk(h, imu, det, win_off, w0, w1, trace, trace_mem, 0, nullptr);
+    const bool piped = host_streams && ch > 0 && nw >= 2 * ch && bytes >= h->pipeline_min_bytes && h->copy_stream;
+    int rc = step_windows_range(h, imu, det, win_off, w0, w1, trace, trace_mem, resume, piped ? ch : 0);
+    h->last_imu_data = device_streams ? (const void*)imu->data : nullptr;
+    h->last_n_samples = imu->n_samples;
+    h->last_w1 = w1;
+    return rc;
 }
 
 static int stereo_solve(fbus_handle* h, const float* corners, size_t n, double* pose, double* corners3d, int32_t* valid, int32_t mem,

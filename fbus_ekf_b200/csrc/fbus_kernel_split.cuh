@@ -531,7 +531,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     int prev_id = prm.prev_id[b];
     int inited = prm.init[b];
     int status = prm.status[b];
-    uint32_t cursor = fused ? prm.win_off[prm.w0] : 0u;
+    uint32_t cursor = fused ? (prm.cursor_resume ? prm.cursor_io[b] : prm.win_off[prm.w0]) : 0u;
     // first IMU sample of the NEXT window, prefetched while this warp waits for the covariance warp's update
     uint32_t pf_i = 0xffffffffu;
     double pf_st = 0.0, pf_sd[6];
@@ -720,6 +720,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     }
     prm.prev_id[b] = prev_id;
     prm.init[b] = inited;
+    if (fused) prm.cursor_io[b] = cursor;
     prm.status[b] = status;
 }
 

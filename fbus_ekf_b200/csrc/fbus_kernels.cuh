@@ -54,6 +54,8 @@ struct WinParams {
     uint32_t prop_first, prop_count;
     double prop_t_end;
     uint32_t n_imu_before;  // un-fused init
+    uint32_t* cursor_io;      // [B] fused mode: index of the first IMU sample a filter has not consumed yet (written at the end)
+    int32_t cursor_resume;    // fused mode: start from cursor_io (continuation of the same stream) instead of win_off[w0]
     uint32_t stagger_cycles;  // split kernel, 2 CTAs per SM: start delay of odd-ticket CTAs
     uint32_t* sm_ticket;      // split kernel: per-SM arrival counters [256] (device), or nullptr
 };
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
     const int mode = prm.mode;
     const bool fused = (mode & M_FUSED) != 0;
 
-    uint32_t cursor = fused ? prm.win_off[prm.w0] : 0u;
+    uint32_t cursor = fused ? (prm.cursor_resume ? prm.cursor_io[b] : prm.win_off[prm.w0]) : 0u;
 
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
         // ---- scan this frame's detections (filter.cpp:329-341 / 418-430 / 639-658) ------------
@@ -344,6 +346,7 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
     }
     prm.prev_id[b] = prev_id;
     prm.init[b] = inited;
+    if (fused) prm.cursor_io[b] = cursor;
     prm.status[b] = status;
 }
 

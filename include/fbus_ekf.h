@@ -203,6 +203,12 @@ int fbus_update(fbus_handle* h, const fbus_det_frames* det, size_t frame);
  * ResetSystemState, BatchImuProcessing over IMU samples [win_off[w], win_off[w+1]) with
  * t_end = det->t[w], ObservationUpdate.  State stays on chip for all the frames of one call.
  * win_off is a HOST array of n_frames+1 sample indices.
+ * IMU buffer semantics (filter.cpp:390,493-520): a frame in which a filter does nothing (no detection for it, failed
+ * initialisation) leaves that filter's IMU samples buffered for its next frame; within one call this is exact for any
+ * memory kind (large host-resident streams are copied and processed in frame chunks, which is invisible in the results).
+ * Across calls: a call starts with an empty buffer at win_off[w0], EXCEPT when it continues the previous call on this
+ * handle -- device-resident streams, the same imu->data pointer and n_samples, w0 equal to the previous w1 -- in which case
+ * the unconsumed samples carry over, exactly as if the two frame ranges had been one call.
  * trace (optional, HOST or DEVICE per trace_mem): [w1-w0][17][B] rows
  *   t p(3) q(wxyz) v(3) b_a(3) b_g(3)  -- the data/fusion.txt row (filter.cpp:241-246) after each frame.
  */

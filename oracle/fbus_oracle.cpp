@@ -835,6 +835,11 @@ void parallel_for(size_t n, int n_threads, Fn fn) {
 struct orc_handle {
     Consts k;
     std::vector<Filter> f;
+    // continuation rule of fbus_step_windows (include/fbus_ekf.h): first unconsumed IMU sample per filter after the last call,
+    // and the identity of that call
+    std::vector<size_t> cursor;
+    const void* last_imu_data = nullptr;
+    size_t last_n_samples = 0, last_w1 = 0;
 };
 
 extern "C" {
@@ -913,6 +918,11 @@ int orc_step_windows(orc_handle* h, const fbus_imu_stream* imu, const fbus_det_f
                      const uint32_t* win_off, size_t w0, size_t w1, double* trace, int n_threads) {
     const size_t B = h->f.size();
     if (imu->batch != B || det->batch != B || w1 > det->n_frames || w0 > w1) return FBUS_E_BADARG;
+    const bool resume = w0 > 0 && w0 == h->last_w1 && imu->data == h->last_imu_data && imu->n_samples == h->last_n_samples;
+    h->cursor.resize(B, 0);
+    h->last_imu_data = imu->data;
+    h->last_n_samples = imu->n_samples;
+    h->last_w1 = w1;
     parallel_for(B, n_threads, [&](size_t lo, size_t hi) {
         std::vector<Det> d(det->max_markers);
         for (size_t b = lo; b < hi; ++b) {
@@ -920,7 +930,7 @@ int orc_step_windows(orc_handle* h, const fbus_imu_stream* imu, const fbus_det_f
             // `cursor` = first IMU sample still in the reference's imuMeasuementBuffer_: samples are
             // erased only when a frame consumes them (filter.cpp:390,520); frames that do nothing
             // leave them buffered for the next frame.
-            size_t cursor = win_off[w0];
+            size_t cursor = resume ? h->cursor[b] : win_off[w0];
             for (size_t w = w0; w < w1; ++w) {
                 const int n = gather_dets(det, w, b, d.data());
                 const size_t first = cursor, count = win_off[w + 1] - cursor;
@@ -946,6 +956,7 @@ int orc_step_windows(orc_handle* h, const fbus_imu_stream* imu, const fbus_det_f
                     for (int c = 0; c < 3; ++c) { row[(8 + c) * B] = f.v[c]; row[(11 + c) * B] = f.ba[c]; row[(14 + c) * B] = f.bg[c]; }
                 }
             }
+            h->cursor[b] = cursor;
             check_finite(&f);
         }
     });
