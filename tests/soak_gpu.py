@@ -69,10 +69,52 @@ def one(it, rng, cfg):
     return ok
 
 
+def board(it, rng, cfg):
+    """multi-marker frames (8 board markers, refractive solve on the GPU -> detections), random subsets of the markers
+    detected per filter and frame, occasional unknown ids: marker selection / hysteresis / prev-id logic across all paths"""
+    path = list(PATHS)[it % 3]
+    for k in ("FBUS_SMALL_BATCH", "FBUS_TRI_WARP"):
+        os.environ.pop(k, None)
+    os.environ.update(PATHS[path])
+    B, m = int(rng.integers(1, 200)), 8
+    bcfg = synth.board_config(cfg)
+    if it % 2:
+        bcfg.flags = 1  # Joseph form
+    traj = synth.truth_trajectory(bcfg, float(rng.choice([0.32, 0.6])), standoff=1.0)
+    W, N = len(traj["t_frames"]), len(traj["t_imu"])
+    base, ids, _ = synth.board_base_corners(bcfg, traj)
+    corners = np.ascontiguousarray((np.repeat(base, B, axis=1) + rng.normal(size=(16, W * m * B)) * 2e-4).astype(np.float32))
+    mids = np.ascontiguousarray(np.repeat(ids[:, :, None], B, axis=2))
+    mids[rng.random(size=mids.shape) < rng.choice([0.0, 0.3, 0.8])] = -1       # markers not detected
+    f = BatchFilter(bcfg, batch=B)
+    det_id, det_pose = f.SolveToDetections(corners, mids, W, m, underwater=True, gn_iters=0)
+    det_id[(rng.random(size=det_id.shape) < 0.02) & (det_id >= 0)] = 99        # ids that are not in the map
+    imu = np.ascontiguousarray(traj["base_imu"][:, :, None] + rng.normal(size=(N, 6, B)) * np.array([0.015] * 3 + [1e-3] * 3)[None, :, None])
+    s = capi.make_imu_stream(traj["t_imu"], imu, B)
+    d = capi.make_det_frames(traj["t_frames"], det_id, det_pose, B, m)
+    f.StepWindows(s, d, traj["win_off"], 0, W)
+    sg = f.GetState()
+    f.close()
+    o = orc.Oracle(bcfg, B)
+    o.step_windows(s, d, traj["win_off"], 0, W, None, 8)
+    so = o.get_state()
+    ok_int = all(np.array_equal(sg[k], so[k]) for k in ("status", "initialised", "prev_marker_id"))
+    fin = np.isfinite(so["p"]).all(axis=0)
+    err = max(float(np.abs(sg[k][:, fin] - so[k][:, fin]).max()) if fin.any() else 0.0 for k in ("p", "q", "v", "ba", "bg", "g"))
+    okP = cov_close(sg["P"][:, fin], so["P"][:, fin], 1e-9)[0] if fin.any() else True
+    ok = ok_int and err <= 1e-9 and okP
+    print(f"{it:3d} {path:8s} board B={B:3d} W={W:2d} joseph={it % 2} ids/status={'ok' if ok_int else 'DIFF'} state_err={err:.2e} cov={'ok' if okP else 'DIFF'}"
+          f" {'' if ok else '  <-- FAIL'}", flush=True)
+    return ok
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     rng = np.random.default_rng(2026)
     cfg = capi.config_default()
     bad = sum(0 if one(i, rng, cfg) else 1 for i in range(n))
+    nb = max(n // 3, 6)
+    bad += sum(0 if board(i, rng, cfg) else 1 for i in range(nb))
+    n += nb
     print(f"soak: {n - bad}/{n} iterations agree with the oracle")
     sys.exit(1 if bad else 0)
