@@ -6,9 +6,9 @@
 
 #include "fbus_math.cuh"
 
-// Newton steps on the characteristic polynomial / Rayleigh-quotient polish of the plane normal (smallest_eigvec_sym3)
+// cap of the Newton steps on the characteristic polynomial / Rayleigh-quotient polish of the plane normal (smallest_eigvec_sym3)
 #ifndef FBUS_EIG_NEWTON
-#define FBUS_EIG_NEWTON 4
+#define FBUS_EIG_NEWTON 60
 #endif
 #ifndef FBUS_EIG_POLISH
 #define FBUS_EIG_POLISH 0
@@ -106,12 +106,15 @@ FBUS_HD void smallest_eigvec_sym3(const double* M, double* z) {
     const double c2 = M[0] + M[4] + M[8];
     const double c1 = (M[0] * M[4] - M[1] * M[1]) + (M[0] * M[8] - M[2] * M[2]) + (M[4] * M[8] - M[5] * M[5]);
     const double c0 = M[0] * (M[4] * M[8] - M[5] * M[5]) - M[1] * (M[1] * M[8] - M[5] * M[2]) + M[2] * (M[1] * M[5] - M[4] * M[2]);
+    // Iterated to convergence: two or three steps for a clean marker; up to FBUS_EIG_NEWTON when the corner noise is so large
+    // that the smallest eigenvalue is no longer well separated (the monotone iteration is then slower, but still safe).
     double lam = 0.0;
-    FBUS_UNROLL
     for (int it = 0; it < FBUS_EIG_NEWTON; ++it) {
         const double f = ((lam - c2) * lam + c1) * lam - c0;
         const double df = (3.0 * lam - 2.0 * c2) * lam + c1;
-        lam -= f * rcp_d(df);
+        const double step = f * rcp_d(df);
+        lam -= step;
+        if (!((step < 0 ? -step : step) > 2.3e-16 * c2)) break;  // also leaves on NaN
     }
 #if FBUS_EIG_POLISH
     double v[3];
