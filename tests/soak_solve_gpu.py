@@ -38,4 +38,22 @@ for it, noise in enumerate([0.0, 2e-4, 2e-3, 1e-2, 3e-2] * 2):
     print(f"{it:2d} {'refract' if under else 'in-air '} n={n:5d} noise={noise:.0e} valid={'ok' if same_valid else 'DIFF'} ({int(good.sum())} good) "
           f"pos={e_p:.1e} quat={e_q:.1e} corners={e_c:.1e} {'' if ok else '  <-- FAIL'}", flush=True)
 print(f"solve soak: {10 - bad}/10 agree with the oracle")
-sys.exit(1 if bad else 0)
+
+# ---- Gauss-Newton refinement against the NumPy restatement (bracketing root finder, LAPACK), a few dozen markers (slow oracle) ----
+import fbus_oracle_np as onp  # noqa: E402
+k = onp.Consts(onp.Config(tsc_left=np.array(cfg.tsc_left).reshape(4, 4), tsc_right=np.array(cfg.tsc_right).reshape(4, 4)))
+bad_gn = 0
+for noise in (0.0, 2e-4, 2e-3):
+    Rm, p = synth.random_marker_poses(24, rng)
+    corners = synth.marker_corners_from_pose(cfg, Rm, p, noise=noise, rng=rng)
+    pose, cost, valid = f.RefractSolveGN(corners, iters=5)
+    worst = 0.0
+    for i in range(corners.shape[1]):
+        if not valid[i]:
+            continue
+        pg, qg, _ = onp.refract_solve_gn(k, corners[:, i].astype(np.float64), 5)
+        worst = max(worst, float(np.abs(pg - pose[:3, i]).max()), float(np.abs(qg - pose[3:, i]).max()))
+    ok = worst <= 1e-8
+    bad_gn += 0 if ok else 1
+    print(f"GN 5 iterations, noise={noise:.0e}: max |GPU - NumPy oracle| = {worst:.1e} {'' if ok else '  <-- FAIL'}", flush=True)
+sys.exit(1 if (bad or bad_gn) else 0)
