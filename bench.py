@@ -201,6 +201,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's own banner / debug lines go to stderr: stdout carries the one JSON line and nothing else
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         import __graft_entry__ as ge

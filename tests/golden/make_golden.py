@@ -11,7 +11,11 @@ Contents (all float64, parsed from the 6-significant-digit text logs with numpy.
   land_imu / water_imu     [n,7] t accel(3) gyro(3) raw IMU log                  (filter.cpp:31-32)
   land_fusion / water_fusion [n,17] logged filter output of an OLDER reference revision: shape-only pin
 Source: /root/reference/matlab/dataset/{landdata/dataset-02,waterdata/dataset-06}.
+
+Also writes log_heads.json: the first 4 text lines of every log verbatim (without the line ends), the format pin of
+fbus_ekf_b200/logio.py (`ofstream <<` at default precision) where /root/reference does not exist.
 """
+import json
 import os
 import numpy as np
 
@@ -25,6 +29,12 @@ def main():
         for name in ("corners", "image", "imu", "fusion"):
             out[f"{key}_{name}"] = np.loadtxt(os.path.join(SRC, sub, name + ".txt"))
     np.savez_compressed(os.path.join(HERE, "fbus_logs.npz"), **out)
+    heads = {}
+    for key, sub in (("land", "landdata/dataset-02"), ("water", "waterdata/dataset-06")):
+        for name in ("corners", "image", "imu", "fusion"):
+            with open(os.path.join(SRC, sub, name + ".txt"), newline="") as fh:
+                heads[f"{key}_{name}"] = [fh.readline().rstrip("\r\n") for _ in range(4)]
+    json.dump(heads, open(os.path.join(HERE, "log_heads.json"), "w"), indent=1)
     for k, v in out.items():
         print(k, v.shape)
 
