@@ -175,7 +175,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(env_int("FBUS_BENCH_BATCH", 1 << 20), max(1, args.gpus)), "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT or sys.stdout, flush=True)
     return 0
 
 
@@ -201,8 +201,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own banner / debug lines go to stderr: stdout carries the one JSON line and nothing else
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         import __graft_entry__ as ge
@@ -381,7 +379,7 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "stats": stats, "solves": solves,
                 "small_batch": small, "single_filter": single, "config4": config4,
                 "timing": "CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -559,7 +557,16 @@ def bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, t
             "rmse_pos_m_last_step": float(np.sqrt(last[0] / max(last[3], 1.0)))}
 
 
+JSON_OUT = None  # the process's real stdout, kept for the one JSON line
+
+
 def main():
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print at the C level (NCCL's version banner
+    # under NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE, make, nvcc) is sent to stderr by pointing fd 1 at fd 2
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -22,9 +22,13 @@ def test_shim_matches_replay(cfg, golden, tmp_path):
     img = img[img[:, 0] <= imu[-1, 0]]
     np.savetxt(tmp_path / "imu.txt", imu, fmt="%.17g")
     np.savetxt(tmp_path / "image.txt", img, fmt="%.17g")
-    for use_iir in (0, 1):
-        out = subprocess.check_output([str(exe), str(tmp_path / "imu.txt"), str(tmp_path / "image.txt"), "500", str(use_iir)], text=True)
+    # threaded = 1: IMU samples through the static InputIMUData callback, frames worked off by the filter thread
+    # (StartFilterThread / SetDetectionResultUpdated -> condition variable), as main.cpp / vision.cpp drive the reference;
+    # the demo also checks GetVisualizeInfo / Get*MarkerPose against the single getters on every frame (exit code 3)
+    for use_iir, threaded in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        out = subprocess.check_output([str(exe), str(tmp_path / "imu.txt"), str(tmp_path / "image.txt"), "500", str(use_iir),
+                                       str(threaded)], text=True)
         rows = np.array([[float(x) for x in line.split()] for line in out.strip().splitlines()])
         ref = replay.replay_log(imu, img, cfg, n_init=500, use_iir=bool(use_iir))["rows"]
         assert rows.shape == ref.shape
-        assert np.array_equal(rows, ref), f"use_iir={use_iir}: max diff {np.abs(rows - ref).max()}"
+        assert np.array_equal(rows, ref), f"use_iir={use_iir} threaded={threaded}: max diff {np.abs(rows - ref).max()}"
