@@ -367,6 +367,8 @@ def run_ours(args):
 
     # ---- e2e: HOST buffers through the C ABI, H2D of every step's streams + D2H of the step's statistics -------------
     e2e = bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq) if not args.no_e2e else None
+    # the same with the IMU stream in the sensor's own float32 format (extra, not the headline: the reference's API takes doubles)
+    e2e_f32 = bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq, sensor_f32=True) if not args.no_e2e else None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -375,7 +377,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": workload_config(B, world), "e2e": e2e, "gpu_launches": K,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(B, world), "e2e": e2e, "e2e_sensor_f32": e2e_f32, "gpu_launches": K,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "stats": stats, "solves": solves,
                 "small_batch": small, "single_filter": single, "config4": config4,
                 "timing": "CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks"}
@@ -502,15 +504,17 @@ def bench_config4(cfg, dev, local, rank, world, K, Wm):
     return out
 
 
-def bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq):
+def bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq, sensor_f32=False):
     """Same metric through the public API with HOST buffers: every step copies that step's per-filter streams from pinned
-    host memory to the device and reads the step's statistics vector back."""
+    host memory to the device and reads the step's statistics vector back.  sensor_f32: the IMU stream is handed over in
+    the IMSEE sensor's own format (float32, g and deg/s; FBUS_IMU_F32_SENSOR) and converted on the device as the
+    reference's IMU callback does -- half the bytes per sample, same doubles inside the filter."""
     import psutil
     import torch
     import torch.distributed as dist
     from fbus_ekf_b200 import BatchFilter, capi
     N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
-    per_filter = N * 48 + W * 60
+    per_filter = N * (24 if sensor_f32 else 48) + W * 60
     local_world = env_int("LOCAL_WORLD_SIZE", world)
     budget = 0.15 * psutil.virtual_memory().available / max(local_world, 1)
     Be = B
@@ -518,10 +522,17 @@ def bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, t
         Be //= 2
     Be = env_int("FBUS_BENCH_E2E_BATCH", Be)
     f2 = BatchFilter(cfg, batch=Be, device=local)
-    h_imu = torch.empty((N, 6, Be), dtype=torch.float64).pin_memory()
+    h_imu = torch.empty((N, 6, Be), dtype=torch.float32 if sensor_f32 else torch.float64).pin_memory()
     h_id = torch.empty((W, 1, Be), dtype=torch.int32).pin_memory()
     h_pose = torch.empty((W, 1, 7, Be), dtype=torch.float64).pin_memory()
-    h_imu.copy_(imu_d[:, :, :Be])
+    if sensor_f32:  # nearest sensor-unit sample of the synthetic SI stream (capi.si_to_sensor, on the device)
+        raw = torch.empty((N, 6, Be), dtype=torch.float32, device=dev)
+        raw[:, 0:3] = (imu_d[:, 0:3, :Be] / cfg.imu_g).float()
+        raw[:, 3:6] = (imu_d[:, 3:6, :Be] * (180.0 / capi.REF_M_PI)).float()
+        h_imu.copy_(raw)
+        del raw
+    else:
+        h_imu.copy_(imu_d[:, :, :Be])
     h_id.copy_(id_d[:, :, :Be])
     h_pose.copy_(pose_d[:, :, :, :Be])
     tpe, tqe = tp[:, :Be].contiguous(), tq[:, :Be].contiguous()
@@ -531,7 +542,8 @@ def bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, t
 
     def step(k):
         ti, tf = shifted(traj, k)
-        imu = capi.make_imu_stream(ti, h_imu.data_ptr(), Be, capi.FBUS_MEM_HOST)
+        imu = capi.make_imu_stream(ti, h_imu.data_ptr(), Be, capi.FBUS_MEM_HOST,
+                                   fmt=capi.FBUS_IMU_F32_SENSOR if sensor_f32 else capi.FBUS_IMU_F64_SI)
         det = capi.make_det_frames(tf, h_id.data_ptr(), h_pose.data_ptr(), Be, 1, capi.FBUS_MEM_HOST)
         rc = lib.fbus_step_windows(f2._h, C.byref(imu), C.byref(det), capi.dptr(off, capi.c_uint32_p), 0, W, None, 0)
         assert rc == 0
@@ -553,7 +565,8 @@ def bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, t
     f2.close()
     return {"value": world * Be * (N + W) * K / sec, "unit": UNIT, "h2d_bytes_per_step": int(Be * per_filter + (N + 2 * W + 1) * 8),
             "d2h_bytes_per_step": 64, "filters_per_gpu": Be, "ms_per_step": 1e3 * sec / K,
-            "api": "fbus_step_windows(FBUS_MEM_HOST streams in pinned memory) + fbus_stats -> host",
+            "api": "fbus_step_windows(FBUS_MEM_HOST streams in pinned memory%s) + fbus_stats -> host"
+                   % (", IMU samples as float32 sensor units (FBUS_IMU_F32_SENSOR), converted on the device as main.cpp:254 does" if sensor_f32 else ""),
             "rmse_pos_m_last_step": float(np.sqrt(last[0] / max(last[3], 1.0)))}
 
 

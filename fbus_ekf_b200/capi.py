@@ -17,6 +17,8 @@ LIB_PATH = os.environ.get("FBUS_EKF_LIB", os.path.join(HERE, "libfbus_ekf.so"))
 FBUS_OK, FBUS_E_BADARG, FBUS_E_CUDA, FBUS_E_NOMEM, FBUS_E_STATE = 0, -1, -2, -3, -4
 FBUS_MEM_HOST = 0
 FBUS_MEM_DEVICE = 1
+FBUS_IMU_F64_SI = 0      # double, m/s^2 and rad/s (IMUData)
+FBUS_IMU_F32_SENSOR = 1  # float, g and deg/s (the IMSEE SDK's ImuData; converted on the device as main.cpp:254 does)
 # per-filter status bits (fbus_state_soa.status)
 FBUS_ST_INIT_FAILED, FBUS_ST_RESET_SKIPPED, FBUS_ST_RESET_DONE, FBUS_ST_UPDATE_SKIPPED = 0x1, 0x2, 0x4, 0x8
 FBUS_ST_NONFINITE, FBUS_ST_NO_DETECTION, FBUS_ST_MARKER_REJECTED = 0x10, 0x20, 0x40
@@ -63,12 +65,13 @@ class FbusConfig(C.Structure):
         ("marker_rot", C.c_double * (FBUS_MAX_MARKERS * 9)),
         ("flags", C.c_int32),
         ("reserved", C.c_int32),
+        ("imu_g", C.c_double),
     ]
 
 
 class ImuStream(C.Structure):
     _fields_ = [("n_samples", C.c_size_t), ("batch", C.c_size_t), ("t", c_double_p), ("data", C.c_void_p),
-                ("mem", C.c_int32), ("reserved", C.c_int32)]
+                ("mem", C.c_int32), ("format", C.c_int32)]
 
 
 class DetFrames(C.Structure):
@@ -191,19 +194,25 @@ def dptr(a: np.ndarray, typ=c_double_p):
     return a.ctypes.data_as(typ)
 
 
-def make_imu_stream(t: np.ndarray, data, batch: int, mem: int = FBUS_MEM_HOST, keep: list | None = None) -> ImuStream:
-    """t: [N] float64 host array; data: numpy [N,6,B] (host) or an int device pointer."""
+def make_imu_stream(t: np.ndarray, data, batch: int, mem: int = FBUS_MEM_HOST, keep: list | None = None,
+                    fmt: int | None = None) -> ImuStream:
+    """t: [N] float64 host array; data: numpy [N,6,B] (host; float64 in SI units or float32 in sensor units) or an int
+    device pointer (then `fmt` says what it points to, default FBUS_IMU_F64_SI)."""
     s = ImuStream()
     t = np.ascontiguousarray(t, dtype=np.float64)
     s.n_samples = t.shape[0]
     s.batch = batch
     s.t = dptr(t)
     if isinstance(data, np.ndarray):
-        assert data.dtype == np.float64 and data.flags["C_CONTIGUOUS"] and data.shape == (t.shape[0], 6, batch)
+        assert data.dtype in (np.float64, np.float32) and data.flags["C_CONTIGUOUS"] and data.shape == (t.shape[0], 6, batch)
         s.data = data.ctypes.data
+        if fmt is None:
+            fmt = FBUS_IMU_F32_SENSOR if data.dtype == np.float32 else FBUS_IMU_F64_SI
+        assert (fmt == FBUS_IMU_F32_SENSOR) == (data.dtype == np.float32)
     else:
         s.data = int(data)
     s.mem = mem
+    s.format = FBUS_IMU_F64_SI if fmt is None else fmt
     if keep is not None:
         keep.extend([t, data])
     s._keep = (t, data)
@@ -229,3 +238,25 @@ def make_det_frames(t: np.ndarray, ids, pose, batch: int, max_markers: int, mem:
     d.mem = mem
     d._keep = (t, ids, pose)
     return d
+
+
+REF_M_PI = 3.1415926  # common.hpp:14
+
+
+def sensor_to_si(raw: np.ndarray, imu_g: float) -> np.ndarray:
+    """float32 sensor units [N,6,B] (accel in g, gyro in deg/s) -> float64 SI, operation by operation as main.cpp:254:
+    accel = (double)a * g ; gyro = (double)(w / 180.f) * M_PI   (host mirror of the kernels' conversion, for tests/oracle)"""
+    raw = np.asarray(raw, dtype=np.float32)
+    out = np.empty(raw.shape, dtype=np.float64)
+    out[:, 0:3] = raw[:, 0:3].astype(np.float64) * np.float64(imu_g)
+    out[:, 3:6] = (raw[:, 3:6] / np.float32(180.0)).astype(np.float64) * np.float64(REF_M_PI)
+    return out
+
+
+def si_to_sensor(si: np.ndarray, imu_g: float) -> np.ndarray:
+    """nearest float32 sensor-unit sample of an SI stream (what a simulated IMSEE IMU would deliver)"""
+    si = np.asarray(si, dtype=np.float64)
+    out = np.empty(si.shape, dtype=np.float32)
+    out[:, 0:3] = (si[:, 0:3] / imu_g).astype(np.float32)
+    out[:, 3:6] = (si[:, 3:6] * (180.0 / REF_M_PI)).astype(np.float32)
+    return out

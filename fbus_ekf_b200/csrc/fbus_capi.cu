@@ -122,6 +122,28 @@ int stage(fbus_handle* h, DevBuf& buf, const T* src, size_t count, int mem, cons
     return stage_on(h, buf, src, count, mem, out, h->stream);
 }
 
+// IMU samples of either element format: bytes per value, validation, and the (imu, imu32) pointer pair of the kernels
+inline size_t imu_elem(const fbus_imu_stream* imu) { return imu->format == FBUS_IMU_F32_SENSOR ? sizeof(float) : sizeof(double); }
+inline bool imu_format_ok(const fbus_imu_stream* imu) { return imu->format == FBUS_IMU_F64_SI || imu->format == FBUS_IMU_F32_SENSOR; }
+inline void set_imu_ptr(const fbus_imu_stream* imu, const void* base, const double** p64, const float** p32) {
+    const bool f32 = imu->format == FBUS_IMU_F32_SENSOR;
+    *p64 = f32 ? nullptr : (const double*)base;
+    *p32 = f32 ? (const float*)base : nullptr;
+}
+// stages values [first, first + count) of the stream's bulk array (count values, not samples) if it lives on the host
+int stage_imu(fbus_handle* h, const fbus_imu_stream* imu, size_t first, size_t count, const void** out) {
+    const size_t es = imu_elem(imu);
+    const char* src = (const char*)imu->data + first * es;
+    if (imu->mem == FBUS_MEM_DEVICE) {
+        *out = src;
+        return FBUS_OK;
+    }
+    CUDA_TRY(h, h->imu_data.reserve(count * es));
+    CUDA_TRY(h, cudaMemcpyAsync(h->imu_data.p, src, count * es, cudaMemcpyHostToDevice, h->stream));
+    *out = h->imu_data.p;
+    return FBUS_OK;
+}
+
 int launch_window(fbus_handle* h, WinParams& prm) {
     prm.nom = h->d_nom;
     prm.P = h->d_P;
@@ -135,18 +157,26 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.stagger_cycles = (prm.mode & M_FUSED) ? h->stagger_cycles : 0u;
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
 #if FBUS_SPLIT
+    const bool jo = (h->k.flags & FBUS_FLAG_JOSEPH) != 0, f32 = prm.imu32 != nullptr;
     if (h->small_batch) {
         // fewer 128-filter CTAs than SMs (e.g. BASELINE configs[2], 4 096 filters): 32-filter CTAs (one covariance + one
         // nominal warp) spread the batch over four times as many SMs
         const unsigned g32 = (unsigned)((h->B + 31) / 32);
         const size_t smem32 = (size_t)(NPK + XCH) * 32 * sizeof(double);
-        if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_split_kernel<32, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
+        if (f32) {
+            if (jo) ekf_window_split_kernel<32, true, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
+            else ekf_window_split_kernel<32, false, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
+        } else if (jo) ekf_window_split_kernel<32, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
         else ekf_window_split_kernel<32, false><<<g32, 64, smem32, h->stream>>>(prm, h->k);
-    } else if (WIN_TMEM && h->tri_warp) {
-        // three warps per 32 filters (top-left / nominal / cross blocks), covariance in tensor memory
-        if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_tri_kernel<true><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
+    } else if (WIN_TMEM && h->tri_warp && !f32) {
+        // three warps per 32 filters (top-left / nominal / cross blocks), covariance in tensor memory (experimental; float32
+        // sensor streams always take the two-warp kernel)
+        if (jo) ekf_window_tri_kernel<true><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
         else ekf_window_tri_kernel<false><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
-    } else if (h->k.flags & FBUS_FLAG_JOSEPH) ekf_window_split_kernel<WIN_BS, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
+    } else if (f32) {
+        if (jo) ekf_window_split_kernel<WIN_BS, true, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
+        else ekf_window_split_kernel<WIN_BS, false, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
+    } else if (jo) ekf_window_split_kernel<WIN_BS, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
     else ekf_window_split_kernel<WIN_BS, false><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
 #else
     ekf_window_kernel<WIN_BS><<<grid, WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
@@ -244,6 +274,8 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
 #if FBUS_SPLIT
     e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
 #else
     e = cudaFuncSetAttribute(ekf_window_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
 #endif
@@ -266,6 +298,8 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
         e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
         if (e != cudaSuccess) return bail("cudaFuncSetAttribute(32)", e);
     }
 #endif
@@ -315,14 +349,18 @@ size_t fbus_batch(const fbus_handle* h) { return h ? h->B : 0; }
 void* fbus_stream(fbus_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int fbus_init_gravity_gyrobias(fbus_handle* h, const fbus_imu_stream* imu, size_t first, size_t count) {
-    if (!h || !imu || imu->batch != h->B || first + count > imu->n_samples || !imu->data) return fail(h, FBUS_E_BADARG, "bad imu stream");
+    if (!h || !imu || imu->batch != h->B || first + count > imu->n_samples || !imu->data || !imu_format_ok(imu))
+        return fail(h, FBUS_E_BADARG, "bad imu stream");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (count == 0) return FBUS_OK;
-    const double* d;
-    int rc = stage(h, h->imu_data, imu->data + first * 6 * h->B, count * 6 * h->B, imu->mem, &d);
+    const void* d;
+    int rc = stage_imu(h, imu, first * 6 * h->B, count * 6 * h->B, &d);
     if (rc) return rc;
+    const double* d64;
+    const float* d32;
+    set_imu_ptr(imu, d, &d64, &d32);
     const unsigned grid = (unsigned)((h->B + 127) / 128);
-    init_gravity_kernel<<<grid, 128, 0, h->stream>>>(h->d_nom, h->B, d, 0u, (uint32_t)count);
+    init_gravity_kernel<<<grid, 128, 0, h->stream>>>(h->d_nom, h->B, d64, d32, h->k.imu_g, 0u, (uint32_t)count);
     CUDA_TRY(h, cudaGetLastError());
     return FBUS_OK;
 }
@@ -340,20 +378,20 @@ int fbus_init_position_quaternion(fbus_handle* h, const fbus_det_frames* det, si
 }
 
 int fbus_propagate(fbus_handle* h, const fbus_imu_stream* imu, size_t first, size_t count, double t_end) {
-    if (!h || !imu || imu->batch != h->B || first + count > imu->n_samples || !imu->t || !imu->data)
+    if (!h || !imu || imu->batch != h->B || first + count > imu->n_samples || !imu->t || !imu->data || !imu_format_ok(imu))
         return fail(h, FBUS_E_BADARG, "bad imu stream");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (count == 0) return FBUS_OK;
     WinParams prm;
     memset(&prm, 0, sizeof prm);
     const double* dt;
-    const double* dd;
+    const void* dd;
     int rc = stage(h, h->imu_t, imu->t + first, count, FBUS_MEM_HOST, &dt);
     if (rc) return rc;
-    rc = stage(h, h->imu_data, imu->data + first * 6 * h->B, count * 6 * h->B, imu->mem, &dd);
+    rc = stage_imu(h, imu, first * 6 * h->B, count * 6 * h->B, &dd);
     if (rc) return rc;
     prm.imu_t = dt;
-    prm.imu = dd;
+    set_imu_ptr(imu, dd, &prm.imu, &prm.imu32);
     prm.mode = M_PROP;
     prm.prop_first = 0;
     prm.prop_count = (uint32_t)count;
@@ -411,12 +449,13 @@ static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const 
     if (rc) return rc;
     // bulk arrays: device-resident ones in place; host-resident ones into buffers that hold the range [s0, s1) / [w0, w1),
     // addressed through base pointers shifted back to index 0 (never dereferenced below the range)
-    const double* dimu = imu->data;
+    const size_t es = imu_elem(imu);  // bytes per IMU value: double (SI) or float (sensor units)
+    const char* dimu = (const char*)imu->data;
     const int32_t* did = det->id;
     const double* dpose = det->pose;
     if (imu_host) {
-        CUDA_TRY(h, h->imu_data.reserve((s1 - s0 ? s1 - s0 : 1) * 6 * B * sizeof(double)));
-        dimu = (const double*)h->imu_data.p - s0 * 6 * B;
+        CUDA_TRY(h, h->imu_data.reserve((s1 - s0 ? s1 - s0 : 1) * 6 * B * es));
+        dimu = (const char*)h->imu_data.p - s0 * 6 * B * es;
     }
     if (det_host) {
         CUDA_TRY(h, h->det_id.reserve(nw * m * B * sizeof(int32_t)));
@@ -433,7 +472,7 @@ static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const 
         }
     }
     prm.imu_t = dt;
-    prm.imu = dimu;
+    set_imu_ptr(imu, dimu, &prm.imu, &prm.imu32);
     prm.win_off = doff;
     prm.det_t = ddt;
     prm.det_id = did;
@@ -452,8 +491,8 @@ static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const 
         const size_t e = (a + step < w1) ? a + step : w1;
         const size_t sa = win_off[a], se = win_off[e];
         if (imu_host && se > sa)
-            CUDA_TRY(h, cudaMemcpyAsync((double*)h->imu_data.p + (sa - s0) * 6 * B, imu->data + sa * 6 * B, (se - sa) * 6 * B * sizeof(double),
-                                        cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(h, cudaMemcpyAsync((char*)h->imu_data.p + (sa - s0) * 6 * B * es, (const char*)imu->data + sa * 6 * B * es,
+                                        (se - sa) * 6 * B * es, cudaMemcpyHostToDevice, cs));
         if (det_host) {
             CUDA_TRY(h, cudaMemcpyAsync((int32_t*)h->det_id.p + (a - w0) * m * B, det->id + a * m * B, (e - a) * m * B * sizeof(int32_t),
                                         cudaMemcpyHostToDevice, cs));
@@ -480,7 +519,7 @@ static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const 
 
 int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det_frames* det, const uint32_t* win_off,
                       size_t w0, size_t w1, double* trace, int32_t trace_mem) {
-    if (!h || !imu || !det || !win_off || imu->batch != h->B || !imu->t || !imu->data)
+    if (!h || !imu || !det || !win_off || imu->batch != h->B || !imu->t || !imu->data || !imu_format_ok(imu))
         return fail(h, FBUS_E_BADARG, "fbus_step_windows: bad argument");
     if (w0 >= w1) return (w0 == w1) ? FBUS_OK : fail(h, FBUS_E_BADARG, "fbus_step_windows: w0 > w1");
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -496,7 +535,7 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
     // chunk c+1 runs while chunk c is computed (the state makes one extra HBM round trip per chunk).
     const size_t ch = h->pipeline_frames;
     const bool host_streams = imu->mem == FBUS_MEM_HOST && det->mem == FBUS_MEM_HOST;
-    const size_t bytes = (size_t)(win_off[w1] - win_off[w0]) * 48 * B;
+    const size_t bytes = (size_t)(win_off[w1] - win_off[w0]) * 6 * imu_elem(imu) * B;
     const bool piped = host_streams && ch > 0 && nw >= 2 * ch && bytes >= h->pipeline_min_bytes && h->copy_stream;
     int rc = step_windows_range(h, imu, det, win_off, w0, w1, trace, trace_mem, resume, piped ? ch : 0);
     h->last_imu_data = device_streams ? (const void*)imu->data : nullptr;

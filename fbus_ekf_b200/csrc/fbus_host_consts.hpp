@@ -77,6 +77,7 @@ inline int make_dev_consts(const fbus_config* c, DevConsts* k, MarkerTable* tab)
     k->rod_c = cos(-3.1415926 / 4);
     k->n_markers = c->n_markers;
     k->flags = c->flags;
+    k->imu_g = c->imu_g;
     double Lil[16];
     host_quat_left(k->Q_IL, Lil);
     for (int m = 0; m < c->n_markers; ++m) {
@@ -155,6 +156,7 @@ inline void config_default(fbus_config* c) {
         memcpy(&c->marker_rot[m * 9], R, sizeof I3);
     }
     c->flags = 0;
+    c->imu_g = 9.802;  // camerainfo1.yml "g" (IMUInfo.g, common.hpp:148)
 }
 
 }  // namespace fbus

@@ -506,7 +506,7 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
     }
 }
 
-template <int BSF, bool TM, int WPG = 2>
+template <int BSF, bool TM, int WPG = 2, bool IMU32 = false>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
                                              int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
     constexpr int NT = WPG * BSF, NW = BSF / 32, GS = WPG * 32;  // WPG warps per group of 32 filters
@@ -588,7 +588,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             const bool pfi = (pf_i == lo);
             double s_t = pfi ? pf_st : prm.imu_t[lo], s_d[6];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) s_d[c] = pfi ? pf_sd[c] : prm.imu[((size_t)lo * 6 + c) * B + b];
+            for (int c = 0; c < 6; ++c) s_d[c] = pfi ? pf_sd[c] : imu_sample_t<IMU32>(prm, k.imu_g, lo, c, B, b);
             for (uint32_t i = lo; i < hi; ++i) {
                 const double ti = s_t;
                 double d[6];
@@ -597,7 +597,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                 if (i + 1 < hi) {  // prefetch the next sample
                     s_t = prm.imu_t[i + 1];
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)(i + 1) * 6 + c) * B + b];
+                    for (int c = 0; c < 6; ++c) s_d[c] = imu_sample_t<IMU32>(prm, k.imu_g, (size_t)i + 1, c, B, b);
                 }
                 const int slot = (int)((i - lo) & 1u);
                 int valid = 0;
@@ -662,7 +662,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                 pf_i = cursor;
                 pf_st = prm.imu_t[cursor];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) pf_sd[c] = prm.imu[((size_t)cursor * 6 + c) * B + b];
+                for (int c = 0; c < 6; ++c) pf_sd[c] = imu_sample_t<IMU32>(prm, k.imu_g, cursor, c, B, b);
             }
             plan_frame<BSF>(prm, k, w + 1, b, live, cursor, n.t, inited, prev_id, status, nx);
         }
@@ -729,7 +729,8 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 // same two schedulers.  Each CTA therefore takes an arrival ticket per SM: odd tickets swap the role order (covariance
 // warps on schedulers 2,3 instead of 0,1) and start half a frame period late, so that one CTA's update phase (one busy
 // warp per filter group) overlaps the other's propagation phase.
-template <int BSF, bool JOSEPH>  // filters per CTA; the CTA has 2*BSF threads
+// IMU32: the IMU stream holds float32 sensor samples (FBUS_IMU_F32_SENSOR) instead of doubles
+template <int BSF, bool JOSEPH, bool IMU32 = false>  // filters per CTA; the CTA has 2*BSF threads
 __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
     extern __shared__ double smem[];
     __shared__ SplitShared sh;
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
         tm_base = tm_alloc_cta(&tm_slot);
     }
     if (is_cov) cov_role<BSF, JOSEPH, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
-    else nominal_role<BSF, TM>(prm, k, smem, sh, sflag, fl, b, live);
+    else nominal_role<BSF, TM, 2, IMU32>(prm, k, smem, sh, sflag, fl, b, live);
     if constexpr (TM) tm_free_cta(tm_base);
 }
 

@@ -40,7 +40,8 @@ struct WinParams {
     int32_t* status;   // [B]
     size_t B;
     const double* imu_t;      // device [N]
-    const double* imu;        // [N][6][B]
+    const double* imu;        // [N][6][B]  FBUS_IMU_F64_SI (nullptr when imu32 is set)
+    const float* imu32;       // [N][6][B]  FBUS_IMU_F32_SENSOR: accel in g, gyro in deg/s, or nullptr
     const double* det_t;      // device [W]
     const int32_t* det_id;    // [W][m][B]
     const double* det_pose;   // [W][m][7][B]
@@ -59,6 +60,27 @@ struct WinParams {
     uint32_t stagger_cycles;  // split kernel, 2 CTAs per SM: start delay of odd-ticket CTAs
     uint32_t* sm_ticket;      // split kernel: per-SM arrival counters [256] (device), or nullptr
 };
+
+// One IMU component (c = 0..2 accel, 3..5 gyro).  Float32 sensor samples are converted exactly as the reference's IMU callback
+// does before it builds IMUData (main.cpp:254): accel = (double)a * g, gyro = (double)(w / 180.f) * M_PI with the reference's
+// M_PI = 3.1415926 (common.hpp:14).  The float division is IEEE and the products are rounded on their own (__dmul_rn: the
+// compiler must not contract them into an FMA with whatever consumes the sample), so the filter sees the same doubles as
+// the reference.
+__device__ __forceinline__ double imu_cvt(float f, int c, double imu_g) {
+    return (c < 3) ? __dmul_rn((double)f, imu_g) : __dmul_rn((double)__fdiv_rn(f, 180.0f), 3.1415926);
+}
+// format decided at run time (one-off kernels, un-split window kernel)
+__device__ __forceinline__ double imu_sample(const double* imu, const float* imu32, double imu_g, size_t i, int c, size_t B, size_t b) {
+    const size_t idx = (i * 6 + (size_t)c) * B + b;
+    return imu32 != nullptr ? imu_cvt(imu32[idx], c, imu_g) : imu[idx];
+}
+// format decided at compile time (the hot window kernels have one instantiation per format)
+template <bool IMU32, class PRM>
+__device__ __forceinline__ double imu_sample_t(const PRM& prm, double imu_g, size_t i, int c, size_t B, size_t b) {
+    const size_t idx = (i * 6 + (size_t)c) * B + b;
+    if constexpr (IMU32) return imu_cvt(prm.imu32[idx], c, imu_g);
+    else return prm.imu[idx];
+}
 
 template <int BS>
 __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
@@ -251,7 +273,7 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
             if (lo < hi) {
                 s_t = prm.imu_t[lo];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)lo * 6 + c) * B + b];
+                for (int c = 0; c < 6; ++c) s_d[c] = imu_sample(prm.imu, prm.imu32, k.imu_g, lo, c, B, b);
             }
             for (uint32_t i = lo; i < hi; ++i) {
                 if (SYNC) __syncthreads();
@@ -262,7 +284,7 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
                 if (i + 1 < hi) {  // prefetch the next sample while this one is processed
                     s_t = prm.imu_t[i + 1];
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) s_d[c] = prm.imu[((size_t)(i + 1) * 6 + c) * B + b];
+                    for (int c = 0; c < 6; ++c) s_d[c] = imu_sample(prm.imu, prm.imu32, k.imu_g, (size_t)i + 1, c, B, b);
                 }
                 if (open && i >= p_first && i < p_end) {
                     if (ti < start) {
@@ -351,15 +373,15 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
 }
 
 // K0: FILTER::InitializeGravityAndBias (filter.cpp:256-285)
-__global__ void init_gravity_kernel(double* nom, size_t B, const double* imu, uint32_t first, uint32_t count) {
+__global__ void init_gravity_kernel(double* nom, size_t B, const double* imu, const float* imu32, double imu_g, uint32_t first, uint32_t count) {
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B || count == 0) return;
     double am[3] = {0, 0, 0}, gm[3] = {0, 0, 0};
     for (uint32_t i = first; i < first + count; ++i) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            am[c] = am[c] + imu[((size_t)i * 6 + c) * B + b];
-            gm[c] = gm[c] + imu[((size_t)i * 6 + 3 + c) * B + b];
+            am[c] = am[c] + imu_sample(imu, imu32, imu_g, i, c, B, b);
+            gm[c] = gm[c] + imu_sample(imu, imu32, imu_g, i, 3 + c, B, b);
         }
     }
     const double nn = (double)count;

@@ -79,6 +79,7 @@ struct DevConsts {
     double T_LR_air[12];               // in-air stereo: [R_IR R_IL^T | P_LI - R P_RI], row-major 3x4 (vision.cpp:402-408)
     int32_t air_lt_glass, glass_gt_water;
     int32_t n_markers, flags;
+    double imu_g;                      // IMUInfo.g: scale of float32 sensor accelerations (main.cpp:252-254)
 };
 // marker map: lives in device global memory (dynamic indexing of kernel parameters would force a
 // local-memory copy of the whole table)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FBUS_ABI_VERSION 1
+#define FBUS_ABI_VERSION 2 /* 2: fbus_config.imu_g, fbus_imu_stream.format */
 
 /* error codes */
 #define FBUS_OK 0
@@ -46,6 +46,15 @@ extern "C" {
 /* where a caller-owned data pointer lives */
 #define FBUS_MEM_HOST 0
 #define FBUS_MEM_DEVICE 1
+
+/* element format of fbus_imu_stream.data */
+#define FBUS_IMU_F64_SI 0     /* double, accel in m/s^2 and gyro in rad/s: the fields of IMUData (common.hpp:176-193) */
+#define FBUS_IMU_F32_SENSOR 1 /* float, accel in g and gyro in deg/s: the fields of the IMSEE SDK's ImuData
+                                 (driver/IMSEE-SDK/include/types.h:122-127) as the IMU callback receives them.  The
+                                 kernels convert every sample exactly as main.cpp:254 does before building IMUData --
+                                 accel = (double)a * imu_g, gyro = (double)(w / 180.f) * M_PI with the reference's
+                                 M_PI = 3.1415926 (common.hpp:14) -- so the filter sees bit-identical doubles while a
+                                 host-resident stream needs half the bytes on the way to the device */
 
 /* dimensions of the reference filter (filter.hpp:82-125): 18 error states, 12 noise terms, 7 rows */
 #define FBUS_NX 18
@@ -102,6 +111,7 @@ typedef struct fbus_config {
     double marker_rot[FBUS_MAX_MARKERS * 9];
     int32_t flags;
     int32_t reserved;
+    double imu_g; /* IMUInfo.g (camerainfo*.yml "g": 9.802): scale of FBUS_IMU_F32_SENSOR accelerations, main.cpp:252-254 */
 } fbus_config;
 
 /* Fill *cfg with the values the bundled logs were recorded with: C++/config/camerainfo1.yml,
@@ -116,9 +126,11 @@ typedef struct fbus_imu_stream {
     size_t n_samples;   /* N */
     size_t batch;       /* B, must equal the handle's batch */
     const double* t;    /* [N]        HOST pointer, seconds */
-    const double* data; /* [N][6][B]  accel xyz (m/s^2) then gyro xyz (rad/s); host or device */
+    const double* data; /* [N][6][B]  accel xyz (m/s^2) then gyro xyz (rad/s); host or device.
+                           With format = FBUS_IMU_F32_SENSOR the pointer is a `const float*` in disguise:
+                           [N][6][B] floats, accel xyz (g) then gyro xyz (deg/s) */
     int32_t mem;        /* FBUS_MEM_HOST / FBUS_MEM_DEVICE for `data` */
-    int32_t reserved;
+    int32_t format;     /* FBUS_IMU_F64_SI (0) / FBUS_IMU_F32_SENSOR */
 } fbus_imu_stream;
 
 /*
