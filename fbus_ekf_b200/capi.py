@@ -145,6 +145,7 @@ def lib() -> C.CDLL:
         "fbus_batch": (C.c_size_t, [H]),
         "fbus_stream": (C.c_void_p, [H]),
         "fbus_init_gravity_gyrobias": (C.c_int, [H, C.POINTER(ImuStream), C.c_size_t, C.c_size_t]),
+        "fbus_iir_prefilter": (C.c_int, [H, C.POINTER(ImuStream), C.c_size_t, C.c_size_t, C.c_void_p, C.c_int32]),
         "fbus_init_position_quaternion": (C.c_int, [H, C.POINTER(DetFrames), C.c_size_t, C.c_size_t]),
         "fbus_propagate": (C.c_int, [H, C.POINTER(ImuStream), C.c_size_t, C.c_size_t, C.c_double]),
         "fbus_reset_state": (C.c_int, [H, C.POINTER(DetFrames), C.c_size_t]),
@@ -176,7 +177,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "fbus_config_default", "fbus_create", "fbus_destroy", "fbus_last_error", "fbus_abi_version", "fbus_synchronize",
-    "fbus_batch", "fbus_stream", "fbus_init_gravity_gyrobias", "fbus_init_position_quaternion", "fbus_propagate",
+    "fbus_batch", "fbus_stream", "fbus_init_gravity_gyrobias", "fbus_iir_prefilter", "fbus_init_position_quaternion", "fbus_propagate",
     "fbus_reset_state", "fbus_update", "fbus_step_windows", "fbus_refract_solve", "fbus_inair_solve", "fbus_undistort_fisheye", "fbus_solve_to_detections", "fbus_refract_solve_gn", "fbus_marker_pose", "fbus_get_state",
     "fbus_set_state", "fbus_clear_status", "fbus_stats", "fbus_stats_combine", "fbus_synth_streams", "fbus_quat_from_rotmat",
     "fbus_measure_fp64_peak")

@@ -365,6 +365,34 @@ int fbus_init_gravity_gyrobias(fbus_handle* h, const fbus_imu_stream* imu, size_
     return FBUS_OK;
 }
 
+int fbus_iir_prefilter(fbus_handle* h, const fbus_imu_stream* imu, size_t first, size_t count, double* out, int32_t out_mem) {
+    if (!h || !imu || imu->batch != h->B || first + count > imu->n_samples || !imu->data || !imu_format_ok(imu) || !out ||
+        (out_mem != FBUS_MEM_HOST && out_mem != FBUS_MEM_DEVICE))
+        return fail(h, FBUS_E_BADARG, "fbus_iir_prefilter: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (count == 0) return FBUS_OK;
+    const size_t n = count * 6 * h->B;
+    const void* d;
+    int rc = stage_imu(h, imu, first * 6 * h->B, n, &d);
+    if (rc) return rc;
+    const double* d64;
+    const float* d32;
+    set_imu_ptr(imu, d, &d64, &d32);
+    double* dout = out;
+    if (out_mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, h->scratch_out.reserve(n * sizeof(double)));
+        dout = (double*)h->scratch_out.p;
+    }
+    const unsigned grid = (unsigned)((6 * h->B + 127) / 128);
+    iir_prefilter_kernel<<<grid, 128, 0, h->stream>>>(d64, d32, h->k.imu_g, h->B, 0u, (uint32_t)count, dout);
+    CUDA_TRY(h, cudaGetLastError());
+    if (out_mem == FBUS_MEM_HOST) {
+        CUDA_TRY(h, cudaMemcpyAsync(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
 int fbus_init_position_quaternion(fbus_handle* h, const fbus_det_frames* det, size_t frame, size_t n_imu_before) {
     if (!h) return FBUS_E_BADARG;
     CUDA_TRY(h, cudaSetDevice(h->device));

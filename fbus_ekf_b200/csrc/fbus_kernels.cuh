@@ -372,6 +372,25 @@ __global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ 
     prm.status[b] = status;
 }
 
+// FILTER::SetImuData's 1-pole IIR (filter.cpp:36-48): one thread per (channel, filter) walks the samples in order; the
+// recurrence is two rounded products and a rounded sum per sample (no FMA contraction: the reference has none).  Loads do not
+// depend on the recurrence, so the unrolled loop keeps several in flight.
+__global__ void iir_prefilter_kernel(const double* imu, const float* imu32, double imu_g, size_t B, uint32_t first, uint32_t count, double* out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 6 * B || count == 0) return;
+    const int c = (int)(idx / B);
+    const size_t b = idx % B;
+    const double keep = 1.0 - 0.1, gain = 0.1;  // (1 - filter_coeff), filter_coeff
+    double prev = imu_sample(imu, imu32, imu_g, first, c, B, b);
+    out[(size_t)c * B + b] = prev;
+#pragma unroll 4
+    for (uint32_t i = 1; i < count; ++i) {
+        const double raw = imu_sample(imu, imu32, imu_g, (size_t)first + i, c, B, b);
+        prev = __dadd_rn(__dmul_rn(prev, keep), __dmul_rn(raw, gain));
+        out[((size_t)i * 6 + c) * B + b] = prev;
+    }
+}
+
 // K0: FILTER::InitializeGravityAndBias (filter.cpp:256-285)
 __global__ void init_gravity_kernel(double* nom, size_t B, const double* imu, const float* imu32, double imu_g, uint32_t first, uint32_t count) {
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -59,6 +59,18 @@ class BatchFilter:
     def InitGravityAndGyrobias(self, imu: capi.ImuStream, first: int, count: int):
         self._ck(self._lib.fbus_init_gravity_gyrobias(self._h, C.byref(imu), first, count))
 
+    def IirPrefilter(self, imu: capi.ImuStream, first: int, count: int, out=None, mem: int = capi.FBUS_MEM_HOST):
+        """FILTER::SetImuData's 1-pole IIR (filter.cpp:36-48) over samples [first, first+count), restarted at `first`.
+        -> float64 [count][6][B] in SI units: a new numpy array, the given numpy array, or the given device pointer"""
+        if mem == capi.FBUS_MEM_HOST:
+            if out is None:
+                out = np.empty((count, 6, self.batch))
+            assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == count * 6 * self.batch
+            self._ck(self._lib.fbus_iir_prefilter(self._h, C.byref(imu), first, count, out.ctypes.data, mem))
+        else:
+            self._ck(self._lib.fbus_iir_prefilter(self._h, C.byref(imu), first, count, int(out), mem))
+        return out
+
     def InitPositionAndQuaternion(self, det: capi.DetFrames, frame: int, n_imu_before: int = 1):
         self._ck(self._lib.fbus_init_position_quaternion(self._h, C.byref(det), frame, n_imu_before))
 

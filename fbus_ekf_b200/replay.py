@@ -13,14 +13,22 @@ from . import capi
 from .filter import BatchFilter
 
 
-def iir_prefilter(imu: np.ndarray, restart_at=()) -> np.ndarray:
-    """FILTER::SetImuData's 1-pole IIR (filter.cpp:36-48): f[i] = 0.9 f[i-1] + 0.1 raw[i]; restarts on an empty buffer."""
-    out = imu.copy()
-    restarts = set(restart_at) | {0}
-    for i in range(len(imu)):
-        if i in restarts:
-            continue
-        out[i, 1:7] = out[i - 1, 1:7] * (1 - 0.1) + imu[i, 1:7] * 0.1
+def iir_prefilter(imu: np.ndarray, restart_at=(), device: int = 0) -> np.ndarray:
+    """FILTER::SetImuData's 1-pole IIR (filter.cpp:36-48) on log rows `t a(3) g(3)`: f[i] = 0.9 f[i-1] + 0.1 raw[i], restarted
+    at row 0 and at every row of `restart_at` (where the live buffer was empty).  Runs on the GPU (fbus_iir_prefilter)."""
+    n = len(imu)
+    out = np.array(imu, dtype=np.float64, copy=True)
+    if n == 0:
+        return out
+    f = BatchFilter(None, batch=1, device=device)
+    try:
+        data = np.ascontiguousarray(out[:, 1:7, None])
+        stream = capi.make_imu_stream(np.ascontiguousarray(out[:, 0]), data, 1)
+        cuts = sorted({0, n} | {int(r) for r in restart_at if 0 < int(r) < n})
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            out[a:b, 1:7] = f.IirPrefilter(stream, a, b - a)[:, :, 0]
+    finally:
+        f.close()
     return out
 
 
@@ -105,7 +113,7 @@ def replay_log(imu: np.ndarray, image_rows: np.ndarray, cfg=None, n_init: int = 
     Returns dict(rows [W,17] of filter 0 in the data/fusion.txt layout, state, filter).
     `buffer_cap` (e.g. IMU_BUFFER_MAX_SIZE) applies the live system's bounded IMU buffer to detection gaps."""
     if use_iir:
-        imu = iir_prefilter(imu, restart_at=(n_init,))
+        imu = iir_prefilter(imu, restart_at=(n_init,), device=device)
     if buffer_cap:
         imu = imu[buffer_cap_keep(imu[:, 0], group_frames(image_rows)[0], n_init, buffer_cap)]
     f = BatchFilter(cfg, batch=batch, device=device)

@@ -279,6 +279,15 @@ int fbus_refract_solve_gn(fbus_handle* h, const void* corners, int32_t corner_dt
    data/corners.txt layout, vision.cpp:120-124). */
 int fbus_marker_pose(fbus_handle* h, const double* corners3d, size_t n, double* pose, int32_t mem);
 
+/* FILTER::SetImuData's 1-pole pre-filter (filter.cpp:36-48) over samples [first, first + count) of a stream, per filter and
+   channel: out[0] = in[first] (the reference pushes the first sample of an empty buffer unfiltered), then
+   out[i] = out[i-1] * (1 - 0.1) + in[first + i] * 0.1 -- two rounded products and one rounded sum, as the Eigen expression
+   evaluates; nothing is contracted into an FMA.  `in` may be of either element format; `out` is [count][6][B] doubles in SI
+   units (host or device; for a device-resident FBUS_IMU_F64_SI stream it may alias the input samples: in place).
+   A caller restarts the recurrence wherever the live buffer was empty (after InitializeGravityAndBias: one call per
+   stretch). */
+int fbus_iir_prefilter(fbus_handle* h, const fbus_imu_stream* in, size_t first, size_t count, double* out, int32_t out_mem);
+
 /* ---- state access ------------------------------------------------------------------------- */
 
 int fbus_get_state(fbus_handle* h, fbus_state_soa* out); /* synchronises */

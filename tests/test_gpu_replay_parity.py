@@ -13,7 +13,8 @@ def _oracle_replay(cfg, imu, image_rows, n_init=500, use_iir=False):
     import orc
     from fbus_ekf_b200 import capi, replay
     if use_iir:
-        imu = replay.iir_prefilter(imu, restart_at=(n_init,))
+        import fbus_oracle_np
+        imu = fbus_oracle_np.iir_prefilter(imu, restart_at=(n_init,))
     o = orc.Oracle(cfg, 1)
     t_imu = np.ascontiguousarray(imu[:, 0])
     data = np.ascontiguousarray(imu[:, 1:7, None])

@@ -118,3 +118,33 @@ def test_unfused_calls_and_bad_format(cfg):
     import ctypes as C
     assert capi.lib().fbus_propagate(f._h, C.byref(bad), 0, 5, float("inf")) == capi.FBUS_E_BADARG
     assert capi.lib().fbus_step_windows(f._h, C.byref(bad), C.byref(det), capi.dptr(np.ascontiguousarray(traj["win_off"], dtype=np.uint32), capi.c_uint32_p), 0, 1, None, 0) == capi.FBUS_E_BADARG
+
+
+def test_iir_prefilter_on_the_device(cfg, golden):
+    """fbus_iir_prefilter == the oracle's restatement of SetImuData's recurrence, bit for bit (two rounded products and a
+    rounded sum per sample, no FMA); both element formats, host and device outputs, in place, restarts"""
+    import fbus_oracle_np
+    import torch
+    from fbus_ekf_b200 import BatchFilter, capi, replay
+    imu = golden["land_imu"][:6000]
+    want = fbus_oracle_np.iir_prefilter(imu, restart_at=(500, 4100))
+    got = replay.iir_prefilter(imu, restart_at=(500, 4100))
+    assert np.array_equal(got, want)
+    # batch of filters, float32 sensor samples in, device-resident out
+    B = 130
+    traj, raw, si, ids, pose = _streams(cfg, B, 0.5, seed=51)
+    N = raw.shape[0]
+    f = BatchFilter(cfg, batch=B)
+    ref = np.empty_like(si)
+    for b in range(0, B, 43):
+        rows = np.concatenate([traj["t_imu"][:, None], si[:, :, b]], axis=1)
+        ref[:, :, b] = fbus_oracle_np.iir_prefilter(rows)[:, 1:7]
+    out_h = f.IirPrefilter(capi.make_imu_stream(traj["t_imu"], raw, B), 0, N)
+    assert np.array_equal(out_h[:, :, ::43], ref[:, :, ::43])
+    si_d = torch.from_numpy(si).cuda()
+    s_d = capi.make_imu_stream(traj["t_imu"], si_d.data_ptr(), B, capi.FBUS_MEM_DEVICE)
+    f.IirPrefilter(s_d, 0, N, out=si_d.data_ptr(), mem=capi.FBUS_MEM_DEVICE)   # in place
+    f.Synchronize()
+    assert np.array_equal(si_d.cpu().numpy(), out_h)
+    part = f.IirPrefilter(capi.make_imu_stream(traj["t_imu"], si, B), 10, 25)
+    assert np.array_equal(part[0], si[10]) and part.shape == (25, 6, B)

@@ -16,12 +16,13 @@ def test_group_frames_and_windows():
     assert list(off) == [1, 3, 6, 8]
 
 
-def test_iir_prefilter_matches_reference_recurrence():
-    """SetImuData: first sample raw, then 0.9*previous filtered + 0.1*raw (filter.cpp:36-48)"""
-    from fbus_ekf_b200 import replay
+def test_oracle_iir_is_the_reference_recurrence():
+    """SetImuData: first sample raw, then 0.9*previous filtered + 0.1*raw (filter.cpp:36-48); the GPU version
+    (fbus_iir_prefilter) is checked against this one in tests/test_gpu_sensor_f32.py"""
+    import fbus_oracle_np
     rng = np.random.default_rng(0)
     imu = np.concatenate([np.arange(20)[:, None] * 0.001, rng.normal(size=(20, 6))], axis=1)
-    out = replay.iir_prefilter(imu, restart_at=(10,))
+    out = fbus_oracle_np.iir_prefilter(imu, restart_at=(10,))
     assert np.array_equal(out[0], imu[0]) and np.array_equal(out[10], imu[10])
     assert np.allclose(out[3, 1:], 0.9 * out[2, 1:] + 0.1 * imu[3, 1:], atol=0, rtol=0)
     assert np.array_equal(out[:, 0], imu[:, 0])
