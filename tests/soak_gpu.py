@@ -1,6 +1,6 @@
 """Randomised GPU-vs-oracle soak of the window kernel (not collected by pytest; run on a B200: python tests/soak_gpu.py [iterations]).
 Every iteration draws a batch size (ragged), a stream length, a pattern of dropped detections / unknown marker ids / far markers
-and a kernel path (32-filter shared-memory CTAs, 128-filter tensor-memory CTAs, three-warp variant), runs the fused windows on the
+and a kernel path (32-filter shared-memory CTAs, 128-filter tensor-memory CTAs, three-warp variant) and an IMU element format, runs the fused windows on the
 GPU and in the CPU oracle and compares status words bit for bit, trace rows and covariance to 1e-9."""
 import os
 import sys
@@ -44,7 +44,14 @@ def one(it, rng, cfg):
     pose[:, :, 0:3, :] = np.where(far[:, :, None, :], pose[:, :, 0:3, :] * 40.0, pose[:, :, 0:3, :])
     id_d.copy_(torch.from_numpy(ids))
     pose_d.copy_(torch.from_numpy(pose))
-    imu = capi.make_imu_stream(traj["t_imu"], imu_d.data_ptr(), B, capi.FBUS_MEM_DEVICE)
+    sensor = bool(rng.random() < 0.4)                                # IMU samples as float32 sensor units (FBUS_IMU_F32_SENSOR)
+    if sensor:
+        raw = np.ascontiguousarray(capi.si_to_sensor(imu_d.cpu().numpy(), cfg.imu_g))
+        raw_d = torch.from_numpy(raw).cuda()
+        imu_d.copy_(torch.from_numpy(capi.sensor_to_si(raw, cfg.imu_g)))   # what the oracle gets: main.cpp:254 applied on the host
+        imu = capi.make_imu_stream(traj["t_imu"], raw_d.data_ptr(), B, capi.FBUS_MEM_DEVICE, fmt=capi.FBUS_IMU_F32_SENSOR)
+    else:
+        imu = capi.make_imu_stream(traj["t_imu"], imu_d.data_ptr(), B, capi.FBUS_MEM_DEVICE)
     det = capi.make_det_frames(traj["t_frames"], id_d.data_ptr(), pose_d.data_ptr(), B, 1, capi.FBUS_MEM_DEVICE)
     cut = int(rng.integers(0, W + 1))                                # two launches: the state must carry over
     tr1 = f.StepWindows(imu, det, traj["win_off"], 0, cut, trace=True) if cut > 0 else np.zeros((0, 17, B))
@@ -64,7 +71,7 @@ def one(it, rng, cfg):
     same_nan = np.array_equal(np.isfinite(tr_g), fin)
     okP = cov_close(sg["P"], so["P"], 1e-9)[0]
     ok = ok_status and err <= 1e-9 and okP and same_nan
-    print(f"{it:3d} {path:8s} B={B:3d} W={W:2d} cut={cut:2d} status={'ok' if ok_status else 'DIFF'} trace_err={err:.2e} cov={'ok' if okP else 'DIFF'}"
+    print(f"{it:3d} {path:8s} {'f32' if sensor else 'f64'} B={B:3d} W={W:2d} cut={cut:2d} status={'ok' if ok_status else 'DIFF'} trace_err={err:.2e} cov={'ok' if okP else 'DIFF'}"
           f" {'' if ok else '  <-- FAIL'}", flush=True)
     return ok
 
