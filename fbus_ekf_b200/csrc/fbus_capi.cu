@@ -23,6 +23,7 @@ namespace {
 #ifndef FBUS_WIN_BS
 #define FBUS_WIN_BS 128
 #endif
+constexpr size_t PACK_MAX = (size_t)256 << 10;  // host-resident calls up to this many input bytes take the packed single-copy path
 constexpr int WIN_BS = FBUS_WIN_BS;  // filters per CTA of the window kernel (171*WIN_BS*8 B of shared memory)
 // 1 (default): warp-specialised window kernel, 2*WIN_BS threads per CTA (covariance warps + nominal warps);
 // 0: one thread per filter does everything (kept for A/B measurements)
@@ -87,6 +88,11 @@ struct fbus_handle {
     // second staging set + copy stream: host-resident streams are copied chunk c+1 while chunk c is computed
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // small host-resident calls (the live single-filter use: one frame, ~8 IMU samples per call): every input array is packed into
+    // one pinned buffer and goes to the device in ONE copy instead of six pageable ones
+    char* pack_host = nullptr;  // pinned, PACK_MAX bytes
+    char* pack_dev = nullptr;
+    cudaEvent_t ev_pack = nullptr;  // the last packed copy has left pack_host
     size_t pipeline_frames = 2;  // frames per chunk of the host-stream pipeline (FBUS_PIPELINE_FRAMES, 0 = off)
     std::string err;
 };
@@ -254,6 +260,9 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
+    if ((e = cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMallocHost((void**)&h->pack_host, PACK_MAX)) != cudaSuccess) return bail("cudaMallocHost pack", e);
+    if ((e = cudaMalloc((void**)&h->pack_dev, PACK_MAX)) != cudaSuccess) return bail("cudaMalloc pack", e);
     if (const char* pf = getenv("FBUS_PIPELINE_FRAMES")) h->pipeline_frames = (size_t)strtoul(pf, nullptr, 10);
     if (const char* pm = getenv("FBUS_PIPELINE_MIN_MB")) h->pipeline_min_bytes = (size_t)strtoul(pm, nullptr, 10) << 20;
     if ((e = cudaMalloc(&h->d_nom, sizeof(double) * NOM_FIELDS * batch)) != cudaSuccess) return bail("cudaMalloc nom", e);
@@ -327,6 +336,9 @@ int fbus_destroy(fbus_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nom); cudaFree(h->d_P); cudaFree(h->d_prev); cudaFree(h->d_init); cudaFree(h->d_status); cudaFree(h->d_tab); cudaFree(h->d_ticket); cudaFree(h->d_cursor);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_pack) cudaEventDestroy(h->ev_pack);
+    if (h->pack_host) cudaFreeHost(h->pack_host);
+    cudaFree(h->pack_dev);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -465,27 +477,55 @@ static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const 
     const bool imu_host = imu->mem == FBUS_MEM_HOST, det_host = det->mem == FBUS_MEM_HOST;
     WinParams prm;
     memset(&prm, 0, sizeof prm);
+    const size_t es = imu_elem(imu);  // bytes per IMU value: double (SI) or float (sensor units)
+    // Small host-resident call (the live use: one filter, one frame): all six input arrays travel in one pinned buffer and one copy.
+    // Layout (16-byte aligned pieces): t[0, s1) | det_t[0, w1) | pose[w0, w1) | imu[s0, s1) | win_off[0, w1] | id[w0, w1)
+    auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t nb_t = al16((s1 ? s1 : 1) * sizeof(double)), nb_dt = al16(w1 * sizeof(double)), nb_pose = al16(nw * m * 7 * B * sizeof(double));
+    const size_t nb_imu = al16((s1 - s0) * 6 * B * es), nb_off = al16((w1 + 1) * sizeof(uint32_t)), nb_id = al16(nw * m * B * sizeof(int32_t));
+    const size_t nb_all = nb_t + nb_dt + nb_pose + nb_imu + nb_off + nb_id;
+    const bool packed = imu_host && det_host && chunk_frames == 0 && h->pack_host && nb_all <= PACK_MAX;
     // small host arrays, staged in full so that absolute indices work: t[0, s1), win_off[0, w1], det_t[0, w1)
     const double* dt;
     const double* ddt;
     const uint32_t* doff;
-    int rc = stage(h, h->imu_t, imu->t, s1 ? s1 : 1, FBUS_MEM_HOST, &dt);
-    if (rc) return rc;
-    rc = stage(h, h->win_off, win_off, w1 + 1, FBUS_MEM_HOST, &doff);
-    if (rc) return rc;
-    rc = stage(h, h->det_t, det->t, w1, FBUS_MEM_HOST, &ddt);
-    if (rc) return rc;
+    int rc;
     // bulk arrays: device-resident ones in place; host-resident ones into buffers that hold the range [s0, s1) / [w0, w1),
     // addressed through base pointers shifted back to index 0 (never dereferenced below the range)
-    const size_t es = imu_elem(imu);  // bytes per IMU value: double (SI) or float (sensor units)
     const char* dimu = (const char*)imu->data;
     const int32_t* did = det->id;
     const double* dpose = det->pose;
-    if (imu_host) {
+    if (packed) {
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_pack));  // the previous packed copy has read the pinned buffer
+        char* ph = h->pack_host;
+        const size_t o_t = 0, o_dt = o_t + nb_t, o_pose = o_dt + nb_dt, o_imu = o_pose + nb_pose, o_off = o_imu + nb_imu, o_id = o_off + nb_off;
+        if (s1) memcpy(ph + o_t, imu->t, s1 * sizeof(double));
+        memcpy(ph + o_dt, det->t, w1 * sizeof(double));
+        memcpy(ph + o_pose, det->pose + w0 * m * 7 * B, nw * m * 7 * B * sizeof(double));
+        if (s1 > s0) memcpy(ph + o_imu, (const char*)imu->data + s0 * 6 * B * es, (s1 - s0) * 6 * B * es);
+        memcpy(ph + o_off, win_off, (w1 + 1) * sizeof(uint32_t));
+        memcpy(ph + o_id, det->id + w0 * m * B, nw * m * B * sizeof(int32_t));
+        CUDA_TRY(h, cudaMemcpyAsync(h->pack_dev, ph, nb_all, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_pack, h->stream));
+        dt = (const double*)(h->pack_dev + o_t);
+        ddt = (const double*)(h->pack_dev + o_dt);
+        doff = (const uint32_t*)(h->pack_dev + o_off);
+        dimu = h->pack_dev + o_imu - s0 * 6 * B * es;
+        did = (const int32_t*)(h->pack_dev + o_id) - w0 * m * B;
+        dpose = (const double*)(h->pack_dev + o_pose) - w0 * m * 7 * B;
+    } else {
+        rc = stage(h, h->imu_t, imu->t, s1 ? s1 : 1, FBUS_MEM_HOST, &dt);
+        if (rc) return rc;
+        rc = stage(h, h->win_off, win_off, w1 + 1, FBUS_MEM_HOST, &doff);
+        if (rc) return rc;
+        rc = stage(h, h->det_t, det->t, w1, FBUS_MEM_HOST, &ddt);
+        if (rc) return rc;
+    }
+    if (imu_host && !packed) {
         CUDA_TRY(h, h->imu_data.reserve((s1 - s0 ? s1 - s0 : 1) * 6 * B * es));
         dimu = (const char*)h->imu_data.p - s0 * 6 * B * es;
     }
-    if (det_host) {
+    if (det_host && !packed) {
         CUDA_TRY(h, h->det_id.reserve(nw * m * B * sizeof(int32_t)));
         CUDA_TRY(h, h->det_pose.reserve(nw * m * 7 * B * sizeof(double)));
         did = (const int32_t*)h->det_id.p - w0 * m * B;
@@ -518,10 +558,10 @@ static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const 
     for (size_t a = w0; a < w1; a += step, ++c) {
         const size_t e = (a + step < w1) ? a + step : w1;
         const size_t sa = win_off[a], se = win_off[e];
-        if (imu_host && se > sa)
+        if (imu_host && !packed && se > sa)
             CUDA_TRY(h, cudaMemcpyAsync((char*)h->imu_data.p + (sa - s0) * 6 * B * es, (const char*)imu->data + sa * 6 * B * es,
                                         (se - sa) * 6 * B * es, cudaMemcpyHostToDevice, cs));
-        if (det_host) {
+        if (det_host && !packed) {
             CUDA_TRY(h, cudaMemcpyAsync((int32_t*)h->det_id.p + (a - w0) * m * B, det->id + a * m * B, (e - a) * m * B * sizeof(int32_t),
                                         cudaMemcpyHostToDevice, cs));
             CUDA_TRY(h, cudaMemcpyAsync((double*)h->det_pose.p + (a - w0) * m * 7 * B, det->pose + a * m * 7 * B,
