@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -364,6 +364,7 @@ def run_ours(args):
     solves = bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak) if not args.no_solves else None
 
     config4 = bench_config4(cfg, dev, local, rank, world, K, Wm) if not args.no_solves else None
+    config4_tol = bench_config4(cfg, dev, local, rank, world, K, Wm, gn_tol=1e-8) if not args.no_solves else None
 
     # ---- e2e: HOST buffers through the C ABI, H2D of every step's streams + D2H of the step's statistics -------------
     e2e = bench_e2e(cfg, traj, imu_d, id_d, pose_d, B, local, dev, world, K, Wm, tp, tq) if not args.no_e2e else None
@@ -379,7 +380,7 @@ def run_ours(args):
                 "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(B, world), "e2e": e2e, "e2e_sensor_f32": e2e_f32, "gpu_launches": K,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "stats": stats, "solves": solves,
-                "small_batch": small, "single_filter": single, "config4": config4,
+                "small_batch": small, "single_filter": single, "config4": config4, "config4_gn_tol": config4_tol,
                 "timing": "CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks"}
         print(json.dumps(line), file=JSON_OUT or sys.stdout, flush=True)
     if world > 1:
@@ -443,7 +444,29 @@ def bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak):
     g1.record(stream)
     f.Synchronize()
     gn_rate = n * g_iters / (g0.elapsed_time(g1) * 1e-3)
-    return {"metric": "refractive solves/sec", "value": rate * world, "gauss_newton_5it_solves_per_s": gn_rate * world, "unit": "solves/s", "markers_per_launch": n,
+    # the same with the convergence stop (fbus_config.gn_tol = 1e-8, at most 5 iterations; north_star's pose tolerance is 1e-8): a second handle, same markers
+    import copy
+    from fbus_ekf_b200 import BatchFilter
+    cfg_t = copy.copy(cfg)
+    cfg_t.gn_tol = 1e-8
+    ft = BatchFilter(cfg_t, batch=1, device=dev.index)
+    t_stream = torch.cuda.ExternalStream(ft.stream, device=dev)
+    pose_t = torch.empty_like(pose)
+    for i in range(2):
+        lib.fbus_refract_solve_gn(ft._h, corners[i % reps].data_ptr(), 0, n, 5, pose_t.data_ptr(), cost.data_ptr(), valid.data_ptr(), capi.FBUS_MEM_DEVICE)
+    ft.Synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(t_stream)
+    for i in range(g_iters):
+        lib.fbus_refract_solve_gn(ft._h, corners[i % reps].data_ptr(), 0, n, 5, pose_t.data_ptr(), cost.data_ptr(), valid.data_ptr(),
+                                  capi.FBUS_MEM_DEVICE)
+    g1.record(t_stream)
+    ft.Synchronize()
+    gn_tol_rate = n * g_iters / (g0.elapsed_time(g1) * 1e-3)
+    gn_tol_diff = float((pose_t - pose).abs().max().item())  # same markers (last launch of both loops): converged vs 5 iterations
+    ft.close()
+    return {"metric": "refractive solves/sec", "value": rate * world, "gauss_newton_5it_solves_per_s": gn_rate * world,
+            "gauss_newton_tol1e-8_max5it_solves_per_s": gn_tol_rate * world, "gauss_newton_tol_vs_5it_max_abs_diff": gn_tol_diff, "unit": "solves/s", "markers_per_launch": n,
             "ms_per_launch": sec * 1e3, "valid_fraction": float(valid.float().mean().item()),
             "e2e": {"value": e2e_rate * world, "unit": "solves/s", "h2d_bytes_per_step": 64 * n, "d2h_bytes_per_step": 60 * n},
             "roofline": {"kernel": "refract_kernel", "bound": "fp64", "achieved": rate * FLOP_SOLVE / 1e12, "peak": fp64_peak / 1e12,
@@ -452,13 +475,14 @@ def bench_solves(f, cfg, dev, stream, K, Wm, world, fp64_peak, hbm_peak):
                                  "frac": rate * BYTES_SOLVE / 1e9 / hbm_peak}}}
 
 
-def bench_config4(cfg, dev, local, rank, world, K, Wm):
+def bench_config4(cfg, dev, local, rank, world, K, Wm, gn_tol=0.0):
     """BASELINE configs[3]: 65,536 filters, per frame 8 board markers x 4 corners x stereo -> refractive solve with 5
     Gauss-Newton iterations -> detection frames -> EKF (nearest of 8 markers), device-resident; one step = 1 s of stream."""
     import torch
     from fbus_ekf_b200 import BatchFilter, capi, synth
     B4, m, gn = env_int("FBUS_BENCH_BATCH4", 65536), 8, 5
     bcfg = synth.board_config(cfg)
+    bcfg.gn_tol = gn_tol
     traj = synth.truth_trajectory(bcfg, PERIOD, IMU_RATE, FRAME_RATE, periodic=True, standoff=1.0)
     N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
     base, ids, _ = synth.board_base_corners(bcfg, traj)
@@ -499,7 +523,8 @@ def bench_config4(cfg, dev, local, rank, world, K, Wm):
                        "iterations -> detections -> EKF, 1 s of 200 Hz IMU + 25 Hz frames per step",
            "filters_per_gpu": B4, "ms_per_step": sec * 1e3, "filter_steps_per_s": world * B4 * (N + W) / sec,
            "refractive_gn_solves_per_s": world * n / sec, "rmse_pos_m": float(np.sqrt(np.mean(err ** 2))),
-           "finite": bool(np.isfinite(st["p"]).all()), "gpu_launches_per_step": 2}
+           "finite": bool(np.isfinite(st["p"]).all()), "gpu_launches_per_step": 2,
+           "gn": "exactly 5 iterations" if gn_tol <= 0 else f"at most 5 iterations, a marker stops once an applied step is below {gn_tol:g} (fbus_config.gn_tol)"}
     f.close()
     return out
 

@@ -66,6 +66,7 @@ class FbusConfig(C.Structure):
         ("flags", C.c_int32),
         ("reserved", C.c_int32),
         ("imu_g", C.c_double),
+        ("gn_tol", C.c_double),
     ]
 
 

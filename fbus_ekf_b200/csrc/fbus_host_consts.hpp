@@ -104,6 +104,7 @@ inline void make_gn_consts(const fbus_config* c, const DevConsts* k, GnConsts* g
     g->d0 = c->d_air; g->d1 = c->d_glass;
     g->k1 = c->n_air / c->n_glass; g->k2 = c->n_air / c->n_water;
     g->size = c->marker_size;
+    g->tol = c->gn_tol;
     for (int i = 0; i < 3; ++i) g->P_LR[i] = k->P_LR[i];
     const double* m = k->R_RL;
     const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);

@@ -367,6 +367,7 @@ struct GnConsts {
     double d0, d1, k1, k2;       // air / glass thickness, n_air/n_glass, n_air/n_water
     double R_RL_inv[9], P_LR[3];  // TRUE inverse of R_RL (the calibration is ~2.5e-6 non-orthonormal)
     double size;                  // marker side (0.28 m, vision.hpp:114)
+    double tol;                   // > 0: stop iterating once an applied step is below this in every component (fbus_config.gn_tol)
 };
 
 // projects X (camera frame) -> uv (2) and, when JAC, the 2x3 Jacobian d(uv)/dX (row-major J[0..2] = du/dX,
@@ -575,6 +576,12 @@ FBUS_HD double gn_refine(const GnConsts& g, const double* c, double* Rm, double*
             for (int cc = 0; cc < 3; ++cc) Rn[r * 3 + cc] = Rm[r * 3] * E[cc] + Rm[r * 3 + 1] * E[3 + cc] + Rm[r * 3 + 2] * E[6 + cc];
         FBUS_UNROLL
         for (int e = 0; e < 9; ++e) Rm[e] = Rn[e];
+        if (g.tol > 0.0) {  // converged: the step just applied is below the tolerance (a warp goes on until its last lane is)
+            double dn = fabs(d[0]);
+            FBUS_UNROLL
+            for (int i = 1; i < 6; ++i) dn = fmax(dn, fabs(d[i]));
+            if (dn < g.tol) break;
+        }
     }
     if (FINAL_COST) cost = gn_normal_eq<false>(g, c, Rm, p, nullptr, nullptr, sw);
     return cost;

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FBUS_ABI_VERSION 2 /* 2: fbus_config.imu_g, fbus_imu_stream.format */
+#define FBUS_ABI_VERSION 2 /* 2: fbus_config.imu_g / gn_tol, fbus_imu_stream.format, fbus_iir_prefilter */
 
 /* error codes */
 #define FBUS_OK 0
@@ -112,6 +112,11 @@ typedef struct fbus_config {
     int32_t flags;
     int32_t reserved;
     double imu_g; /* IMUInfo.g (camerainfo*.yml "g": 9.802): scale of FBUS_IMU_F32_SENSOR accelerations, main.cpp:252-254 */
+    double gn_tol; /* Gauss-Newton refinement (fbus_refract_solve_gn, gn_iters of fbus_solve_to_detections): 0 (default) runs
+                      exactly the requested number of iterations; > 0 stops a marker as soon as an applied step is smaller than
+                      this in every component (metres / radians).  The iteration contracts by ~1e-2 per step at the
+                      logs' corner noise (~0.2 at ten times that noise), so the result agrees with the fixed count to well
+                      below gn_tol */
 } fbus_config;
 
 /* Fill *cfg with the values the bundled logs were recorded with: C++/config/camerainfo1.yml,
