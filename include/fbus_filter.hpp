@@ -96,7 +96,7 @@ class FILTER {
     // (StartFilterThread) this does the same; without one the frame body (init | reset -> propagate -> update,
     // filter.cpp:207-235) runs on the GPU before this call returns.
     void SetDetectionResultUpdated() {
-        if (thread_.joinable()) {
+        if (threaded_.load()) {  // producers never touch the std::thread object itself
             std::lock_guard<std::mutex> lk(cv_mu_);
             pending_ = true;
             cv_.notify_one();
@@ -112,10 +112,12 @@ class FILTER {
         if (thread_.joinable()) return;
         stop_ = false;
         ready_ = false;
+        threaded_.store(true);
         thread_ = std::thread(&FILTER::FilterThreadFunction, this, init_wait_ms);
     }
     void JoinFilterThread() {
         if (thread_.joinable()) thread_.join();
+        threaded_.store(false);
     }
     void StopFilterThread() {
         {
@@ -156,7 +158,7 @@ class FILTER {
     // the live callers never wait).  Rethrows an error the thread ran into.
     void WaitIdle() {
         std::unique_lock<std::mutex> lk(cv_mu_);
-        idle_.wait(lk, [&] { return !thread_.joinable() || (ready_ && !pending_ && !busy_); });
+        idle_.wait(lk, [&] { return !threaded_.load() || (ready_ && !pending_ && !busy_); });
         if (!thread_error_.empty()) throw std::runtime_error("fbus filter thread: " + thread_error_);
     }
 
@@ -305,6 +307,7 @@ class FILTER {
     std::mutex mu_;  // buffers + handle (the reference's imuMutex / imgMutex / visualMutex in one)
     // filter thread (the reference's ekfMutex + ekfCondVar, with a pending flag instead of a bare wait)
     std::thread thread_;
+    std::atomic<bool> threaded_{false};
     std::mutex cv_mu_;
     std::condition_variable cv_, idle_;
     bool pending_ = false, busy_ = false, ready_ = false, stop_ = false;
