@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBUS_EKF_LIB", os.path.join(HERE, "libfbus_ekf.so"))
 
 FBUS_OK, FBUS_E_BADARG, FBUS_E_CUDA, FBUS_E_NOMEM, FBUS_E_STATE = 0, -1, -2, -3, -4
+FBUS_ABI_VERSION = 2  # include/fbus_ekf.h
 FBUS_MEM_HOST = 0
 FBUS_MEM_DEVICE = 1
 FBUS_IMU_F64_SI = 0      # double, m/s^2 and rad/s (IMUData)
@@ -172,6 +173,9 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    if L.fbus_abi_version() != FBUS_ABI_VERSION:
+        raise RuntimeError(f"fbus_ekf_b200: {LIB_PATH} has ABI version {L.fbus_abi_version()}, this binding mirrors version "
+                           f"{FBUS_ABI_VERSION} of include/fbus_ekf.h -- rebuild with __graft_entry__.build()")
     _lib = L
     return L
 
