@@ -45,6 +45,7 @@ class FILTER {
     static constexpr size_t IMU_BUFFER_MAX_SIZE = 2000;  // filter.hpp:25
 
     explicit FILTER(const fbus_config& cfg, int device = 0, bool iir = true) : iir_(iir), cfg_(cfg) {
+        if (fbus_abi_version() != FBUS_ABI_VERSION) throw std::runtime_error("libfbus_ekf.so was built from another version of fbus_ekf.h");
         if (fbus_create(&h_, &cfg, device, 1) != FBUS_OK) throw std::runtime_error(std::string("fbus_create: ") + fbus_last_error(nullptr));
     }
     ~FILTER() {
