@@ -78,7 +78,7 @@ struct fbus_handle {
     uint32_t stagger_cycles = 0;
     size_t pipeline_min_bytes = (size_t)64 << 20;  // host streams smaller than this are staged and processed in one go
     bool small_batch = false;
-    bool tri_warp = false;  // large batches: three-warp window kernel (FBUS_TRI_WARP=1) instead of the two-warp one
+    bool tri_warp = false;  // -DFBUS_ENABLE_TRI=1 builds only: three-warp window kernel (FBUS_TRI_WARP=1) instead of the two-warp one
     double* d_nom = nullptr;
     double* d_P = nullptr;
     int32_t* d_prev = nullptr;
@@ -174,11 +174,13 @@ int launch_window(fbus_handle* h, WinParams& prm) {
             else ekf_window_split_kernel<32, false, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
         } else if (jo) ekf_window_split_kernel<32, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
         else ekf_window_split_kernel<32, false><<<g32, 64, smem32, h->stream>>>(prm, h->k);
+#if FBUS_ENABLE_TRI
     } else if (WIN_TMEM && h->tri_warp && !f32) {
-        // three warps per 32 filters (top-left / nominal / cross blocks), covariance in tensor memory (experimental; float32
-        // sensor streams always take the two-warp kernel)
+        // three warps per 32 filters (top-left / nominal / cross blocks), covariance in tensor memory (experimental build only;
+        // float32 sensor streams always take the two-warp kernel)
         if (jo) ekf_window_tri_kernel<true><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
         else ekf_window_tri_kernel<false><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
+#endif
     } else if (f32) {
         if (jo) ekf_window_split_kernel<WIN_BS, true, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
         else ekf_window_split_kernel<WIN_BS, false, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
@@ -298,12 +300,14 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         // to ~3e9 filter-steps/s beyond (three small CTAs per SM), where the large CTAs keep scaling with the SMs they fill
         h->small_batch = WIN_BS > 32 && (batch + 31) / 32 <= 2 * (size_t)prop.multiProcessorCount;
         if (const char* sb = getenv("FBUS_SMALL_BATCH")) h->small_batch = atoi(sb) != 0;
+#if FBUS_ENABLE_TRI
         if (const char* tw = getenv("FBUS_TRI_WARP")) h->tri_warp = atoi(tw) != 0;
         if (WIN_TMEM) {
             e = cudaFuncSetAttribute(ekf_window_tri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_tri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
             if (e != cudaSuccess) return bail("cudaFuncSetAttribute(tri)", e);
         }
+#endif
         const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
         e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);

@@ -769,6 +769,14 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
     if constexpr (TM) tm_free_cta(tm_base);
 }
 
+// 0 (default): the experimental three-warp kernel below is NOT part of the library.  It lost to the two-warp kernel and
+// a compute-sanitizer memcheck run of the log replay through it ended with a covariance mismatch that the plain run does not show
+// (timing-dependent hand-over between its cross and top-left warps, or the tool's register use under setmaxnreg -- not resolved),
+// so it is kept as source for the record only: build with -DFBUS_ENABLE_TRI=1 to experiment with it (FBUS_TRI_WARP=1 then selects it).
+#ifndef FBUS_ENABLE_TRI
+#define FBUS_ENABLE_TRI 0
+#endif
+#if FBUS_ENABLE_TRI
 #ifndef FBUS_TRI_SETMAXNREG
 #define FBUS_TRI_SETMAXNREG 1
 #endif
@@ -808,5 +816,6 @@ __global__ void __launch_bounds__(384, 1) ekf_window_tri_kernel(const __grid_con
     }
     tm_free_cta(tm_base);
 }
+#endif  // FBUS_ENABLE_TRI
 
 }  // namespace fbus

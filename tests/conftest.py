@@ -52,20 +52,19 @@ def cfg(built):
 
 # The window kernel has two covariance stores: tensor memory (128-filter CTAs, chosen when the batch fills the GPU) and
 # shared memory (32-filter CTAs, small batches).  The parity tests work on small batches, so the modules listed here run
-# three times: with the library's own choice, with FBUS_SMALL_BATCH=0, which forces the tensor-memory kernel, and with
-# FBUS_TRI_WARP=1 on top of that (the experimental three-warp variant of the tensor-memory kernel).
+# twice: with the library's own choice and with FBUS_SMALL_BATCH=0, which forces the tensor-memory kernel.
 _BOTH_PATHS = ("test_gpu_step_parity", "test_gpu_replay_parity", "test_gpu_synth_batch")
 
 
 def pytest_generate_tests(metafunc):
     if metafunc.module.__name__.split(".")[-1] in _BOTH_PATHS and "cov_store" in metafunc.fixturenames:
-        metafunc.parametrize("cov_store", ["auto", "tmem", "tri"], indirect=True)
+        metafunc.parametrize("cov_store", ["auto", "tmem"], indirect=True)
 
 
 @pytest.fixture(autouse=True)
 def cov_store(request):
     mode = getattr(request, "param", "auto")
-    want = {"auto": {}, "tmem": {"FBUS_SMALL_BATCH": "0"}, "tri": {"FBUS_SMALL_BATCH": "0", "FBUS_TRI_WARP": "1"}}[mode]
+    want = {"auto": {}, "tmem": {"FBUS_SMALL_BATCH": "0"}}[mode]
     old = {k: os.environ.get(k) for k in want}
     os.environ.update(want)
     yield mode
