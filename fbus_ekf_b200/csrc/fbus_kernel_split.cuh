@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
 
 // 0 (default): the experimental three-warp kernel below is NOT part of the library.  It lost to the two-warp kernel and
 // a compute-sanitizer memcheck run of the log replay through it ended with a covariance mismatch that the plain run does not show
-// (timing-dependent hand-over between its cross and top-left warps, or the tool's register use under setmaxnreg -- not resolved),
+// (also with setmaxnreg compiled out: a timing-dependent ordering hole in the mbarrier hand-over between its cross and top-left warps),
 // so it is kept as source for the record only: build with -DFBUS_ENABLE_TRI=1 to experiment with it (FBUS_TRI_WARP=1 then selects it).
 #ifndef FBUS_ENABLE_TRI
 #define FBUS_ENABLE_TRI 0
