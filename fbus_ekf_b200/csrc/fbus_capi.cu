@@ -24,19 +24,10 @@ namespace {
 #define FBUS_WIN_BS 128
 #endif
 constexpr size_t PACK_MAX = (size_t)256 << 10;  // host-resident calls up to this many input bytes take the packed single-copy path
-constexpr int WIN_BS = FBUS_WIN_BS;  // filters per CTA of the window kernel (171*WIN_BS*8 B of shared memory)
-// 1 (default): warp-specialised window kernel, 2*WIN_BS threads per CTA (covariance warps + nominal warps);
-// 0: one thread per filter does everything (kept for A/B measurements)
-#ifndef FBUS_SPLIT
-#define FBUS_SPLIT 1
-#endif
-#if FBUS_SPLIT
+constexpr int WIN_BS = FBUS_WIN_BS;  // filters per CTA of the window kernel; the CTA has 2*WIN_BS threads (covariance + nominal warps)
 // the 128-filter CTAs keep P in tensor memory (FBUS_TMEM): shared memory then only holds the exchange area
 constexpr bool WIN_TMEM = (FBUS_TMEM != 0) && WIN_BS == 128;
 constexpr size_t WIN_SMEM = (size_t)((WIN_TMEM ? 0 : NPK) + XCH) * WIN_BS * sizeof(double);
-#else
-constexpr size_t WIN_SMEM = (size_t)NPK * WIN_BS * sizeof(double);
-#endif
 
 thread_local std::string g_last_error;
 
@@ -78,7 +69,6 @@ struct fbus_handle {
     uint32_t stagger_cycles = 0;
     size_t pipeline_min_bytes = (size_t)64 << 20;  // host streams smaller than this are staged and processed in one go
     bool small_batch = false;
-    bool tri_warp = false;  // -DFBUS_ENABLE_TRI=1 builds only: three-warp window kernel (FBUS_TRI_WARP=1) instead of the two-warp one
     double* d_nom = nullptr;
     double* d_P = nullptr;
     int32_t* d_prev = nullptr;
@@ -150,6 +140,13 @@ int stage_imu(fbus_handle* h, const fbus_imu_stream* imu, size_t first, size_t c
     return FBUS_OK;
 }
 
+// the continuation rule of fbus_step_windows ends here: the next fused call starts with an empty IMU buffer at win_off[w0]
+inline void forget_stream_position(fbus_handle* h) {
+    h->last_imu_data = nullptr;
+    h->last_n_samples = 0;
+    h->last_w1 = 0;
+}
+
 int launch_window(fbus_handle* h, WinParams& prm) {
     prm.nom = h->d_nom;
     prm.P = h->d_P;
@@ -162,7 +159,6 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.cursor_io = h->d_cursor;
     prm.stagger_cycles = (prm.mode & M_FUSED) ? h->stagger_cycles : 0u;
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
-#if FBUS_SPLIT
     const bool jo = (h->k.flags & FBUS_FLAG_JOSEPH) != 0, f32 = prm.imu32 != nullptr;
     if (h->small_batch) {
         // fewer 128-filter CTAs than SMs (e.g. BASELINE configs[2], 4 096 filters): 32-filter CTAs (one covariance + one
@@ -174,21 +170,11 @@ int launch_window(fbus_handle* h, WinParams& prm) {
             else ekf_window_split_kernel<32, false, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
         } else if (jo) ekf_window_split_kernel<32, true><<<g32, 64, smem32, h->stream>>>(prm, h->k);
         else ekf_window_split_kernel<32, false><<<g32, 64, smem32, h->stream>>>(prm, h->k);
-#if FBUS_ENABLE_TRI
-    } else if (WIN_TMEM && h->tri_warp && !f32) {
-        // three warps per 32 filters (top-left / nominal / cross blocks), covariance in tensor memory (experimental build only;
-        // float32 sensor streams always take the two-warp kernel)
-        if (jo) ekf_window_tri_kernel<true><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
-        else ekf_window_tri_kernel<false><<<grid, 384, WIN_SMEM, h->stream>>>(prm, h->k);
-#endif
     } else if (f32) {
         if (jo) ekf_window_split_kernel<WIN_BS, true, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
         else ekf_window_split_kernel<WIN_BS, false, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
     } else if (jo) ekf_window_split_kernel<WIN_BS, true><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
     else ekf_window_split_kernel<WIN_BS, false><<<grid, 2 * WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
-#else
-    ekf_window_kernel<WIN_BS><<<grid, WIN_BS, WIN_SMEM, h->stream>>>(prm, h->k);
-#endif
     CUDA_TRY(h, cudaGetLastError());
     return FBUS_OK;
 }
@@ -282,16 +268,11 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     }
     if ((e = cudaMalloc(&h->d_tab, sizeof(MarkerTable))) != cudaSuccess) return bail("cudaMalloc marker table", e);
     if ((e = cudaMemcpy(h->d_tab, &h->tab, sizeof(MarkerTable), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("marker table copy", e);
-#if FBUS_SPLIT
     e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<WIN_BS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
-#else
-    e = cudaFuncSetAttribute(ekf_window_kernel<WIN_BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
-#endif
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute", e);
-#if FBUS_SPLIT
     {
         cudaDeviceProp prop;
         if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
@@ -300,14 +281,6 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         // to ~3e9 filter-steps/s beyond (three small CTAs per SM), where the large CTAs keep scaling with the SMs they fill
         h->small_batch = WIN_BS > 32 && (batch + 31) / 32 <= 2 * (size_t)prop.multiProcessorCount;
         if (const char* sb = getenv("FBUS_SMALL_BATCH")) h->small_batch = atoi(sb) != 0;
-#if FBUS_ENABLE_TRI
-        if (const char* tw = getenv("FBUS_TRI_WARP")) h->tri_warp = atoi(tw) != 0;
-        if (WIN_TMEM) {
-            e = cudaFuncSetAttribute(ekf_window_tri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_tri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
-            if (e != cudaSuccess) return bail("cudaFuncSetAttribute(tri)", e);
-        }
-#endif
         const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
         e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
@@ -315,14 +288,9 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
         if (e != cudaSuccess) return bail("cudaFuncSetAttribute(32)", e);
     }
-#endif
     if (getenv("FBUS_DEBUG")) {
         int nb = -1;
-#if FBUS_SPLIT
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_window_split_kernel<WIN_BS, false>, 2 * WIN_BS, WIN_SMEM);
-#else
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_window_kernel<WIN_BS>, WIN_BS, WIN_SMEM);
-#endif
         fprintf(stderr, "[fbus] window kernel: %d filters/CTA, %zu B dynamic smem, %d CTA(s)/SM\n", WIN_BS, WIN_SMEM, nb);
     }
     const unsigned grid = (unsigned)((batch + 127) / 128);
@@ -369,6 +337,7 @@ int fbus_init_gravity_gyrobias(fbus_handle* h, const fbus_imu_stream* imu, size_
         return fail(h, FBUS_E_BADARG, "bad imu stream");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (count == 0) return FBUS_OK;
+    forget_stream_position(h);  // InitializeGravityAndBias clears the IMU buffer (filter.cpp:279)
     const void* d;
     int rc = stage_imu(h, imu, first * 6 * h->B, count * 6 * h->B, &d);
     if (rc) return rc;
@@ -418,6 +387,7 @@ int fbus_init_position_quaternion(fbus_handle* h, const fbus_det_frames* det, si
     if (rc) return rc;
     prm.mode = M_INIT;
     prm.n_imu_before = (uint32_t)n_imu_before;
+    forget_stream_position(h);  // the un-fused initialisation stands outside any fused call's IMU buffer
     return launch_window(h, prm);
 }
 
@@ -503,7 +473,7 @@ static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const 
         CUDA_TRY(h, cudaEventSynchronize(h->ev_pack));  // the previous packed copy has read the pinned buffer
         char* ph = h->pack_host;
         const size_t o_t = 0, o_dt = o_t + nb_t, o_pose = o_dt + nb_dt, o_imu = o_pose + nb_pose, o_off = o_imu + nb_imu, o_id = o_off + nb_off;
-        if (s1) memcpy(ph + o_t, imu->t, s1 * sizeof(double));
+        if (s1) memcpy(ph + o_t, imu->t, s1 * sizeof(double));  // s1 == 0: nothing of imu->t is read (the kernel indexes no sample)
         memcpy(ph + o_dt, det->t, w1 * sizeof(double));
         memcpy(ph + o_pose, det->pose + w0 * m * 7 * B, nw * m * 7 * B * sizeof(double));
         if (s1 > s0) memcpy(ph + o_imu, (const char*)imu->data + s0 * 6 * B * es, (s1 - s0) * 6 * B * es);
@@ -518,8 +488,13 @@ static int step_windows_range(fbus_handle* h, const fbus_imu_stream* imu, const 
         did = (const int32_t*)(h->pack_dev + o_id) - w0 * m * B;
         dpose = (const double*)(h->pack_dev + o_pose) - w0 * m * 7 * B;
     } else {
-        rc = stage(h, h->imu_t, imu->t, s1 ? s1 : 1, FBUS_MEM_HOST, &dt);
-        if (rc) return rc;
+        if (s1) {
+            rc = stage(h, h->imu_t, imu->t, s1, FBUS_MEM_HOST, &dt);
+            if (rc) return rc;
+        } else {  // an empty sample range: imu->t may be empty too, the kernel indexes no sample
+            CUDA_TRY(h, h->imu_t.reserve(sizeof(double)));
+            dt = (const double*)h->imu_t.p;
+        }
         rc = stage(h, h->win_off, win_off, w1 + 1, FBUS_MEM_HOST, &doff);
         if (rc) return rc;
         rc = stage(h, h->det_t, det->t, w1, FBUS_MEM_HOST, &ddt);
@@ -610,9 +585,10 @@ int fbus_step_windows(fbus_handle* h, const fbus_imu_stream* imu, const fbus_det
     const size_t bytes = (size_t)(win_off[w1] - win_off[w0]) * 6 * imu_elem(imu) * B;
     const bool piped = host_streams && ch > 0 && nw >= 2 * ch && bytes >= h->pipeline_min_bytes && h->copy_stream;
     int rc = step_windows_range(h, imu, det, win_off, w0, w1, trace, trace_mem, resume, piped ? ch : 0);
-    h->last_imu_data = device_streams ? (const void*)imu->data : nullptr;
+    // a failed call leaves nothing to continue from
+    h->last_imu_data = (device_streams && rc == FBUS_OK) ? (const void*)imu->data : nullptr;
     h->last_n_samples = imu->n_samples;
-    h->last_w1 = w1;
+    h->last_w1 = (rc == FBUS_OK) ? w1 : 0;
     return rc;
 }
 
@@ -809,6 +785,7 @@ int fbus_get_state(fbus_handle* h, fbus_state_soa* out) {
 int fbus_set_state(fbus_handle* h, const fbus_state_soa* in) {
     if (!h || !in || in->batch != h->B) return fail(h, FBUS_E_BADARG, "fbus_set_state: bad argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    forget_stream_position(h);  // an overwritten state does not continue the previous fused call's IMU buffer
     const size_t B = h->B;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     struct { const double* src; int field; int n; } f[] = {{in->t, F_T, 1}, {in->q, F_Q, 4}, {in->R, F_R, 9}, {in->p, F_P, 3},

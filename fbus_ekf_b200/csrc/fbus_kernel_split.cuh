@@ -17,29 +17,15 @@
 // meanwhile the nominal warp plans the next frame.  Variants that were measured and dropped (cooperative update, deeper
 // mbarrier ring, register-resident blocks across frames, ...) are listed in DESIGN.md; the git history has their code.
 //
-// Numerically identical to ekf_window_kernel (same device functions, same order of operations per filter).
 #pragma once
 
 #include "fbus_kernels.cuh"
 #include "fbus_tmem.cuh"
 
-// 1 (default): the covariance warp keeps the top-left 9x9 block of P in registers while it propagates a window
-#ifndef FBUS_TL_REGS
-#define FBUS_TL_REGS 1
-#endif
 // 1 (default): the 128-filter CTAs keep the covariance in TENSOR MEMORY (one TMEM lane per filter, fbus_tmem.cuh) instead
 // of shared memory; the 32-filter CTAs of small batches (several per SM) always use shared memory
 #ifndef FBUS_TMEM
 #define FBUS_TMEM 1
-#endif
-// 1: the per-sample ring barrier is private to a warp pair (64 threads); the CTA re-aligns once per frame
-#ifndef FBUS_PAIR_BARRIER
-#define FBUS_PAIR_BARRIER 1
-#endif
-// 1: one CTA-wide barrier per frame (all warps loop over the CTA's common IMU range and re-align on the same code);
-// 0: warp pairs are fully independent (needs FBUS_PAIR_BARRIER), each loops over its own range
-#ifndef FBUS_FRAME_CTA_BARRIER
-#define FBUS_FRAME_CTA_BARRIER 1
 #endif
 
 namespace fbus {
@@ -50,39 +36,17 @@ constexpr int XCH = 54;  // doubles of exchange area per filter: ring 2 x 22 (+ 
 // different program counters; whole warps take each path, and arrivals are counted per barrier id)
 template <int NT>
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
-// per-sample barrier: either the whole CTA or only the covariance + nominal warp of one filter group (ids 2..9)
-template <int NT, int GS = 64>
-__device__ __forceinline__ void step_bar(int pair) {
-#if FBUS_PAIR_BARRIER
-    asm volatile("bar.sync %0, %1;" ::"r"(pair + 2), "n"(GS) : "memory");
-#else
-    (void)pair;
-    cta_bar<NT>();
-#endif
-}
-// three-warp kernel: "new cross blocks of block column kk stored" -- one mbarrier per filter group and column (32 arrivals
-// from the cross warp, the top-left warp waits on the phase parity = parity of the step count); the per-sample rendezvous of
-// the three warps keeps the producer at most one phase ahead
-__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mb_arrive(uint64_t* bar) {  // release: everything this thread did before is visible to the waiter
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {  // acquire; the warp reconverges afterwards
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    } while (!ok);
-    __syncwarp();
-}
-
+// per-sample barrier, private to the covariance + nominal warp of one filter group (barrier ids 2..9); the CTA re-aligns
+// once per frame with cta_bar
+__device__ __forceinline__ void step_bar(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 2) : "memory"); }
 struct SplitShared {
-    uint32_t lo_hi[2][8];   // per nominal warp: min first / max end of the candidate IMU range
-    int32_t any_upd[8];     // per nominal warp: some filter requests an update
-    uint64_t col_done[4][3];  // three-warp kernel: mbarriers "cross blocks of block column kk stored", per filter group
+    // per nominal warp: min first / max end of the candidate IMU range.  Double-buffered by frame parity: a nominal warp
+    // posts frame w+1's range after passing only its pair-private barriers, while warps of OTHER pairs may still be
+    // reading frame w's entries (they read after the CTA barrier (a) of frame w); with two copies the writer of frame w+2
+    // -- which has passed barrier (a) of frame w+1, i.e. after every reader of frame w arrived there -- is the first to
+    // touch frame w's copy again.
+    uint32_t lo_hi[2][2][8];
+    int32_t any_upd[8];     // per nominal warp: some filter requests an update (pair-private: written before (r), read after)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -137,97 +101,18 @@ __device__ __forceinline__ void tl_store_any(const CV P, const double* TL) {
     }
 }
 
-template <int NT>
-__device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) {
-#if FBUS_PAIR_BARRIER
-    return sh.any_upd[wq];
-#else
-    int any = sh.any_upd[0];
-#pragma unroll
-    for (int q = 1; q < NT / 64; ++q) any |= sh.any_upd[q];
-    return any;
-#endif
-}
-
-// three-warp kernel: hand-over inside a propagate step (see propagate_cov_core PART 1 / 2)
-struct CrossWait {   // top-left warp: wait for a block column of the step with parity `par`
-    uint64_t* bars;
-    uint32_t par;
-    __device__ __forceinline__ void begin(int kk) const {
-        mb_wait(bars + kk, par);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    __device__ __forceinline__ void end(int) const {}
-};
-struct CrossSignal {  // cross warp: a block column is stored
-    uint64_t* bars;
-    __device__ __forceinline__ void begin(int) const {}
-    __device__ __forceinline__ void end(int kk) const {
-        tm_wait_st();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mb_arrive(bars + kk);
-    }
-};
-
-// ------------------------------------------------------------------------------------------------------------------
-// CROSS role (three-warp kernel only): the cross blocks P[0:9, 9:18] of every propagate step and the process noise on
-// the bias diagonals; everything else of the frame is done by the other two warps, this one only keeps their barriers.
-// ------------------------------------------------------------------------------------------------------------------
-template <int BSF>
-__device__ __forceinline__ void cross_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh, int32_t (*sflag)[BSF],
-                                           int fl, uint32_t tm_base) {
-    constexpr int NT = 3 * BSF, NW = BSF / 32, GS = 96;
-    CovTM2 P;
-    P.base = __shfl_sync(0xffffffffu, tm_base + ((uint32_t)((threadIdx.x >> 5) & 3) << 21), 0);
-    const double* const X = smem + fl;
-    const int wq = fl >> 5;
-    for (uint32_t w = prm.w0; w < prm.w1; ++w) {
-#if FBUS_FRAME_CTA_BARRIER || !FBUS_PAIR_BARRIER
-        cta_bar<NT>();  // (a)
-        uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
-#pragma unroll
-        for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
-#else
-        step_bar<NT, GS>(wq);  // (a)
-        const uint32_t lo = sh.lo_hi[0][wq], hi = sh.lo_hi[1][wq];
-#endif
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");  // the update of the previous frame rewrote the blocks
-        for (uint32_t i = lo; i < hi; ++i) {
-            step_bar<NT, GS>(wq);  // record (i) is complete
-            const int slot = (int)((i - lo) & 1u);
-            const int valid = sflag[slot][fl];
-            if (__any_sync(0xffffffffu, valid)) {
-                const double* rec = X + (size_t)slot * 22 * BSF;
-                double A[9], Bm[9];
-#pragma unroll
-                for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * BSF]; Bm[e] = rec[(size_t)(9 + e) * BSF]; }
-                const double u0 = rec[(size_t)18 * BSF], u1 = rec[(size_t)19 * BSF], u2 = rec[(size_t)20 * BSF];
-                const double dt = rec[(size_t)21 * BSF];
-                double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
-                if (!valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;
-                propagate_cov_core<BSF, false, false, CovTM2, 2>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, nullptr, CrossSignal{&sh.col_done[wq][0]});
-                P.cur ^= 1u;
-            }
-        }
-        P.tr_home();  // the update works on the home positions
-        tm_wait_st();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        step_bar<NT, GS>(wq);  // (r)
-        if (pair_any<NT>(sh, wq)) step_bar<NT, GS>(wq);  // (d)
-    }
-}
+__device__ __forceinline__ int pair_any(const SplitShared& sh, int wq) { return sh.any_upd[wq]; }
 
 // ------------------------------------------------------------------------------------------------------------------
 // COVARIANCE role: owns P (shared memory; top-left 9x9 in registers while propagating)
 // ------------------------------------------------------------------------------------------------------------------
-template <int BSF, bool JOSEPH, bool TM, int WPG = 2>
+template <int BSF, bool JOSEPH, bool TM>
 __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh, int32_t (*sflag)[BSF],
                                          int fl, size_t b, bool live, uint32_t tm_base) {
-    constexpr int NT = WPG * BSF, NW = BSF / 32, GS = WPG * 32;  // WPG warps per group of 32 filters
+    constexpr int NT = 2 * BSF, NW = BSF / 32;
     constexpr int NPS = TM ? 0 : NPK;  // doubles of P per filter in shared memory
     const size_t B = prm.B;
-    static_assert(WPG == 2 || TM, "the three-warp kernel keeps the covariance in tensor memory");
-    using CV = typename std::conditional<WPG == 3, CovTM2, typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type>::type;
+    using CV = typename std::conditional<TM, CovTM<false>, Cov<BSF>>::type;
     CV P;
     if constexpr (TM) {
         // lane 32*(warp%4) in bits 31..16; broadcast from lane 0 so that the compiler knows the address is warp-uniform and
@@ -237,7 +122,6 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
     else P.s = smem + fl;
     double* const X = smem + (size_t)NPS * BSF + fl;
     const int wq = fl >> 5;
-    uint32_t nstep = 0;  // three-warp kernel: propagate steps executed so far (phase parity of the column mbarriers)
     if constexpr (TM) {
         FBUS_UNROLL
         for (int bj = 0; bj < 6; ++bj)
@@ -255,24 +139,18 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
         for (int e = 0; e < NPK; ++e) smem[e * BSF + fl] = prm.P[(size_t)e * B + b];
     }
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
-#if FBUS_FRAME_CTA_BARRIER || !FBUS_PAIR_BARRIER
         cta_bar<NT>();  // (a) the nominal warps have posted their IMU ranges
-        uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
+        const int fp = (int)((w - prm.w0) & 1u);
+        uint32_t lo = sh.lo_hi[fp][0][0], hi = sh.lo_hi[fp][1][0];
 #pragma unroll
-        for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
-#else
-        step_bar<NT, GS>(wq);  // (a) this pair's nominal warp has posted its IMU range
-        const uint32_t lo = sh.lo_hi[0][wq], hi = sh.lo_hi[1][wq];
-#endif
+        for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[fp][0][q]); hi = max(hi, sh.lo_hi[fp][1][q]); }
         int fs = 0;  // ring slot that carries the update request
         if (lo < hi) {
             fs = (int)((hi - lo) & 1u);
-#if FBUS_TL_REGS
             double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
             tl_load_any<TM>(P, TL);
-#endif
             for (uint32_t i = lo; i < hi; ++i) {
-                step_bar<NT, GS>(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
+                step_bar(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
                 const int slot = (int)((i - lo) & 1u);
                 const int valid = sflag[slot][fl];
                 // tensor-memory accesses are warp-wide: a warp with any valid lane runs the step on all lanes, the
@@ -287,30 +165,13 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                     double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
                     if (TM && !valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;  // the record of an invalid sample is all zeros
                     P.fence_st();  // the previous step's stores
-                    if constexpr (WPG == 3) {
-                        // three-warp kernel: this warp does the top-left block (phase 1 from the old cross blocks, then the
-                        // fold of the NEW cross blocks, which the cross warp computes meanwhile)
-                        static_assert(FBUS_TL_REGS, "three-warp kernel: top-left block in registers");
-                        propagate_cov_core<BSF, false, true, CV, 1>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL, CrossWait{&sh.col_done[wq][0], nstep & 1u});
-                        P.cur ^= 1u;
-                        ++nstep;
-                    } else {
-#if FBUS_TL_REGS
-                        propagate_cov_core<BSF, false, true>(P, A, Bm, u0, u1, u2, dt, Qv, nullptr, TL);
-#else
-                        propagate_cov_core<BSF>(P, A, Bm, u0, u1, u2, dt, Qv);
-#endif
-                    }
+                    propagate_cov_core<BSF, true>(P, A, Bm, u0, u1, u2, dt, Qv, TL);
                 }
             }
-#if FBUS_TL_REGS
             tl_store_any<TM>(P, TL);
-#endif
         }
-        if constexpr (WPG == 3) P.cur = 0;  // the cross warp moves its blocks home before (r)
-        step_bar<NT, GS>(wq);  // (r) update request posted (normally long before this warp gets here)
-        if constexpr (WPG == 3) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (pair_any<NT>(sh, wq)) {
+        step_bar(wq);  // (r) update request posted (normally long before this warp gets here)
+        if (pair_any(sh, wq)) {
             const int req = sflag[2][fl];
             if (TM ? true : (req != 0)) {  // tensor memory: all lanes, the ones without a request with zero gain
                 const double* rq = X + (size_t)fs * 22 * BSF;
@@ -342,8 +203,7 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #pragma unroll
                 for (int c = 0; c < 4; ++c) X[(size_t)(26 + c) * BSF] = t.q[c];
             }
-            if constexpr (WPG == 3) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            step_bar<NT, GS>(wq);  // (d) results posted
+            step_bar(wq);  // (d) results posted
         }
     }
     if constexpr (TM) {
@@ -378,6 +238,7 @@ struct FramePlan {
     bool do_prop, apply_init, apply_reset;
     int req;                 // marker index + 1 of the update, 0 = no update
     uint32_t p_first, p_end;
+    uint32_t n_init_erase;   // F6b: imuCnt, the leading buffered samples not later than the frame (filter.cpp:299-305)
     double t_det, t_end;
     double y[7];             // measurement of the update (p, q of the chosen detection)
     double qv[4], pv[3];     // vision-only pose for init / reset
@@ -393,6 +254,7 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
     pl.do_prop = pl.apply_init = pl.apply_reset = false;
     pl.req = 0;
     pl.p_first = pl.p_end = 0;
+    pl.n_init_erase = 0;
     pl.t_det = pl.t_end = 0.0;
     bool do_update = false;
     int n_det = 0, idx_near = 0, idx_prev = 0;
@@ -427,7 +289,11 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
             do_init = true;
             n_before = 0;
             const uint32_t hi = prm.win_off[w + 1];
-            for (uint32_t i = cursor; i < hi; ++i) n_before += (prm.imu_t[i] <= pl.t_det) ? 1u : 0u;
+            for (uint32_t i = cursor; i < hi; ++i) {  // the reference's loop stops at the first later sample
+                if (prm.imu_t[i] > pl.t_det) break;
+                ++n_before;
+            }
+            pl.n_init_erase = n_before;
         } else {
             do_reset = pl.do_prop = do_update = true;
             pl.p_first = cursor;
@@ -506,10 +372,10 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
     }
 }
 
-template <int BSF, bool TM, int WPG = 2, bool IMU32 = false>
+template <int BSF, bool TM, bool IMU32 = false>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
                                              int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
-    constexpr int NT = WPG * BSF, NW = BSF / 32, GS = WPG * 32;  // WPG warps per group of 32 filters
+    constexpr int NT = 2 * BSF, NW = BSF / 32;
     const size_t B = prm.B;
     double* const X = smem + (size_t)(TM ? 0 : NPK) * BSF + fl;
     const bool fused = (prm.mode & M_FUSED) != 0;
@@ -550,7 +416,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             for (int i = 0; i < 3; ++i) n.p[i] = pl.pv[i];
             n.g[0] = 9.8; n.g[1] = 0.0; n.g[2] = 0.0;  // filter.cpp:387
             inited = 1;
-            if (fused) cursor = prm.win_off[w + 1];  // consumed IMU samples erased (filter.cpp:390)
+            if (fused) cursor += pl.n_init_erase;  // only the samples not later than the frame are erased (filter.cpp:299-305,390)
         }
         if (pl.apply_reset) {
             n.t = pl.t_det;
@@ -565,20 +431,16 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         const int req = pl.req;
 
         // ---- F3 BatchImuProcessing (filter.cpp:483-531): one sample ahead of the covariance warp -------------
+        const int fp = (int)((w - prm.w0) & 1u);  // copy of the range table this frame uses (see SplitShared)
         {
             const uint32_t vlo = __reduce_min_sync(0xffffffffu, do_prop ? p_first : 0xffffffffu);
             const uint32_t vhi = __reduce_max_sync(0xffffffffu, do_prop ? p_end : 0u);
-            if ((fl & 31) == 0) { sh.lo_hi[0][wq] = vlo; sh.lo_hi[1][wq] = vhi; }
+            if ((fl & 31) == 0) { sh.lo_hi[fp][0][wq] = vlo; sh.lo_hi[fp][1][wq] = vhi; }
         }
-#if FBUS_FRAME_CTA_BARRIER || !FBUS_PAIR_BARRIER
         cta_bar<NT>();  // (a)
-        uint32_t lo = sh.lo_hi[0][0], hi = sh.lo_hi[1][0];
+        uint32_t lo = sh.lo_hi[fp][0][0], hi = sh.lo_hi[fp][1][0];
 #pragma unroll
-        for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[0][q]); hi = max(hi, sh.lo_hi[1][q]); }
-#else
-        step_bar<NT, GS>(wq);  // (a)
-        const uint32_t lo = sh.lo_hi[0][wq], hi = sh.lo_hi[1][wq];
-#endif
+        for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[fp][0][q]); hi = max(hi, sh.lo_hi[fp][1][q]); }
         int fs = 0;
         if (lo < hi) {
             fs = (int)((hi - lo) & 1u);
@@ -629,7 +491,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                     for (int e = 0; e < 22; ++e) rec[(size_t)e * BSF] = 0.0;
                 }
                 sflag[slot][fl] = valid;
-                step_bar<NT, GS>(wq);  // publish record (i); also: the covariance warp has finished sample i-1
+                step_bar(wq);  // publish record (i); also: the covariance warp has finished sample i-1
             }
             if (fused && do_prop) cursor = consumed;
         }
@@ -651,8 +513,8 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             const int wany = __any_sync(0xffffffffu, req != 0);
             if ((fl & 31) == 0) sh.any_upd[wq] = wany;
         }
-        step_bar<NT, GS>(wq);  // (r)
-        const int any = pair_any<NT>(sh, wq);
+        step_bar(wq);  // (r)
+        const int any = pair_any(sh, wq);
         // ---- while the update runs: the next window's first IMU sample and the next frame's plan ---------------
         FramePlan nx;
         nx.do_prop = nx.apply_init = nx.apply_reset = false;
@@ -667,7 +529,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             plan_frame<BSF>(prm, k, w + 1, b, live, cursor, n.t, inited, prev_id, status, nx);
         }
         if (any) {
-            step_bar<NT, GS>(wq);  // (d) results posted
+            step_bar(wq);  // (d) results posted
             if (req) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -765,57 +627,8 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
         tm_base = tm_alloc_cta(&tm_slot);
     }
     if (is_cov) cov_role<BSF, JOSEPH, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
-    else nominal_role<BSF, TM, 2, IMU32>(prm, k, smem, sh, sflag, fl, b, live);
+    else nominal_role<BSF, TM, IMU32>(prm, k, smem, sh, sflag, fl, b, live);
     if constexpr (TM) tm_free_cta(tm_base);
 }
-
-// 0 (default): the experimental three-warp kernel below is NOT part of the library.  It lost to the two-warp kernel and
-// a compute-sanitizer memcheck run of the log replay through it ended with a covariance mismatch that the plain run does not show
-// (also with setmaxnreg compiled out: a timing-dependent ordering hole in the mbarrier hand-over between its cross and top-left warps),
-// so it is kept as source for the record only: build with -DFBUS_ENABLE_TRI=1 to experiment with it (FBUS_TRI_WARP=1 then selects it).
-#ifndef FBUS_ENABLE_TRI
-#define FBUS_ENABLE_TRI 0
-#endif
-#if FBUS_ENABLE_TRI
-#ifndef FBUS_TRI_SETMAXNREG
-#define FBUS_TRI_SETMAXNREG 1
-#endif
-// Three warps per 32 filters (covariance in tensor memory, 128 filters per CTA): top-left warp, nominal warp, cross warp.
-// 384 threads would get 168 registers each; setmaxnreg gives the top-left warps 232 and leaves 136 to the others.
-template <bool JOSEPH>
-__global__ void __launch_bounds__(384, 1) ekf_window_tri_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
-    constexpr int BSF = 128;
-    extern __shared__ double smem[];
-    __shared__ SplitShared sh;
-    __shared__ int32_t sflag[3][BSF];
-    __shared__ uint32_t tm_slot;
-    const int wi = threadIdx.x >> 5;
-    const int role = wi >> 2;  // 0: top-left / update, 1: nominal, 2: cross blocks
-    const int fl = (wi & 3) * 32 + (threadIdx.x & 31);
-    const size_t b0 = (size_t)blockIdx.x * BSF + fl;
-    const bool live = b0 < prm.B;
-    const size_t b = live ? b0 : prm.B - 1;
-    if (threadIdx.x < 12) mb_init(&sh.col_done[threadIdx.x / 3][threadIdx.x % 3], 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t tm_base = tm_alloc_cta(&tm_slot);
-    if (role == 0) {
-#if FBUS_TRI_SETMAXNREG
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-#endif
-        cov_role<BSF, JOSEPH, true, 3>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
-    } else if (role == 1) {
-#if FBUS_TRI_SETMAXNREG
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
-#endif
-        nominal_role<BSF, true, 3>(prm, k, smem, sh, sflag, fl, b, live);
-    } else {
-#if FBUS_TRI_SETMAXNREG
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
-#endif
-        cross_role<BSF>(prm, k, smem, sh, sflag, fl, tm_base);
-    }
-    tm_free_cta(tm_base);
-}
-#endif  // FBUS_ENABLE_TRI
 
 }  // namespace fbus

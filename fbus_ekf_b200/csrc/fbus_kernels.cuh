@@ -1,29 +1,20 @@
 // fbus_kernels.cuh -- CUDA kernels of the batched FBUS-EKF hot path (sm_100a).
 //
-//   ekf_window_kernel   K12: fused per-frame body of FILTER::FilterThreadFunction (filter.cpp:207-235):
-//                       InitializePose | ResetSystemState -> BatchImuProcessing -> ObservationUpdate,
-//                       state resident on chip for all frames of a launch.  The un-fused C-ABI calls
-//                       (propagate / update / reset / init) run the same kernel with a mode mask.
+//   (K12, the fused window kernel ekf_window_split_kernel, lives in fbus_kernel_split.cuh; this header holds the
+//   parameter block it shares with the host and every other kernel)
 //   init_gravity_kernel K0 : FILTER::InitializeGravityAndBias (filter.cpp:256-285)
 //   refract_kernel      K3+K4: RefractionTriangulation + ComputeMarkerPose (vision.cpp:472-759)
 //   marker_pose_kernel  K4 alone
 //   stats_kernel / stats_reduce_kernel, synth_kernel, fp64_peak_kernel: measurement support.
 //
 // Thread mapping: one thread per filter (or per marker); filter index fastest in every array, so a warp
-// reads/writes 32 consecutive doubles (256 B) per field.  The packed 18x18 covariance of the CTA's
-// filters lives in shared memory as [171][BS]; no __syncthreads is needed anywhere because a thread
-// only ever touches its own column.
+// reads/writes 32 consecutive doubles (256 B) per field.
 #pragma once
 
 #include <cuda_runtime.h>
 
 #include "fbus_math.cuh"
 #include "fbus_refract.cuh"
-
-// 1 = keep the bottom-right 9x9 covariance block in registers while a window's IMU samples are propagated
-#ifndef FBUS_BR_REGS
-#define FBUS_BR_REGS 0
-#endif
 
 namespace fbus {
 
@@ -69,7 +60,7 @@ struct WinParams {
 __device__ __forceinline__ double imu_cvt(float f, int c, double imu_g) {
     return (c < 3) ? __dmul_rn((double)f, imu_g) : __dmul_rn((double)__fdiv_rn(f, 180.0f), 3.1415926);
 }
-// format decided at run time (one-off kernels, un-split window kernel)
+// format decided at run time (one-off kernels)
 __device__ __forceinline__ double imu_sample(const double* imu, const float* imu32, double imu_g, size_t i, int c, size_t B, size_t b) {
     const size_t idx = (i * 6 + (size_t)c) * B + b;
     return imu32 != nullptr ? imu_cvt(imu32[idx], c, imu_g) : imu[idx];
@@ -80,296 +71,6 @@ __device__ __forceinline__ double imu_sample_t(const PRM& prm, double imu_g, siz
     const size_t idx = (i * 6 + (size_t)c) * B + b;
     if constexpr (IMU32) return imu_cvt(prm.imu32[idx], c, imu_g);
     else return prm.imu[idx];
-}
-
-template <int BS>
-__global__ void __launch_bounds__(BS) ekf_window_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
-    extern __shared__ double smem[];
-    const size_t B = prm.B;
-    // CTAs larger than one warp keep their warps in step with __syncthreads (one barrier per IMU sample): the
-    // warps then run the same ~30 KB instruction stream at the same time and share its instruction-cache lines.
-    // Threads past the end of the batch therefore stay alive (they mirror the last filter) but never store.
-    constexpr bool SYNC = BS > 32;
-    __shared__ uint32_t sred[2][(BS + 31) / 32];
-    const size_t b0 = (size_t)blockIdx.x * BS + threadIdx.x;
-    const bool live = b0 < B;
-    const size_t b = live ? b0 : B - 1;
-    const Cov<BS> P{smem + threadIdx.x};
-
-    // ---- load state --------------------------------------------------------------------------
-    for (int e = 0; e < NPK; ++e) smem[e * BS + threadIdx.x] = prm.P[(size_t)e * B + b];
-    Nominal n;
-    n.t = prm.nom[(size_t)F_T * B + b];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) n.q[i] = prm.nom[(size_t)(F_Q + i) * B + b];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) n.R[i] = prm.nom[(size_t)(F_R + i) * B + b];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        n.p[i] = prm.nom[(size_t)(F_P + i) * B + b];
-        n.v[i] = prm.nom[(size_t)(F_V + i) * B + b];
-        n.ba[i] = prm.nom[(size_t)(F_BA + i) * B + b];
-        n.bg[i] = prm.nom[(size_t)(F_BG + i) * B + b];
-        n.g[i] = prm.nom[(size_t)(F_G + i) * B + b];
-    }
-    int prev_id = prm.prev_id[b];
-    int inited = prm.init[b];
-    int status = prm.status[b];
-    const int mode = prm.mode;
-    const bool fused = (mode & M_FUSED) != 0;
-
-    uint32_t cursor = fused ? (prm.cursor_resume ? prm.cursor_io[b] : prm.win_off[prm.w0]) : 0u;
-
-    for (uint32_t w = prm.w0; w < prm.w1; ++w) {
-        // ---- scan this frame's detections (filter.cpp:329-341 / 418-430 / 639-658) ------------
-        int n_det = 0, idx_near = 0, idx_prev = 0;
-        double md = 10.0, prev_dist = 0.0;
-        double t_det = 0.0;
-        const bool uses_det = (mode & (M_INIT | M_RESET | M_UPDATE | M_FUSED)) != 0;
-        if (uses_det) {
-            t_det = prm.det_t[w];
-            for (int s = 0; s < prm.m; ++s) {
-                const size_t slot = (size_t)w * prm.m + s;
-                const int id = prm.det_id[slot * B + b];
-                if (id < 0) continue;
-                const double* pp = prm.det_pose + slot * 7 * B + b;
-                const double px = pp[0], py = pp[B], pz = pp[2 * B];
-                const double dist = sqrt(px * px + py * py + pz * pz);
-                if (n_det == 0) { idx_near = s; idx_prev = s; }  // detectionResult_[0] defaults (min_dist_id = 0)
-                if (dist < md) { md = dist; idx_near = s; }
-                if (id == prev_id) { prev_dist = dist; idx_prev = s; }
-                ++n_det;
-            }
-        }
-        // chosen slots: nearest for init/reset; nearest-with-hysteresis for the update (filter.cpp:660-664)
-        int idx_upd = idx_near;
-        {
-            const double dd = prev_dist - md;
-            if ((dd < 0 ? -dd : dd) < k.switch_thres && prev_dist != 0) idx_upd = idx_prev;
-        }
-        double dp[3], dq[4];
-        int did = -1;
-        auto load_det = [&](int s) {
-            const size_t slot = (size_t)w * prm.m + s;
-            did = prm.det_id[slot * B + b];
-            const double* pp = prm.det_pose + slot * 7 * B + b;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) dp[c] = pp[(size_t)c * B];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dq[c] = pp[(size_t)(3 + c) * B];
-        };
-
-        bool do_init = false, do_reset = false, do_prop = false, do_update = false;
-        uint32_t p_first = 0, p_end = 0;
-        double t_end = 0.0;
-        uint32_t n_before = prm.n_imu_before;
-        if (fused) {
-            if (n_det == 0) {
-                status |= FBUS_ST_NO_DETECTION;  // filter thread not woken (vision.cpp:136-140)
-            } else if (!inited) {
-                do_init = true;
-                n_before = 0;
-                const uint32_t hi = prm.win_off[w + 1];
-                for (uint32_t i = cursor; i < hi; ++i) n_before += (prm.imu_t[i] <= t_det) ? 1u : 0u;
-            } else {
-                do_reset = do_prop = do_update = true;
-                p_first = cursor;
-                p_end = prm.win_off[w + 1];
-                t_end = t_det;
-            }
-        } else {
-            do_init = (mode & M_INIT) != 0;
-            do_reset = (mode & M_RESET) != 0;
-            do_update = (mode & M_UPDATE) != 0;
-            if (mode & M_PROP) {
-                do_prop = true;
-                p_first = prm.prop_first;
-                p_end = prm.prop_first + prm.prop_count;
-                t_end = prm.prop_t_end;
-            }
-            if ((mode & M_UPDATE) && n_det == 0) status |= FBUS_ST_NO_DETECTION;
-        }
-
-        // ---- F6b InitializePose (filter.cpp:291-399) -----------------------------------------
-        if (do_init) {
-            bool ok = (n_before > 0) && (n_det > 0) && !(md > k.max_dist);
-            int mk = -1;
-            if (ok) {
-                load_det(idx_near);
-                mk = find_marker(k, prm.tab, did);
-                ok = mk >= 0;
-            }
-            if (ok) {
-                double qn[4], Rn[9], pn[3];
-                const MarkerConst mkc = prm.tab->mk[mk];
-                vision_pose(k, mkc, dp, dq, qn, Rn, pn);
-                n.t = t_det;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) n.R[i] = Rn[i];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) n.p[i] = pn[i];
-                n.g[0] = 9.8; n.g[1] = 0.0; n.g[2] = 0.0;  // filter.cpp:387
-                inited = 1;
-                if (fused) cursor = prm.win_off[w + 1];  // consumed IMU samples erased (filter.cpp:390)
-            } else {
-                status |= FBUS_ST_INIT_FAILED;
-            }
-        }
-        // ---- F5 ResetSystemState (filter.cpp:405-477) ----------------------------------------
-        if (do_reset && n_det > 0) {
-            bool ok = !(md > k.max_dist);
-            int mk = -1;
-            if (ok) {
-                load_det(idx_near);
-                mk = find_marker(k, prm.tab, did);
-                ok = mk >= 0;
-            }
-            if (ok) {
-                double qv[4], Rv[9], pv[3];
-                const MarkerConst mkc = prm.tab->mk[mk];
-                vision_pose(k, mkc, dp, dq, qv, Rv, pv);
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) prm.nom[(size_t)(F_PV + i) * B + b] = pv[i];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_QV + i) * B + b] = qv[i];
-                }
-                if (t_det - n.t > k.reset_gap && inited) {
-                    n.t = t_det;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) n.q[i] = qv[i];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) { n.p[i] = pv[i]; n.v[i] = 0.0; n.ba[i] = 0.0; n.bg[i] = 0.0; }
-                    status |= FBUS_ST_RESET_DONE;  // P, g and the carried R stay untouched
-                }
-            } else {
-                status |= FBUS_ST_RESET_SKIPPED;
-            }
-        }
-        // ---- F3 BatchImuProcessing (filter.cpp:483-531): F1 then F2 per sample ------------------
-        if (SYNC ? (__syncthreads_or(do_prop ? 1 : 0) != 0) : do_prop) {
-            // block-uniform candidate range [lo, hi) so that the per-sample barrier is reached by every thread
-            uint32_t lo = p_first, hi = p_end;
-            if (SYNC) {
-                const uint32_t vlo = __reduce_min_sync(0xffffffffu, do_prop ? p_first : 0xffffffffu);
-                const uint32_t vhi = __reduce_max_sync(0xffffffffu, do_prop ? p_end : 0u);
-                if ((threadIdx.x & 31) == 0) { sred[0][threadIdx.x >> 5] = vlo; sred[1][threadIdx.x >> 5] = vhi; }
-                __syncthreads();
-                lo = sred[0][0]; hi = sred[1][0];
-#pragma unroll
-                for (int q = 1; q < (BS + 31) / 32; ++q) { lo = min(lo, sred[0][q]); hi = max(hi, sred[1][q]); }
-                __syncthreads();
-            }
-#if FBUS_BR_REGS
-            double BR[NBR];
-            br_load<BS>(P, BR);
-#endif
-            const double start = n.t;
-            bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
-            uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
-            double s_t = 0.0, s_d[6];
-            if (lo < hi) {
-                s_t = prm.imu_t[lo];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) s_d[c] = imu_sample(prm.imu, prm.imu32, k.imu_g, lo, c, B, b);
-            }
-            for (uint32_t i = lo; i < hi; ++i) {
-                if (SYNC) __syncthreads();
-                const double ti = s_t;
-                double d[6];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) d[c] = s_d[c];
-                if (i + 1 < hi) {  // prefetch the next sample while this one is processed
-                    s_t = prm.imu_t[i + 1];
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) s_d[c] = imu_sample(prm.imu, prm.imu32, k.imu_g, (size_t)i + 1, c, B, b);
-                }
-                if (open && i >= p_first && i < p_end) {
-                    if (ti < start) {
-                        consumed = i + 1;
-                    } else if (ti > t_end) {
-                        open = false;  // this sample stays buffered
-                    } else {
-                        consumed = i + 1;
-                        const double dt = ti - n.t;
-                        double wv[3], av[3];
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
-#if FBUS_BR_REGS
-                        propagate_cov<BS, true>(P, n.R, av, wv, dt, k.Qd, BR);  // uses the CARRIED rotmatI2G (A.3-2,3)
-#else
-                        propagate_cov<BS>(P, n.R, av, wv, dt, k.Qd);  // uses the CARRIED rotmatI2G (A.3-2,3)
-#endif
-                        propagate_nominal(n, dt, d, d + 3);
-                        n.t = ti;
-                    }
-                }
-            }
-            if (fused && do_prop) cursor = consumed;
-#if FBUS_BR_REGS
-            br_store_diag<BS>(P, BR);
-#endif
-        }
-        if (SYNC) __syncthreads();
-        // ---- F4 ObservationUpdate (filter.cpp:622-739) -----------------------------------------
-        if (do_update && n_det > 0) {
-            load_det(idx_upd);
-            const int mk = find_marker(k, prm.tab, did);
-            if (mk >= 0) {
-                prev_id = did;
-                const MarkerConst mkc = prm.tab->mk[mk];
-                measurement_update<BS>(P, n, k, mkc, dp, dq);
-            } else {
-                status |= FBUS_ST_UPDATE_SKIPPED;
-            }
-        }
-        // ---- trace row: the data/fusion.txt record (filter.cpp:241-246) -------------------------
-        if (prm.trace && live) {
-            double* row = prm.trace + (size_t)(w - prm.w0) * 17 * B + b;
-            row[0] = n.t;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) row[(size_t)(1 + c) * B] = n.p[c];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) row[(size_t)(4 + c) * B] = n.q[c];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                row[(size_t)(8 + c) * B] = n.v[c];
-                row[(size_t)(11 + c) * B] = n.ba[c];
-                row[(size_t)(14 + c) * B] = n.bg[c];
-            }
-        }
-    }
-
-    // ---- store state ----------------------------------------------------------------------------
-    {
-        bool fin = isfinite(n.t);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) fin = fin && isfinite(n.q[i]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) fin = fin && isfinite(n.p[i]) && isfinite(n.v[i]);
-        if (!fin) status |= FBUS_ST_NONFINITE;
-    }
-    if (!live) return;
-    for (int e = 0; e < NPK; ++e) prm.P[(size_t)e * B + b] = smem[e * BS + threadIdx.x];
-    prm.nom[(size_t)F_T * B + b] = n.t;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_Q + i) * B + b] = n.q[i];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) prm.nom[(size_t)(F_R + i) * B + b] = n.R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        prm.nom[(size_t)(F_P + i) * B + b] = n.p[i];
-        prm.nom[(size_t)(F_V + i) * B + b] = n.v[i];
-        prm.nom[(size_t)(F_BA + i) * B + b] = n.ba[i];
-        prm.nom[(size_t)(F_BG + i) * B + b] = n.bg[i];
-        prm.nom[(size_t)(F_G + i) * B + b] = n.g[i];
-    }
-    prm.prev_id[b] = prev_id;
-    prm.init[b] = inited;
-    if (fused) prm.cursor_io[b] = cursor;
-    prm.status[b] = status;
 }
 
 // FILTER::SetImuData's 1-pole IIR (filter.cpp:36-48): one thread per (channel, filter) walks the samples in order; the

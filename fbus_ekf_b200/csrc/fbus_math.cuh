@@ -108,9 +108,9 @@ FBUS_HD void qmul_conjb(const double* a, const double* b, double* o) {  // a * c
 }
 // reciprocal square root: one MUFU.RSQ64H + Newton steps on the device (1-2 ulp) instead of a correctly rounded
 // sqrt followed by a correctly rounded division (~4x the instructions); the host build keeps 1/sqrt
-// Device versions are call-free on purpose (hardware seed + Newton steps, no out-of-line slow path): the three-warp window
-// kernel gives its warpgroups different register budgets (setmaxnreg), and ptxas cannot share a library subroutine between
-// them.  Arguments on these paths are far inside the normal range; 0 gives NaN (the callers treat 0 separately or want it).
+// Device versions are call-free on purpose (hardware seed + Newton steps, no out-of-line slow path: fewer instructions and
+// nothing for the register allocator to save around a call).  Arguments on these paths are far inside the normal range;
+// 0 gives NaN (the callers treat 0 separately or want it).
 FBUS_HD double rsqrt_d(double x) {
 #ifdef __CUDA_ARCH__
     double y;
@@ -253,8 +253,7 @@ struct CovX {
     FBUS_HD void fence_st() const {}  // accessors with asynchronous stores (tensor memory) order them here
     // asynchronous-load API of the tensor-memory accessor (fbus_tmem.cuh); plain loads here
     FBUS_HD void ldblk_nw(int bi, int bj, double* X) const { ldany(bi, bj, X); }
-    // cross blocks of rows 1, 2 (bi in {1,2}, k in 3..5): a double-buffering accessor distinguishes the values before /
-    // after the current step; here there is one copy
+    // cross blocks of rows 1, 2 (bi in {1,2}, k in 3..5)
     FBUS_HD void ldtr_nw(int bi, int k, double* X, bool) const { ldany(bi, k, X); }
     FBUS_HD void sttr(int bi, int k, const double* X) const { stblk(bi, k, X); }
     FBUS_HD void wait_ld() const {}
@@ -315,11 +314,6 @@ using Cov = CovX<S, false>;
 // Evaluation: (1) top-left 3x3 blocks from OLD values, (2) block columns 4,3,5 of rows 0..2, folding
 // their contribution into the top-left accumulators.  ~650 FMA instead of the 2*18^3 dense product.
 // ------------------------------------------------------------------------------------------------
-// packed index inside the bottom-right 9x9 (rows/cols 9..17), used when that block is cached in registers
-FBUS_HD constexpr int bridx(int i, int j) {  // any order; i,j in 9..17
-    return (i <= j) ? ((i - 9) * 9 - ((i - 9) * (i - 10)) / 2 + (j - i)) : ((j - 9) * 9 - ((j - 9) * (j - 10)) / 2 + (i - j));
-}
-constexpr int NBR = 45;
 constexpr int NTL = 45;  // packed size of the top-left 9x9 (tlidx)
 template <int S, class CV = Cov<S>>
 FBUS_HD void tl_load(const CV P, double* TL) {
@@ -335,21 +329,6 @@ FBUS_HD void tl_store(const CV P, const double* TL) {
         FBUS_UNROLL
         for (int j = i; j < 9; ++j) P.st(i, j, TL[tlidx(i, j)]);
 }
-template <int S>
-FBUS_HD void br_load(const Cov<S> P, double* BR) {
-    FBUS_UNROLL
-    for (int i = 9; i < 18; ++i)
-        FBUS_UNROLL
-        for (int j = i; j < 18; ++j) BR[bridx(i, j)] = P.ld(i, j);
-}
-template <int S>
-FBUS_HD void br_store_diag(const Cov<S> P, const double* BR) {  // only the b_a / b_g diagonals change while propagating
-    FBUS_UNROLL
-    for (int i = 9; i < 15; ++i) P.st(i, i, BR[bridx(i, i)]);
-}
-
-// BRR = true: the bottom-right 9x9 (b_a, b_g, g covariance; read-only while propagating except for the process noise on
-// its diagonal) is held in the caller's registers BR[45] instead of being re-read from shared memory every step.
 // coefficients of F for one IMU sample: A = -R*[a]x*dt, B = -R*dt (row-major 3x3), u = w*dt
 FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, double dt, double* A, double* B, double* u) {
     const double ndt = -dt;
@@ -369,18 +348,12 @@ FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, dou
 
 // TLR = true: the top-left 9x9 (p, v, theta covariance: read AND written by every step) is held in the caller's
 // registers TL[45] across the IMU samples of a window instead of making a round trip through shared memory per step.
-// hooks of propagate_cov_core around each block column of phase 2 (kk = 0, 1, 2 for columns 4, 3, 5): the three-warp kernel
-// synchronises its two covariance warps column by column through them
-struct NoMid {
-    FBUS_HD void begin(int) const {}
-    FBUS_HD void end(int) const {}
-};
-template <int S, bool BRR = false, bool TLR = false, class CV = Cov<S>, int PART = 0, class MidF = NoMid>
+template <int S, bool TLR = false, class CV = Cov<S>>
 FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, double u0, double u1, double u2, double dt,
-                                const double* Qd, double* BR = nullptr, double* TL = nullptr, MidF mid = MidF()) {
+                                const double* Qd, double* TL = nullptr) {
 // element (r, c) of block (bi, bj) loaded with ldblk_nw: a blocked accessor delivers the stored block (min, max), i.e. the
-// transpose when bi > bj (BRR: the register cache is already in the requested orientation)
-#define FBUS_BLK(X, bi, bj, r, c) ((CV::kBlocked && !BRR && (bi) > (bj)) ? X[(c) * 3 + (r)] : X[(r) * 3 + (c)])
+// transpose when bi > bj
+#define FBUS_BLK(X, bi, bj, r, c) ((CV::kBlocked && (bi) > (bj)) ? X[(c) * 3 + (r)] : X[(r) * 3 + (c)])
 #define FBUS_TLLD(i, j) (TLR ? TL[tlidx((i), (j))] : P.ld((i), (j)))
 #define FBUS_TLST(i, j, v)                        \
     do {                                          \
@@ -421,7 +394,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
     // ---------------- phase 1: top-left blocks from old values -------------------------------
     // Staged so that few blocks are live at a time (FBUS_FENCE stops the scheduler hoisting every
     // shared-memory load to the top, which would blow the 255-register budget).
-    if (PART != 2) {
+    {
         double P11[9], P12[9];
         FBUS_TL_LDBLK(1, 2, P12);
         double M12[9];
@@ -542,22 +515,13 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
     }
     FBUS_FENCE_B;
     // ---------------- phase 2: block columns 4, 3, 5 of rows 0..2 -----------------------------
-    // PART 0: compute the new cross blocks and fold them into the top-left block (one warp does everything).
-    // PART 2: compute and store the cross blocks only (the "cross" warp of the three-warp kernel).
-    // PART 1: phase 1 above, then per block column: mid.begin(kk) (wait for the PART-2 warp), LOAD the new cross blocks, fold.
-    // PART 2 calls mid.end(kk) after the stores of a block column (signal).
+    // the new cross blocks are computed and folded into the top-left block
     double d01[9], d11[9];
     FBUS_UNROLL
     for (int kk = 0; kk < 3; ++kk) {
         const int k = (kk == 0) ? 4 : (kk == 1) ? 3 : 5;
-        mid.begin(kk);
         double X1[9], X2[9], M0[9], M2[9];
-        if (PART == 1) {
-            P.ldblk_nw(0, k, M0);
-            P.ldtr_nw(1, k, X1, true);
-            P.ldtr_nw(2, k, M2, true);
-            P.wait_ld();
-        } else {
+        {
             P.ldtr_nw(1, k, X1, false);
             P.ldblk_nw(0, k, M0);
             P.ldtr_nw(2, k, X2, false);
@@ -567,7 +531,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
             for (int e = 0; e < 9; ++e) M0[e] += a * X1[e];
             P.stblk(0, k, M0);
         }
-        if (PART != 2) {
+        {
             if (k == 4) {  // P'02 -= a*M04
                 FBUS_UNROLL
                 for (int i = 0; i < 3; ++i)
@@ -600,22 +564,12 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
         }
         FBUS_FENCE_A;
         double X4[9];
-        if (PART != 1) {   // row 1: M1 = P1k + A*P2k + B*P3k + a*P5k
+        {   // row 1: M1 = P1k + A*P2k + B*P3k + a*P5k
             double X3[9], X5[9];
-            if (BRR) {
-                FBUS_UNROLL
-                for (int r = 0; r < 3; ++r)
-                    FBUS_UNROLL
-                    for (int c = 0; c < 3; ++c) {
-                        X3[r * 3 + c] = BR[bridx(9 + r, 3 * k + c)];
-                        X5[r * 3 + c] = BR[bridx(15 + r, 3 * k + c)];
-                    }
-            } else {
-                P.ldblk_nw(3, k, X3);
-                P.ldblk_nw(5, k, X5);
-                P.ldblk_nw(4, k, X4);
-                P.wait_ld();  // blocks below the diagonal arrive transposed from a blocked accessor: FBUS_BLK indexes them
-            }
+            P.ldblk_nw(3, k, X3);
+            P.ldblk_nw(5, k, X5);
+            P.ldblk_nw(4, k, X4);
+            P.wait_ld();  // blocks below the diagonal arrive transposed from a blocked accessor: FBUS_BLK indexes them
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -632,13 +586,10 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
             P.sttr(1, k, X1);
             if (k == 3) {  // accel-bias process noise on P33's diagonal
                 FBUS_UNROLL
-                for (int i = 0; i < 3; ++i) {
-                    if (BRR) BR[bridx(9 + i, 9 + i)] = X3[i * 3 + i] + Qd[2];
-                    else P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);
-                }
+                for (int i = 0; i < 3; ++i) P.st(9 + i, 9 + i, X3[i * 3 + i] + Qd[2]);
             }
         }
-        if (PART != 2) {
+        {
             if (k == 4) {  // P'12 -= a*M14
                 FBUS_UNROLL
                 for (int i = 0; i < 3; ++i)
@@ -670,13 +621,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
             }
         }
         FBUS_FENCE_A;
-        if (PART != 1) {   // row 2: M2 = (I+Wm)*P2k - a*P4k
-            if (BRR) {
-                FBUS_UNROLL
-                for (int r = 0; r < 3; ++r)
-                    FBUS_UNROLL
-                    for (int c = 0; c < 3; ++c) X4[r * 3 + c] = BR[bridx(12 + r, 3 * k + c)];
-            }
+        {   // row 2: M2 = (I+Wm)*P2k - a*P4k
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -689,13 +634,10 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
             P.sttr(2, k, M2);
             if (k == 4) {  // gyro-bias process noise on P44's diagonal
                 FBUS_UNROLL
-                for (int i = 0; i < 3; ++i) {
-                    if (BRR) BR[bridx(12 + i, 12 + i)] = X4[i * 3 + i] + Qd[3];
-                    else P.st(12 + i, 12 + i, X4[i * 3 + i] + Qd[3]);
-                }
+                for (int i = 0; i < 3; ++i) P.st(12 + i, 12 + i, X4[i * 3 + i] + Qd[3]);
             }
         }
-        if (PART != 2 && k == 4) {  // P'22 -= a*M24 (upper)
+        if (k == 4) {  // P'22 -= a*M24 (upper)
             FBUS_UNROLL
             for (int i = 0; i < 3; ++i)
                 FBUS_UNROLL
@@ -706,7 +648,6 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
                 }
         }
         FBUS_FENCE_B;
-        mid.end(kk);
     }
 #undef FBUS_WX_ACC
 #undef FBUS_XWT_ACC
@@ -717,12 +658,11 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
 #undef FBUS_TL_STBLK
 }
 
-template <int S, bool BRR = false>
-FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, const double* w, double dt, const double* Qd,
-                           double* BR = nullptr) {
+template <int S>
+FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, const double* w, double dt, const double* Qd) {
     double A[9], B[9], u[3];
     cov_coeffs(R, acc, w, dt, A, B, u);
-    propagate_cov_core<S, BRR, false>(P, A, B, u[0], u[1], u[2], dt, Qd, BR, nullptr);
+    propagate_cov_core<S, false>(P, A, B, u[0], u[1], u[2], dt, Qd, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

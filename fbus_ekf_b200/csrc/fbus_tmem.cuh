@@ -175,42 +175,4 @@ struct CovTM {
     }
 };
 
-// Three-warp kernel: the cross blocks of block rows 1 and 2 (six blocks, 108 columns) exist twice, at their home position
-// and at columns 378..485.  A propagate step reads one copy ("old") and writes the other ("new"), so the warp that computes
-// the new cross blocks never overwrites values the top-left warp is still reading.  `cur` = which copy holds the current
-// values (0 = home); after a step the roles swap.
-constexpr uint32_t TM_ALT0 = 378u;
-struct CovTM2 : CovTM<false> {
-    uint32_t cur = 0;
-    __device__ __forceinline__ uint32_t tr_col(int bi, int k, bool newer) const {
-        const uint32_t which = newer ? (cur ^ 1u) : cur;
-        return base + (which ? (TM_ALT0 + 18u * (uint32_t)((k - 3) * 2 + (bi - 1))) : tm_blk_col(bi, k));
-    }
-    __device__ __forceinline__ void ldtr_nw(int bi, int k, double* X, bool newer) const {
-        const uint32_t a = tr_col(bi, k, newer);
-        tm_ld8(a, X);
-        tm_ld1(a + 16u, X[8]);
-    }
-    __device__ __forceinline__ void sttr(int bi, int k, const double* X) const {
-        const uint32_t a = tr_col(bi, k, true);
-        tm_st8(a, X);
-        tm_st1(a + 16u, X[8]);
-    }
-    // move the six blocks home when they live in the alternate copy (before anything that uses the plain accessor)
-    __device__ __forceinline__ void tr_home() {
-        if (cur) {
-            FBUS_UNROLL
-            for (int k = 3; k < 6; ++k)
-                FBUS_UNROLL
-                for (int bi = 1; bi < 3; ++bi) {
-                    double T[9];
-                    ldtr_nw(bi, k, T, false);
-                    tm_wait_ld();
-                    straw(bi, k, T);
-                }
-            cur = 0;
-        }
-    }
-};
-
 }  // namespace fbus

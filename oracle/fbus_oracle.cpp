@@ -940,9 +940,10 @@ int orc_step_windows(orc_handle* h, const fbus_imu_stream* imu, const fbus_det_f
                     // (vision.cpp:136-140): nothing happens for this filter in this frame
                     f.status |= FBUS_ST_NO_DETECTION;
                 } else if (!f.initialised) {
-                    size_t cnt = 0;
-                    for (size_t i = first; i < first + count; ++i) if (imu->t[i] <= t_det) ++cnt;
-                    if (InitializePose(h->k, &f, d.data(), n, t_det, cnt)) { f.initialised = 1; cursor = win_off[w + 1]; }
+                    size_t cnt = 0;  // imuCnt: leading buffered samples not later than the frame (filter.cpp:299-305)
+                    for (size_t i = first; i < first + count; ++i) { if (imu->t[i] > t_det) break; ++cnt; }
+                    // only those are erased (filter.cpp:390); later samples stay buffered for the next frame
+                    if (InitializePose(h->k, &f, d.data(), n, t_det, cnt)) { f.initialised = 1; cursor = first + cnt; }
                 } else {
                     ResetSystemState(h->k, &f, d.data(), n, t_det);
                     cursor = first + BatchImuProcessing(h->k, &f, imu->t, imu->data, B, b, first, count, t_det);

@@ -274,16 +274,21 @@ class Filter:
 
     # filter.cpp:483-531
     def batch_imu(self, imu_rows, t_end):
+        """-> imuCnt, the number of leading rows the reference erases afterwards (filter.cpp:492-503,520)"""
         start = self.t
+        cnt = 0
         for row in imu_rows:
             if row[0] < start:
+                cnt += 1
                 continue
             if row[0] > t_end:
                 break
+            cnt += 1
             dt = row[0] - self.t
             self.update_covariance(dt, row[1:4], row[4:7])
             self.update_nominal(dt, row[1:4], row[4:7])
             self.t = row[0]
+        return cnt
 
     def measurement_model(self, d):
         """returns (hP, hQ, H) for detection d before sign disambiguation (filter.cpp:677-694)"""
@@ -489,13 +494,13 @@ def replay(cfg: Config, imu, image_rows, n_init=500, use_iir=False, joseph=False
     for w, (t_det, dets) in enumerate(frames):
         hi = int(off[w + 1])
         if not f.initialised:
-            cnt = int(np.sum(imu[cursor:hi, 0] <= t_det))
+            later = np.nonzero(imu[cursor:hi, 0] > t_det)[0]
+            cnt = int(later[0]) if len(later) else hi - cursor  # imuCnt: leading rows not later than the frame (filter.cpp:299-305)
             if f.init_pose(dets, t_det, cnt):
-                cursor = hi
+                cursor += cnt  # only those are erased (filter.cpp:390)
         else:
             f.reset_state(dets, t_det)
-            f.batch_imu(imu[cursor:hi], t_det)
-            cursor = hi
+            cursor += f.batch_imu(imu[cursor:hi], t_det)
             f.observation_update(dets, joseph=joseph)
         rows.append(np.concatenate([[f.t], f.p, f.q, f.v, f.ba, f.bg]))
         if trace_cov:
