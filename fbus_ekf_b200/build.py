@@ -17,6 +17,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 HASH_FILE = OUT + ".srchash"
+LAST_MODE = "not built in this process"  # "compiled" | "up to date (source hash matches)" | "prebuilt, nvcc missing"
+
+
+def nvcc_version() -> str:
+    try:
+        out = subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "--version"], capture_output=True, text=True).stdout
+        return out.strip().splitlines()[-1] if out.strip() else "unknown"
+    except OSError:
+        return "nvcc not found"
 
 
 def source_hash() -> str:
@@ -28,6 +37,14 @@ def source_hash() -> str:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
+
+
+def built_with() -> str:
+    """compiler that produced the library on disk (recorded next to it at build time)"""
+    try:
+        return open(OUT + ".nvcc").read().strip()
+    except OSError:
+        return "unknown"
 
 
 def needs_build() -> bool:
@@ -55,15 +72,19 @@ def build_variant(win_bs: int, suffix: str, extra=()) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    global LAST_MODE
     if not force and not needs_build():
+        LAST_MODE = "up to date (source hash matches)"
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     try:
         res = subprocess.run(cmd, capture_output=True, text=True)
     except FileNotFoundError:
-        if os.path.exists(OUT):  # no nvcc on this machine: keep the prebuilt library that travelled with the repo
-            sys.stderr.write("fbus_ekf_b200.build: nvcc not found, using the prebuilt libfbus_ekf.so\n")
+        if os.path.exists(OUT):  # no nvcc on this machine: keep the prebuilt library that travelled with the repo -- loudly
+            sys.stderr.write("fbus_ekf_b200.build: nvcc not found and the sources changed since libfbus_ekf.so was built; "
+                             "using the STALE prebuilt library\n")
+            LAST_MODE = "prebuilt and STALE, nvcc missing"
             return OUT
         raise
     log = res.stdout + res.stderr
@@ -74,6 +95,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libfbus_ekf.so")
     with open(HASH_FILE, "w") as f:
         f.write(source_hash())
+    with open(OUT + ".nvcc", "w") as f:
+        f.write(nvcc_version())
+    LAST_MODE = "compiled"
     if verbose:
         print(log)
     return OUT

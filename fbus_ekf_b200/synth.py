@@ -58,10 +58,30 @@ def _right_jacobian(phi):
 
 
 def quat_from_rotmat(R):
-    """Eigen Quaterniond(Matrix3d) via the library helper (main.cpp:201)."""
-    R = np.ascontiguousarray(R, dtype=np.float64).ravel()
+    """Eigen Quaterniond(Matrix3d) (main.cpp:201): w,x,y,z, not normalised.  Host arithmetic of the workload
+    generator only (the filter path derives its own constants on the device side of the C ABI); tests check it against the
+    library helper fbus_quat_from_rotmat."""
+    m = np.asarray(R, dtype=np.float64).reshape(3, 3)
     q = np.zeros(4)
-    capi.lib().fbus_quat_from_rotmat(capi.dptr(R), capi.dptr(q))
+    t = m[0, 0] + m[1, 1] + m[2, 2]
+    if t > 0:
+        t = np.sqrt(t + 1.0)
+        q[0] = 0.5 * t
+        t = 0.5 / t
+        q[1], q[2], q[3] = (m[2, 1] - m[1, 2]) * t, (m[0, 2] - m[2, 0]) * t, (m[1, 0] - m[0, 1]) * t
+    else:
+        i = 0
+        if m[1, 1] > m[0, 0]:
+            i = 1
+        if m[2, 2] > m[i, i]:
+            i = 2
+        j, k = (i + 1) % 3, (i + 2) % 3
+        t = np.sqrt(m[i, i] - m[j, j] - m[k, k] + 1.0)
+        q[1 + i] = 0.5 * t
+        t = 0.5 / t
+        q[0] = (m[k, j] - m[j, k]) * t
+        q[1 + j] = (m[j, i] + m[i, j]) * t
+        q[1 + k] = (m[k, i] + m[i, k]) * t
     return q
 
 

@@ -15,6 +15,9 @@
 #include <thread>
 #include <vector>
 
+#include <pthread.h>
+#include <sched.h>
+
 namespace {
 
 // common.hpp:14 -- the reference overrides M_PI for all of its code (parity trap A.3-1)
@@ -821,11 +824,25 @@ void ComputeMarkerPose(const double* C, double* p, double* q, double* Rml) {
 template <class Fn>
 void parallel_for(size_t n, int n_threads, Fn fn) {
     if (n_threads <= 1 || n < 2) { fn(0, n); return; }
+    // one thread per core the process may run on, pinned 1:1
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    std::vector<int> cpus;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0)
+        for (int c = 0; c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &allowed)) cpus.push_back(c);
     std::vector<std::thread> th;
     const size_t T = (size_t)n_threads;
     for (size_t i = 0; i < T; ++i) {
         const size_t lo = n * i / T, hi = n * (i + 1) / T;
-        if (lo < hi) th.emplace_back([=] { fn(lo, hi); });
+        if (lo >= hi) continue;
+        th.emplace_back([=] { fn(lo, hi); });
+        if (!cpus.empty()) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(cpus[i % cpus.size()], &one);
+            pthread_setaffinity_np(th.back().native_handle(), sizeof one, &one);
+        }
     }
     for (auto& x : th) x.join();
 }

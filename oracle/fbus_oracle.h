@@ -6,16 +6,17 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (fbus_ekf_b200/) never links, imports or calls it.
  *
- * Parity status: the reference itself cannot be built here (needs Eigen3, OpenCV 3.4.3,
- * ArUco 3.1.12, yaml-cpp, glog, Pangolin -- none present, no network), so this restatement is
- * pinned by the reference's bundled logs:
+ * Parity status:
+ *   - F1-F6 (EKF chain): PINNED to the reference's own code.  oracle/_ref is C++/src/filter.cpp compiled
+ *     UNMODIFIED from /root/reference against stand-in third-party headers (oracle/ref_build/: the image
+ *     has no Eigen / OpenCV / ArUco / yaml-cpp / glog) and executed here; tests/test_oracle_vs_ref.py
+ *     compares this restatement with it per call on random states (1e-13 relative) and over both bundled
+ *     log replays, reset frames included.  fusion.txt stays a shape-only check (older revision).
  *   - R1+R2 (refractive triangulation + marker pose): PINNED by waterdata/dataset-06
  *     corners.txt -> image.txt (1062 rows) to the 6-significant-digit precision of the logs;
  *   - R2 (marker pose): PINNED by landdata/dataset-02 corners.txt -> image.txt (1257 rows);
- *   - F1-F6 (EKF): "parity unpinned" at better than cm level -- fusion.txt was written by an
- *     older revision of the reference.  The EKF chain is instead cross-checked
- *     between this C++ restatement and an independent NumPy restatement (oracle/fbus_oracle_np.py)
- *     plus analytic known-answer tests.
+ *   - R3 (Gauss-Newton refinement): "parity unpinned" -- it does not exist in the reference.
+ *   vision.cpp itself is not compiled (it needs ArUco's patched tracker and a dozen OpenCV calls).
  * The third-party arithmetic on the path is Eigen3 (un-vendored, version unpinned; Ubuntu 18.04
  * ships 3.3.4): quaternion product / normalize / toRotationMatrix / Quaterniond(AngleAxisd) /
  * Quaterniond(Matrix3d), AngleAxisd::matrix, LDLT::solve, EigenSolver<Matrix3d>, determinant.

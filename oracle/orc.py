@@ -173,6 +173,7 @@ def marker_pose(cfg, corners3d: np.ndarray):
 REF_DIR = os.path.join(HERE, "_ref")
 REF_LIB_PATH = os.path.join(REF_DIR, "libfbus_ref.so")
 REF_DBG_LIB_PATH = os.path.join(REF_DIR, "libfbus_ref_dbg.so")
+REF_AVX2_LIB_PATH = os.path.join(REF_DIR, "libfbus_ref_avx2.so")
 _ref_libs = {}
 
 
@@ -185,8 +186,8 @@ def ref_available() -> bool:
     return os.path.exists(REF_LIB_PATH)
 
 
-def ref_lib(debug: bool = False):
-    path = REF_DBG_LIB_PATH if debug else REF_LIB_PATH
+def ref_lib(variant: str = ""):
+    path = {"": REF_LIB_PATH, "dbg": REF_DBG_LIB_PATH, "avx2": REF_AVX2_LIB_PATH}[variant]
     if path in _ref_libs:
         return _ref_libs[path]
     if not os.path.exists(path):
@@ -224,11 +225,11 @@ class Ref(Oracle):
     """Batch of FBUSEKF::FILTER objects of the reference itself (oracle/_ref); same calls as Oracle."""
 
     _pfx = "ref_"
-    _debug = False
+    _variant = ""
 
     @classmethod
     def _lib(cls):
-        return ref_lib(cls._debug)
+        return ref_lib(cls._variant)
 
     def stats(self, truth_p, truth_q):
         raise NotImplementedError("the reference has no statistics")
@@ -247,9 +248,25 @@ class Ref(Oracle):
         return cam.reshape(4, 4), vis.reshape(4, 4)
 
 
+def host_has_avx2() -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " avx2" in line
+    except OSError:
+        pass
+    return False
+
+
+class RefFast(Ref):
+    """oracle/_ref built -O3 -mavx2 (bench.py's CPU baseline on hosts with AVX2); same arithmetic, one rounding per operation"""
+    _variant = "avx2"
+
+
 class RefDebug(Ref):
     """the same library with the stand-in headers' bounds / shape assertions compiled in"""
-    _debug = True
+    _variant = "dbg"
 
 
 def config_default():

@@ -55,6 +55,18 @@ def test_helpers_without_device(built):
     R = np.array([1, 0, 0, 0, -1, 0, 0, 0, -1], dtype=np.float64)  # trace < 0 branch
     lib.fbus_quat_from_rotmat(capi.dptr(R), capi.dptr(q))
     assert np.allclose(q, [0, 1, 0, 0], atol=1e-15)
+    # the workload generator's own NumPy copy of the rule (synth.quat_from_rotmat) and the product-free default config of the
+    # CPU arm (orc.config_default) agree with the library bit for bit
+    import orc
+    from fbus_ekf_b200 import synth
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        A *= np.sign(np.linalg.det(A))
+        lib.fbus_quat_from_rotmat(capi.dptr(np.ascontiguousarray(A.ravel())), capi.dptr(q))
+        assert np.array_equal(q, synth.quat_from_rotmat(A))
+    oc = orc.config_default()
+    assert bytes(oc) == bytes(cfg)
 
 
 def test_no_cpu_fallback(built):

@@ -188,6 +188,12 @@ def test_replay_prefix_tight_and_assertions(cfg, golden):
     rows_r, st_r, _ = _replay(orc.RefDebug, cfg, imu, img)
     assert _rel(rows_o, rows_r) <= RTOL
     _assert_same(st_o, st_r, tol=1e-12, what="prefix")
+    # the three builds of oracle/_ref (-O2, -O2 with assertions, -O3 -mavx2: bench.py's CPU baseline) are the same arithmetic
+    rows_p, st_p, _ = _replay(orc.Ref, cfg, imu, img)
+    assert np.array_equal(rows_p, rows_r) and np.array_equal(st_p["P"], st_r["P"])
+    if orc.host_has_avx2() and os.path.exists(orc.REF_AVX2_LIB_PATH):
+        rows_f, st_f, _ = _replay(orc.RefFast, cfg, imu, img)
+        assert np.array_equal(rows_f, rows_r) and np.array_equal(st_f["P"], st_r["P"])
 
 
 def test_init_frame_keeps_later_samples(cfg):
