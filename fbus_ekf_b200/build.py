@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfbus_ekf.so")
 SOURCES = ["fbus_capi.cu"]
-DEPS = ["fbus_capi.cu", "fbus_kernels.cuh", "fbus_kernel_split.cuh", "fbus_tmem.cuh", "fbus_math.cuh", "fbus_refract.cuh", "fbus_host_consts.hpp",
+DEPS = ["fbus_capi.cu", "fbus_kernels.cuh", "fbus_kernel_split.cuh", "fbus_kernel_lane.cuh", "fbus_tmem.cuh", "fbus_math.cuh", "fbus_refract.cuh", "fbus_host_consts.hpp",
         os.path.join("..", "..", "include", "fbus_ekf.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-cudart", "static"]

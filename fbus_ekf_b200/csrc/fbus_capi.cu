@@ -15,6 +15,7 @@
 #include "fbus_host_consts.hpp"
 #include "fbus_kernels.cuh"
 #include "fbus_kernel_split.cuh"
+#include "fbus_kernel_lane.cuh"
 
 using namespace fbus;
 
@@ -69,6 +70,7 @@ struct fbus_handle {
     uint32_t stagger_cycles = 0;
     size_t pipeline_min_bytes = (size_t)64 << 20;  // host streams smaller than this are staged and processed in one go
     bool small_batch = false;
+    bool lane_batch = false;  // batches that leave SMs idle even with 32-filter CTAs: nine lanes per filter (fbus_kernel_lane.cuh)
     double* d_nom = nullptr;
     double* d_P = nullptr;
     int32_t* d_prev = nullptr;
@@ -160,7 +162,14 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.stagger_cycles = (prm.mode & M_FUSED) ? h->stagger_cycles : 0u;
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
     const bool jo = (h->k.flags & FBUS_FLAG_JOSEPH) != 0, f32 = prm.imu32 != nullptr;
-    if (h->small_batch) {
+    if (h->lane_batch) {
+        const unsigned g32 = (unsigned)((h->B + 31) / 32);
+        if (f32) {
+            if (jo) ekf_window_lane_kernel<true, true><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
+            else ekf_window_lane_kernel<false, true><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
+        } else if (jo) ekf_window_lane_kernel<true, false><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
+        else ekf_window_lane_kernel<false, false><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
+    } else if (h->small_batch) {
         // fewer 128-filter CTAs than SMs (e.g. BASELINE configs[2], 4 096 filters): 32-filter CTAs (one covariance + one
         // nominal warp) spread the batch over four times as many SMs
         const unsigned g32 = (unsigned)((h->B + 31) / 32);
@@ -281,6 +290,15 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         // to ~3e9 filter-steps/s beyond (three small CTAs per SM), where the large CTAs keep scaling with the SMs they fill
         h->small_batch = WIN_BS > 32 && (batch + 31) / 32 <= 2 * (size_t)prop.multiProcessorCount;
         if (const char* sb = getenv("FBUS_SMALL_BATCH")) h->small_batch = atoi(sb) != 0;
+        // one 32-filter lanes-per-filter CTA per SM at most: below that the batch is latency-bound and nine lanes per filter
+        // cut the latency of a filter-step ~3x; an explicit FBUS_SMALL_BATCH choice keeps the thread-per-filter kernels
+        h->lane_batch = !getenv("FBUS_SMALL_BATCH") && (batch + 31) / 32 <= (size_t)prop.multiProcessorCount;
+        if (const char* lb = getenv("FBUS_LANE")) h->lane_batch = atoi(lb) != 0;
+        e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
+        if (e != cudaSuccess) return bail("cudaFuncSetAttribute(lane)", e);
         const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
         e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);

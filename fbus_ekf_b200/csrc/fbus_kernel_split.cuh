@@ -372,12 +372,52 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
     }
 }
 
-template <int BSF, bool TM, bool IMU32 = false>
+// exchange area of the lanes-per-filter kernel (fbus_kernel_lane.cuh), doubles per filter laid out [entry][32 filters]:
+// ring 2 x 22 | P6 (6x6 of the p/theta rows and columns) | Lc (21, Joseph form only) | y (6) or z (7) | dx (18) |
+// X = L^-1 Hs (42: scratch of the update prologue, and the 7-row factor the lanes read in the default form)
+constexpr int LX_P6 = 44, LX_CM = 80, LX_Y = 101, LX_DX = 108, LX_SCR = 126, LX_TOTAL = 168;
+constexpr int LANE_NT = 384;  // 11 covariance warps (3 filters each, 9 lanes per filter) + the nominal warp
+
+// the p/theta sub-matrix P6 = P[{0,1,2,6,7,8}, {0,1,2,6,7,8}] as the covariance lanes publish it: the only part of P the
+// update prologue reads (accessor interface of update_prologue)
+struct P6View {
+    const double* s;  // [36][32] entries of this filter
+    static constexpr bool kTLR = false;
+    static constexpr bool kBlocked = false;
+    static FBUS_HD constexpr int m6(int i) { return i < 3 ? i : i - 3; }  // rows 0,1,2 -> 0..2 ; 6,7,8 -> 3..5
+    __device__ __forceinline__ double at(int a, int c) const { return s[(size_t)(a * 6 + c) * 32]; }
+    __device__ __forceinline__ double ld(int i, int j) const { return at(m6(i), m6(j)); }
+    __device__ __forceinline__ void lddiag(int bb, double* X) const {
+        const int o = bb == 0 ? 0 : 3;
+        FBUS_UNROLL
+        for (int r = 0; r < 3; ++r)
+            FBUS_UNROLL
+            for (int c = 0; c < 3; ++c) X[r * 3 + c] = at(o + r, o + c);
+    }
+    __device__ __forceinline__ void ldblk(int bi, int bj, double* X) const {
+        const int oi = bi == 0 ? 0 : 3, oj = bj == 0 ? 0 : 3;
+        FBUS_UNROLL
+        for (int r = 0; r < 3; ++r)
+            FBUS_UNROLL
+            for (int c = 0; c < 3; ++c) X[r * 3 + c] = at(oi + r, oj + c);
+    }
+};
+
+// LANE = true: the role runs inside the lanes-per-filter kernel (fbus_kernel_lane.cuh): every barrier is CTA-wide, invalid ring
+// records need no neutral content, and the update is split differently -- this warp (one lane per filter) runs the
+// state-only prologue (predicted measurement, Hs, S, the gain factors) from the published P6 and the error-state
+// injection, the covariance lanes run the sweep P -= Z^T Z and dx = Z^T y.
+template <int BSF, bool TM, bool IMU32 = false, bool LANE = false, bool JOSEPH = false>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
                                              int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
-    constexpr int NT = 2 * BSF, NW = BSF / 32;
+    constexpr int NT = LANE ? LANE_NT : 2 * BSF, NW = BSF / 32;
+    static_assert(!LANE || BSF == 32, "the lanes-per-filter kernel has 32 filters per CTA");
     const size_t B = prm.B;
-    double* const X = smem + (size_t)(TM ? 0 : NPK) * BSF + fl;
+    double* const X = smem + (size_t)((TM || LANE) ? 0 : NPK) * BSF + fl;
+    auto sbar = [&](int pair) {
+        if constexpr (LANE) cta_bar<NT>();
+        else step_bar(pair);
+    };
     const bool fused = (prm.mode & M_FUSED) != 0;
     const int wq = fl >> 5;  // nominal warp index
     Nominal n;
@@ -485,20 +525,20 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                         n.t = ti;
                     }
                 }
-                if (TM && !valid) {  // tensor-memory mode: the covariance warp runs every lane, invalid ones with F = I
+                if (TM && !LANE && !valid) {  // tensor-memory mode: the covariance warp runs every lane, invalid ones with F = I
                     double* rec = X + (size_t)slot * 22 * BSF;
 #pragma unroll
                     for (int e = 0; e < 22; ++e) rec[(size_t)e * BSF] = 0.0;
                 }
                 sflag[slot][fl] = valid;
-                step_bar(wq);  // publish record (i); also: the covariance warp has finished sample i-1
+                sbar(wq);  // publish record (i); also: the covariance warp has finished sample i-1
             }
             if (fused && do_prop) cursor = consumed;
         }
 
         // ---- F4 ObservationUpdate (filter.cpp:622-739): post the request (into the ring slot the covariance warp is
         //      not reading), the covariance warp does the algebra ------------------------------------------------
-        if (req) {
+        if (req && !LANE) {
             double* rq = X + (size_t)fs * 22 * BSF;
 #pragma unroll
             for (int c = 0; c < 7; ++c) rq[(size_t)c * BSF] = pl.y[c];  // yP (3), yQ (4)
@@ -513,8 +553,35 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             const int wany = __any_sync(0xffffffffu, req != 0);
             if ((fl & 31) == 0) sh.any_upd[wq] = wany;
         }
-        step_bar(wq);  // (r)
+        sbar(wq);  // (r)
         const int any = pair_any(sh, wq);
+        if constexpr (LANE) {
+            if (any) {
+                sbar(wq);  // (p) the covariance lanes have published P6
+                if (req) {
+                    const MarkerConst mkc = prm.tab->mk[req - 1];
+                    if constexpr (JOSEPH) {  // 6-row factor Lc of the Joseph-form C_J and y = Lc^-1 u
+                        double Cm[21], yv[6];
+                        update_prologue<BSF, BSF, true, P6View>(P6View{X + (size_t)LX_P6 * BSF}, n, k, mkc, pl.y, pl.y + 3, Cm, yv,
+                                                                X + (size_t)LX_SCR * BSF);
+#pragma unroll
+                        for (int c = 0; c < 21; ++c) X[(size_t)(LX_CM + c) * BSF] = Cm[c];
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) X[(size_t)(LX_Y + c) * BSF] = yv[c];
+                    } else {  // 7-row factor X = L^-1 Hs (left in the scratch entries) and z = L^-1 r: no second factorisation
+                        // (computing Hs and r before the barrier, while the lanes finish, measured slower: the 37 doubles held
+                        // across the wait spill at this kernel's 168 registers)
+                        double L[28], Li[7], zv[7];
+                        UpdHs hh;
+                        update_hs(n, k, mkc, pl.y, pl.y + 3, hh);
+                        update_prologue_sx<BSF, BSF, P6View>(P6View{X + (size_t)LX_P6 * BSF}, k, hh, L, Li, zv, X + (size_t)LX_SCR * BSF);
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) X[(size_t)(LX_Y + c) * BSF] = zv[c];
+                    }
+                }
+                sbar(wq);  // (c) gain factors posted
+            }
+        }
         // ---- while the update runs: the next window's first IMU sample and the next frame's plan ---------------
         FramePlan nx;
         nx.do_prop = nx.apply_init = nx.apply_reset = false;
@@ -529,18 +596,25 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             plan_frame<BSF>(prm, k, w + 1, b, live, cursor, n.t, inited, prev_id, status, nx);
         }
         if (any) {
-            step_bar(wq);  // (d) results posted
+            sbar(wq);  // (d) results posted
             if (req) {
+                if constexpr (LANE) {
+                    double dx[18];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    n.p[c] = X[(size_t)(23 + c) * BSF];
-                    n.v[c] += X[(size_t)(30 + c) * BSF];
-                    n.ba[c] += X[(size_t)(33 + c) * BSF];
-                    n.bg[c] += X[(size_t)(36 + c) * BSF];
-                    n.g[c] += X[(size_t)(39 + c) * BSF];
+                    for (int c = 0; c < 18; ++c) dx[c] = X[(size_t)(LX_DX + c) * BSF];
+                    inject_error_state(n, dx);  // rotmatI2G deliberately NOT refreshed (A.3-2)
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        n.p[c] = X[(size_t)(23 + c) * BSF];
+                        n.v[c] += X[(size_t)(30 + c) * BSF];
+                        n.ba[c] += X[(size_t)(33 + c) * BSF];
+                        n.bg[c] += X[(size_t)(36 + c) * BSF];
+                        n.g[c] += X[(size_t)(39 + c) * BSF];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(26 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
                 }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) n.q[c] = X[(size_t)(26 + c) * BSF];  // rotmatI2G deliberately NOT refreshed (A.3-2)
             }
         }
         // ---- trace row: the data/fusion.txt record (filter.cpp:241-246) -------------------------

@@ -677,20 +677,26 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
     const double wn = wn2 * inv;      // |w|
     double R0[9], qh[4], qn[4];
     q2R(n.q, R0);
-    if (wn > 10e-5) {
+    {
+        // Both forms of the increment are evaluated and the one the reference's branch takes (filter.cpp:544-561) is selected:
+        // straight-line code instead of a divergent region, so that the scheduler can overlap the sincos chain with the rest
+        // of the step.  The values selected are exactly those the branch would have produced (a zero rate gives inf / NaN in
+        // the unused axis-angle form, which the select discards).
+        const bool big = wn > 10e-5;
         const double ax[3] = {w[0] * inv, w[1] * inv, w[2] * inv};
         // one sincos: the half-interval quaternion needs angle/2 = wn*dt/4, the full one twice that
         // (double-angle identities; ~1 ulp from evaluating sin/cos of wn*dt/2 directly)
         double sh, ch;
-        sincos_d(wn * dt * 0.25, &sh, &ch);
+        sincos_d(big ? wn * dt * 0.25 : 0.0, &sh, &ch);
         const double sf = 2.0 * sh * ch, cf = 1.0 - 2.0 * sh * sh;
-        const double dqh[4] = {ch, sh * ax[0], sh * ax[1], sh * ax[2]};
-        const double dq[4] = {cf, sf * ax[0], sf * ax[1], sf * ax[2]};
-        qmul(n.q, dqh, qh);
-        qmul(n.q, dq, qn);
-    } else {
-        const double dqh[4] = {1.0, 0.25 * dt * w[0], 0.25 * dt * w[1], 0.25 * dt * w[2]};
-        const double dq[4] = {1.0, 0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
+        double dqh[4], dq[4];
+        dqh[0] = big ? ch : 1.0;
+        dq[0] = big ? cf : 1.0;
+        FBUS_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            dqh[1 + i] = big ? sh * ax[i] : 0.25 * dt * w[i];
+            dq[1 + i] = big ? sf * ax[i] : 0.5 * dt * w[i];
+        }
         qmul(n.q, dqh, qh);
         qmul(n.q, dq, qn);
     }
@@ -785,15 +791,19 @@ struct CholStep<N, N> {
     static FBUS_HD void run(double*, double*) {}
 };
 
-// Prologue of the update: everything up to the gain factors.  Reads only the 21 entries of P6 = P[{p,theta},{p,theta}].
-// Outputs Cm = lower-packed Cholesky factor Lc of C = Hs^T S^-1 Hs and y = Lc^-1 u (u = Hs^T S^-1 r), so that
-//   (I-KH)P = P - Z^T Z with Z = Lc^T G, and dx = K r = Z^T y.
-template <int S, int XS, bool JOSEPH = false, class CV = Cov<S>>
-FBUS_HD void update_prologue(const CV P, const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
-                             const double* yQ, double* Cm, double* y, double* scr) {
-    // scr: 42 doubles of scratch with element stride XS (shared memory in the warp-specialised kernel) for X = L^-1 Hs
-    // ---- predicted measurement and Hs ------------------------------------------------------
+// First half: predicted measurement, Hs, S = Hs P6 Hs^T + R = L L^T, X = L^-1 Hs (7x6, left in scr with element stride XS) and
+// z = L^-1 r.  With these alone (I-KH)P = P - (X G)^T (X G) and dx = (X G)^T z (the lanes-per-filter kernel stops here: a
+// 7-row factor costs its parallel sweep little and saves the serial second factorisation); the second half below reduces
+// the factor to 6 rows.
+// the state-only part: Hs = [Hp0 Hp2; 0 Hq] and the residual r (filter.cpp:677-721); needs nothing of P
+struct UpdHs {
     double Hp0[9], Hp2[9], Hq[12], r[7];
+};
+FBUS_HD void update_hs(const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP, const double* yQ, UpdHs& hh) {
+    double* const Hp0 = hh.Hp0;
+    double* const Hp2 = hh.Hp2;
+    double* const Hq = hh.Hq;
+    double* const r = hh.r;
     {
         double dp[3], rtdp[3], RP[3], d2[3], rt2[3], hP[3];
         FBUS_UNROLL
@@ -849,8 +859,16 @@ FBUS_HD void update_prologue(const CV P, const Nominal& n, const DevConsts& k, c
         FBUS_UNROLL
         for (int i = 0; i < 4; ++i) r[3 + i] = yQ[i] - sg * hQ[i];
     }
+}
+template <int S, int XS, class CV = Cov<S>>
+FBUS_HD void update_prologue_sx(const CV P, const DevConsts& k, const UpdHs& hh, double* L, double* Li, double* z, double* scr) {
+    // scr: 42 doubles of scratch with element stride XS (shared memory in the warp-specialised kernel) for X = L^-1 Hs
+    const double* const Hp0 = hh.Hp0;
+    const double* const Hp2 = hh.Hp2;
+    const double* const Hq = hh.Hq;
+    const double* const r = hh.r;
     // ---- S = Hs P6 Hs^T + R (lower triangle, packed in L) --------------------------------------
-    double L[28];  // row-major packed lower triangle: L[i*(i+1)/2 + j]
+    // L[28]: row-major packed lower triangle: L[i*(i+1)/2 + j]
 #define FBUS_L(i, j) L[(i) * ((i) + 1) / 2 + (j)]
     {
         double P00[9], P02[9], P22[9];
@@ -922,14 +940,10 @@ FBUS_HD void update_prologue(const CV P, const Nominal& n, const DevConsts& k, c
         }
     }
     // ---- Cholesky S = L L^T (in place), reciprocal diagonal in Li -------------------------------
-    double Li[7];
     CholStep<7, 0>::run(L, Li);
-    // ---- X = L^-1 Hs (7x6), z = L^-1 r ; C = X^T X ; u = X^T z -------------------------------
-    double u[6];  // (Cm: C lower packed, Cm[i*(i+1)/2+j])
-#define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
-    {
-        double z[7];
+    // ---- X = L^-1 Hs (7x6), z = L^-1 r -----------------------------------------------------------
 #define FBUS_X(i) scr[(i) * XS]
+    {
         FBUS_UNROLL
         for (int i = 0; i < 7; ++i) {
             FBUS_UNROLL
@@ -944,6 +958,29 @@ FBUS_HD void update_prologue(const CV P, const Nominal& n, const DevConsts& k, c
             for (int j = 0; j < i; ++j) s -= FBUS_L(i, j) * z[j];
             z[i] = s * Li[i];
         }
+    }
+#undef FBUS_L
+#undef FBUS_X
+}
+
+// Prologue of the update: everything up to the gain factors.  Reads only the 21 entries of P6 = P[{p,theta},{p,theta}].
+// Outputs Cm = lower-packed Cholesky factor Lc of C = Hs^T S^-1 Hs and y = Lc^-1 u (u = Hs^T S^-1 r), so that
+//   (I-KH)P = P - Z^T Z with Z = Lc^T G, and dx = K r = Z^T y.
+template <int S, int XS, bool JOSEPH = false, class CV = Cov<S>>
+FBUS_HD void update_prologue(const CV P, const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP,
+                             const double* yQ, double* Cm, double* y, double* scr) {
+    double L[28], Li[7], z[7];
+    {
+        UpdHs hh;
+        update_hs(n, k, mk, yP, yQ, hh);
+        update_prologue_sx<S, XS, CV>(P, k, hh, L, Li, z, scr);
+    }
+#define FBUS_L(i, j) L[(i) * ((i) + 1) / 2 + (j)]
+#define FBUS_X(i) scr[(i) * XS]
+    // ---- C = X^T X ; u = X^T z -------------------------------------------------------------------
+    double u[6];  // (Cm: C lower packed, Cm[i*(i+1)/2+j])
+#define FBUS_C(i, j) Cm[(i) * ((i) + 1) / 2 + (j)]
+    {
         FBUS_UNROLL
         for (int i = 0; i < 6; ++i) {
             FBUS_UNROLL

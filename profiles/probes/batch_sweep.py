@@ -1,5 +1,6 @@
-"""Throughput of the window kernel vs batch size for its two CTA shapes (32-filter shared-memory CTAs, FBUS_SMALL_BATCH=1, and
-128-filter tensor-memory CTAs, FBUS_SMALL_BATCH=0): where should fbus_create switch?  Run on a B200: python profiles/probes/batch_sweep.py"""
+"""Throughput of the window kernel vs batch size for its three forms (nine lanes per filter, FBUS_LANE=1; 32-filter
+shared-memory CTAs, FBUS_SMALL_BATCH=1; 128-filter tensor-memory CTAs, FBUS_SMALL_BATCH=0): where should fbus_create
+switch?  Run on a B200: python profiles/probes/batch_sweep.py"""
 import os
 import sys
 
@@ -14,12 +15,15 @@ cfg = capi.config_default()
 traj = synth.truth_trajectory(cfg, 1.0, 200.0, 25.0, periodic=True)
 N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
 dev = torch.device("cuda:0")
-print("| filters | 32-filter CTAs (smem) | 128-filter CTAs (TMEM) |")
-print("|---|---|---|")
-for B in (1024, 4096, 8192, 10240, 12288, 14336, 16384, 18944, 32768, 65536):
+print("| filters | 9 lanes per filter (registers) | 32-filter CTAs (smem) | 128-filter CTAs (TMEM) |")
+print("|---|---|---|---|")
+SIZES = (1, 32, 256, 1024, 2048, 4096, 4736, 6144, 8192, 9472, 10240, 12288, 14336, 16384, 18944, 32768, 65536)
+if len(sys.argv) > 1:
+    SIZES = tuple(int(x) for x in sys.argv[1:])
+for B in SIZES:
     row = []
-    for mode in ("1", "0"):
-        os.environ["FBUS_SMALL_BATCH"] = mode
+    for env in ({"FBUS_LANE": "1"}, {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"}, {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}):
+        os.environ.update(env)
         f = BatchFilter(cfg, batch=B, device=0)
         imu_d = torch.empty((N, 6, B), dtype=torch.float64, device=dev)
         id_d = torch.empty((W, 1, B), dtype=torch.int32, device=dev)
@@ -45,4 +49,4 @@ for B in (1024, 4096, 8192, 10240, 12288, 14336, 16384, 18944, 32768, 65536):
         sec = e0.elapsed_time(e1) * 1e-3 / reps
         row.append(B * (N + W) / sec)
         f.close()
-    print(f"| {B} | {row[0]:.3g} | {row[1]:.3g} |")
+    print(f"| {B} | {row[0]:.3g} | {row[1]:.3g} | {row[2]:.3g} |", flush=True)

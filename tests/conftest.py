@@ -50,22 +50,27 @@ def cfg(built):
     return capi.config_default()
 
 
-# The window kernel has two covariance stores: tensor memory (128-filter CTAs, chosen when the batch fills the GPU) and
-# shared memory (32-filter CTAs, small batches).  The parity tests work on small batches, so the modules listed here run
-# twice: with the library's own choice and with FBUS_SMALL_BATCH=0, which forces the tensor-memory kernel.
-_BOTH_PATHS = ("test_gpu_step_parity", "test_gpu_replay_parity", "test_gpu_synth_batch")
+# The window kernel exists in three forms: nine lanes per filter with the covariance in registers (small batches,
+# fbus_kernel_lane.cuh), one thread per filter with the covariance in shared memory (32-filter CTAs) and one thread per filter
+# with the covariance in tensor memory (128-filter CTAs, batches that fill the GPU).  The parity tests work on small batches,
+# so the modules listed here run three times, forcing each kernel in turn.
+_ALL_PATHS = ("test_gpu_step_parity", "test_gpu_replay_parity", "test_gpu_synth_batch", "test_gpu_init_overshoot")
+_PATH_ENV = {"auto": {}, "lane": {"FBUS_LANE": "1"}, "smem": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"},
+             "tmem": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}}
 
 
 def pytest_generate_tests(metafunc):
-    if metafunc.module.__name__.split(".")[-1] in _BOTH_PATHS and "cov_store" in metafunc.fixturenames:
-        metafunc.parametrize("cov_store", ["auto", "tmem"], indirect=True)
+    if metafunc.module.__name__.split(".")[-1] in _ALL_PATHS and "cov_store" in metafunc.fixturenames:
+        metafunc.parametrize("cov_store", ["lane", "smem", "tmem"], indirect=True)
 
 
 @pytest.fixture(autouse=True)
 def cov_store(request):
     mode = getattr(request, "param", "auto")
-    want = {"auto": {}, "tmem": {"FBUS_SMALL_BATCH": "0"}}[mode]
-    old = {k: os.environ.get(k) for k in want}
+    want = _PATH_ENV[mode]
+    old = {k: os.environ.get(k) for k in ("FBUS_LANE", "FBUS_SMALL_BATCH")}
+    for k in old:
+        os.environ.pop(k, None)
     os.environ.update(want)
     yield mode
     for k, v in old.items():

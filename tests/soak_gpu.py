@@ -15,12 +15,12 @@ import orc  # noqa: E402
 from fbus_ekf_b200 import BatchFilter, capi, synth  # noqa: E402
 from helpers import cov_close  # noqa: E402
 
-PATHS = {"smem32": {"FBUS_SMALL_BATCH": "1"}, "tmem128": {"FBUS_SMALL_BATCH": "0"}}
+PATHS = {"lane9": {"FBUS_LANE": "1"}, "smem32": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"}, "tmem128": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}}
 
 
 def one(it, rng, cfg):
     path = list(PATHS)[it % len(PATHS)]
-    for k in ("FBUS_SMALL_BATCH",):
+    for k in ("FBUS_SMALL_BATCH", "FBUS_LANE"):
         os.environ.pop(k, None)
     os.environ.update(PATHS[path])
     B = int(rng.integers(1, 400))
@@ -80,7 +80,7 @@ def board(it, rng, cfg):
     """multi-marker frames (8 board markers, refractive solve on the GPU -> detections), random subsets of the markers
     detected per filter and frame, occasional unknown ids: marker selection / hysteresis / prev-id logic across all paths"""
     path = list(PATHS)[it % len(PATHS)]
-    for k in ("FBUS_SMALL_BATCH",):
+    for k in ("FBUS_SMALL_BATCH", "FBUS_LANE"):
         os.environ.pop(k, None)
     os.environ.update(PATHS[path])
     B, m = int(rng.integers(1, 200)), 8

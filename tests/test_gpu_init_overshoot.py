@@ -29,11 +29,10 @@ def _case(B, rng):
     return t, data, tdet, ids, pose, off
 
 
-@pytest.mark.parametrize("B,small", [(48, "1"), (160, "0")])
-def test_init_frame_overshoot(cfg, B, small, monkeypatch):
+@pytest.mark.parametrize("B", [48, 160])
+def test_init_frame_overshoot(cfg, B, cov_store):
     import orc
     from fbus_ekf_b200 import BatchFilter, capi
-    monkeypatch.setenv("FBUS_SMALL_BATCH", small)
     rng = np.random.default_rng(9)
     t, data, tdet, ids, pose, off = _case(B, rng)
     W = len(tdet)
