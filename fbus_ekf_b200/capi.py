@@ -14,8 +14,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBUS_EKF_LIB", os.path.join(HERE, "libfbus_ekf.so"))
 
-FBUS_OK, FBUS_E_BADARG, FBUS_E_CUDA, FBUS_E_NOMEM, FBUS_E_STATE = 0, -1, -2, -3, -4
-FBUS_ABI_VERSION = 2  # include/fbus_ekf.h
+FBUS_OK, FBUS_E_BADARG, FBUS_E_CUDA, FBUS_E_NOMEM, FBUS_E_STATE, FBUS_E_NCCL = 0, -1, -2, -3, -4, -5
+FBUS_ABI_VERSION = 3  # include/fbus_ekf.h
 FBUS_MEM_HOST = 0
 FBUS_MEM_DEVICE = 1
 FBUS_IMU_F64_SI = 0      # double, m/s^2 and rad/s (IMUData)
@@ -165,6 +165,8 @@ def lib() -> C.CDLL:
         "fbus_clear_status": (C.c_int, [H]),
         "fbus_stats": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_int32, c_double_p, C.c_void_p]),
         "fbus_stats_combine": (C.c_int, [c_double_p, C.c_size_t, c_double_p]),
+        "fbus_stats_allreduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), c_double_p]),
+        "fbus_stats_allreduce_comm": (C.c_int, [H, C.c_void_p, C.c_void_p, c_double_p]),
         "fbus_synth_streams": (C.c_int, [H, C.POINTER(SynthSpec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "fbus_quat_from_rotmat": (None, [c_double_p, c_double_p]),
         "fbus_measure_fp64_peak": (C.c_int, [H, c_double_p]),
@@ -184,7 +186,7 @@ EXPORTED_SYMBOLS = (
     "fbus_config_default", "fbus_create", "fbus_destroy", "fbus_last_error", "fbus_abi_version", "fbus_synchronize",
     "fbus_batch", "fbus_stream", "fbus_init_gravity_gyrobias", "fbus_iir_prefilter", "fbus_init_position_quaternion", "fbus_propagate",
     "fbus_reset_state", "fbus_update", "fbus_step_windows", "fbus_refract_solve", "fbus_inair_solve", "fbus_undistort_fisheye", "fbus_solve_to_detections", "fbus_refract_solve_gn", "fbus_marker_pose", "fbus_get_state",
-    "fbus_set_state", "fbus_clear_status", "fbus_stats", "fbus_stats_combine", "fbus_synth_streams", "fbus_quat_from_rotmat",
+    "fbus_set_state", "fbus_clear_status", "fbus_stats", "fbus_stats_combine", "fbus_stats_allreduce", "fbus_stats_allreduce_comm", "fbus_synth_streams", "fbus_quat_from_rotmat",
     "fbus_measure_fp64_peak")
 
 

@@ -4,10 +4,13 @@
 // handle's stream.  There is no CPU compute path: every entry point that does arithmetic launches a
 // kernel from fbus_kernels.cuh, and fbus_create fails when no CUDA device is usable.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -864,6 +867,128 @@ int fbus_stats(fbus_handle* h, const double* truth_p, const double* truth_q, int
     CUDA_TRY(h, cudaGetLastError());
     if (out_host) {
         CUDA_TRY(h, cudaMemcpyAsync(out_host, dout, FBUS_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return FBUS_OK;
+}
+
+// ---- NCCL, loaded at run time: the library itself has no link-time dependency on it ------------------------------------
+namespace {
+// the few NCCL declarations used (nccl.h: ncclResult_t ncclSuccess = 0; ncclDataType_t ncclFloat64 = 8; ncclRedOp_t ncclSum = 0,
+// ncclMax = 2); kept local so that the library builds on machines without the NCCL headers
+typedef void* nccl_comm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("FBUS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm || !*nm) continue;
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (api.lib) break;
+            api.why = dlerror();
+        }
+        if (!api.lib) return;
+        api.CommInitAll = (int (*)(nccl_comm_t*, int, const int*))dlsym(api.lib, "ncclCommInitAll");
+        api.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+        api.GroupStart = (int (*)())dlsym(api.lib, "ncclGroupStart");
+        api.GroupEnd = (int (*)())dlsym(api.lib, "ncclGroupEnd");
+        api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+        if (!api.CommInitAll || !api.AllReduce || !api.GroupStart || !api.GroupEnd) {
+            api.why = "libnccl lacks ncclCommInitAll / ncclAllReduce / ncclGroupStart / ncclGroupEnd";
+            api.lib = nullptr;
+        }
+    });
+    return api;
+}
+int nccl_fail(fbus_handle* h, const char* what, int rc) {
+    NcclApi& a = nccl_api();
+    return fail(h, FBUS_E_NCCL, std::string(what) + ": " + ((a.lib && a.GetErrorString) ? a.GetErrorString(rc) : "NCCL error"));
+}
+// sum of entries 0..4, maximum of entry 5, entries 6..7 zero: two all-reduces on the handle's stream (inside the caller's group)
+int enqueue_stats_allreduce(fbus_handle* h, nccl_comm_t comm, double* v) {
+    NcclApi& a = nccl_api();
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemsetAsync(v + 6, 0, 2 * sizeof(double), h->stream));
+    int rc = a.AllReduce(v, v, 5, kNcclFloat64, kNcclSum, comm, h->stream);
+    if (rc) return nccl_fail(h, "ncclAllReduce(sum)", rc);
+    rc = a.AllReduce(v + 5, v + 5, 1, kNcclFloat64, kNcclMax, comm, h->stream);
+    if (rc) return nccl_fail(h, "ncclAllReduce(max)", rc);
+    return FBUS_OK;
+}
+std::mutex g_comm_mu;
+std::map<std::vector<int>, std::vector<nccl_comm_t>> g_comms;  // one clique per device list, kept for the life of the process
+}  // namespace
+
+int fbus_stats_allreduce(fbus_handle* const* handles, int n, double* const* dev_vecs, double* out_host) {
+    if (!handles || !dev_vecs || n <= 0) return fail(nullptr, FBUS_E_BADARG, "fbus_stats_allreduce: bad argument");
+    for (int i = 0; i < n; ++i)
+        if (!handles[i] || !dev_vecs[i]) return fail(nullptr, FBUS_E_BADARG, "fbus_stats_allreduce: null handle or vector");
+    fbus_handle* h0 = handles[0];
+    if (n > 1) {
+        std::vector<int> devs(n);
+        for (int i = 0; i < n; ++i) {
+            devs[i] = handles[i]->device;
+            for (int j = 0; j < i; ++j)
+                if (devs[j] == devs[i]) return fail(h0, FBUS_E_BADARG, "fbus_stats_allreduce: two handles on the same device (combine those with fbus_stats_combine)");
+        }
+        NcclApi& a = nccl_api();
+        if (!a.lib) return fail(h0, FBUS_E_NCCL, "fbus_stats_allreduce: NCCL not available (" + a.why + "); set FBUS_NCCL_LIB");
+        std::vector<nccl_comm_t> comms;
+        {
+            std::lock_guard<std::mutex> lk(g_comm_mu);
+            auto it = g_comms.find(devs);
+            if (it == g_comms.end()) {
+                std::vector<nccl_comm_t> c(n, nullptr);
+                const int rc = a.CommInitAll(c.data(), n, devs.data());
+                if (rc) return nccl_fail(h0, "ncclCommInitAll", rc);
+                it = g_comms.emplace(devs, c).first;
+            }
+            comms = it->second;
+        }
+        int rc = a.GroupStart();
+        if (rc) return nccl_fail(h0, "ncclGroupStart", rc);
+        int frc = FBUS_OK;
+        for (int i = 0; i < n && frc == FBUS_OK; ++i) frc = enqueue_stats_allreduce(handles[i], comms[i], dev_vecs[i]);
+        rc = a.GroupEnd();
+        if (frc != FBUS_OK) return frc;
+        if (rc) return nccl_fail(h0, "ncclGroupEnd", rc);
+    } else {
+        CUDA_TRY(h0, cudaSetDevice(h0->device));
+        CUDA_TRY(h0, cudaMemsetAsync(dev_vecs[0] + 6, 0, 2 * sizeof(double), h0->stream));
+    }
+    for (int i = 0; i < n; ++i) {  // every vector is final when the call returns
+        CUDA_TRY(handles[i], cudaSetDevice(handles[i]->device));
+        if (i == 0 && out_host)
+            CUDA_TRY(h0, cudaMemcpyAsync(out_host, dev_vecs[0], FBUS_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, h0->stream));
+        CUDA_TRY(handles[i], cudaStreamSynchronize(handles[i]->stream));
+    }
+    return FBUS_OK;
+}
+
+int fbus_stats_allreduce_comm(fbus_handle* h, void* nccl_comm, double* dev_vec, double* out_host) {
+    if (!h || !nccl_comm || !dev_vec) return fail(h, FBUS_E_BADARG, "fbus_stats_allreduce_comm: bad argument");
+    NcclApi& a = nccl_api();
+    if (!a.lib) return fail(h, FBUS_E_NCCL, "fbus_stats_allreduce_comm: NCCL not available (" + a.why + "); set FBUS_NCCL_LIB");
+    int rc = a.GroupStart();
+    if (rc) return nccl_fail(h, "ncclGroupStart", rc);
+    const int frc = enqueue_stats_allreduce(h, (nccl_comm_t)nccl_comm, dev_vec);
+    rc = a.GroupEnd();
+    if (frc != FBUS_OK) return frc;
+    if (rc) return nccl_fail(h, "ncclGroupEnd", rc);
+    if (out_host) {
+        CUDA_TRY(h, cudaMemcpyAsync(out_host, dev_vec, FBUS_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
     return FBUS_OK;

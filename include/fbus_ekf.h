@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FBUS_ABI_VERSION 2 /* 2: fbus_config.imu_g / gn_tol, fbus_imu_stream.format, fbus_iir_prefilter */
+#define FBUS_ABI_VERSION 3 /* 2: fbus_config.imu_g / gn_tol, fbus_imu_stream.format, fbus_iir_prefilter; 3: fbus_stats_allreduce*, FBUS_E_NCCL */
 
 /* error codes */
 #define FBUS_OK 0
@@ -42,6 +42,7 @@ extern "C" {
 #define FBUS_E_CUDA (-2)
 #define FBUS_E_NOMEM (-3)
 #define FBUS_E_STATE (-4)
+#define FBUS_E_NCCL (-5) /* NCCL missing (libnccl.so.2 could not be loaded) or an NCCL call failed */
 
 /* where a caller-owned data pointer lives */
 #define FBUS_MEM_HOST 0
@@ -313,6 +314,23 @@ int fbus_stats(fbus_handle* h, const double* truth_p, const double* truth_q, int
    that gather the vectors themselves -- several handles in one process, MPI): parts is [n_parts][FBUS_NSTATS] on the HOST;
    out[0..4] = sums over the parts, out[5] = maximum, out[6..7] = 0.  Pure host code, needs no handle. */
 int fbus_stats_combine(const double* parts, size_t n_parts, double* out);
+
+/*
+ * The one collective of the multi-GPU path (north_star: "only a final NCCL allreduce of RMSE/NEES statistics
+ * over NVLink"): filters are independent, every device works on its own shard with no hot-path traffic, and at the end the
+ * FBUS_NSTATS-double vectors of fbus_stats are combined with ncclAllReduce -- entries 0..4 with ncclSum, entry 5 with ncclMax,
+ * entries 6..7 zeroed -- over NVLink / NVSwitch.  NCCL is loaded at run time (libnccl.so.2, or the path in FBUS_NCCL_LIB);
+ * without it the calls return FBUS_E_NCCL, nothing else of the library needs it.
+ *
+ * One process, one handle per device (the C++ host of north_star): handles[0..n) live on n DIFFERENT devices; dev_vecs[i]
+ * is the DEVICE vector on handles[i]'s device that fbus_stats(.., out_dev) wrote.  After the call every dev_vecs[i] holds the
+ * combined vector, and out_host (optional, HOST, FBUS_NSTATS doubles) too.  The communicators are created on first use
+ * (ncclCommInitAll) and cached per device list.  n = 1 needs no NCCL.
+ */
+int fbus_stats_allreduce(fbus_handle* const* handles, int n, double* const* dev_vecs, double* out_host);
+/* One rank per process (torchrun, MPI): nccl_comm is an ncclComm_t the caller owns whose rank on this process uses the
+   handle's device; dev_vec as above.  Enqueued on the handle's stream; synchronises when out_host is given. */
+int fbus_stats_allreduce_comm(fbus_handle* h, void* nccl_comm, double* dev_vec, double* out_host);
 
 /* ---- synthetic Monte-Carlo streams (benchmark workload generator) ---- */
 

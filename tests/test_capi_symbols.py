@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported(built):
     for n in names:
         assert hasattr(lib, n), f"libfbus_ekf.so does not export {n}"
     assert sorted(capi.EXPORTED_SYMBOLS) == names
-    assert lib.fbus_abi_version() == capi.FBUS_ABI_VERSION == 2
+    assert lib.fbus_abi_version() == capi.FBUS_ABI_VERSION == 3
 
 
 def test_struct_sizes_match_header(built, tmp_path):
