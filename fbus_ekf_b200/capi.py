@@ -24,6 +24,7 @@ FBUS_IMU_F32_SENSOR = 1  # float, g and deg/s (the IMSEE SDK's ImuData; converte
 FBUS_ST_INIT_FAILED, FBUS_ST_RESET_SKIPPED, FBUS_ST_RESET_DONE, FBUS_ST_UPDATE_SKIPPED = 0x1, 0x2, 0x4, 0x8
 FBUS_ST_NONFINITE, FBUS_ST_NO_DETECTION, FBUS_ST_MARKER_REJECTED = 0x10, 0x20, 0x40
 FBUS_FLAG_JOSEPH = 0x1
+FBUS_FLAG_MATLAB = 0x2
 FBUS_MAX_MARKERS = 16
 FBUS_NSTATS = 8
 
@@ -139,6 +140,7 @@ def lib() -> C.CDLL:
     H = C.c_void_p
     sig = {
         "fbus_config_default": (C.c_int, [C.POINTER(FbusConfig)]),
+        "fbus_config_matlab": (C.c_int, [C.POINTER(FbusConfig)]),
         "fbus_create": (C.c_int, [C.POINTER(H), C.POINTER(FbusConfig), C.c_int, C.c_size_t]),
         "fbus_destroy": (C.c_int, [H]),
         "fbus_last_error": (C.c_char_p, [H]),
@@ -183,7 +185,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "fbus_config_default", "fbus_create", "fbus_destroy", "fbus_last_error", "fbus_abi_version", "fbus_synchronize",
+    "fbus_config_default", "fbus_config_matlab", "fbus_create", "fbus_destroy", "fbus_last_error", "fbus_abi_version", "fbus_synchronize",
     "fbus_batch", "fbus_stream", "fbus_init_gravity_gyrobias", "fbus_iir_prefilter", "fbus_init_position_quaternion", "fbus_propagate",
     "fbus_reset_state", "fbus_update", "fbus_step_windows", "fbus_refract_solve", "fbus_inair_solve", "fbus_undistort_fisheye", "fbus_solve_to_detections", "fbus_refract_solve_gn", "fbus_marker_pose", "fbus_get_state",
     "fbus_set_state", "fbus_clear_status", "fbus_stats", "fbus_stats_combine", "fbus_stats_allreduce", "fbus_stats_allreduce_comm", "fbus_synth_streams", "fbus_quat_from_rotmat",
@@ -195,6 +197,14 @@ def config_default() -> FbusConfig:
     rc = lib().fbus_config_default(C.byref(cfg))
     if rc != 0:
         raise RuntimeError("fbus_config_default failed")
+    return cfg
+
+
+def config_matlab() -> FbusConfig:
+    """the constants of matlab/FBUS_EKF.m (P0, measurement noise) with FBUS_FLAG_MATLAB set"""
+    cfg = FbusConfig()
+    if lib().fbus_config_matlab(C.byref(cfg)) != 0:
+        raise RuntimeError("fbus_config_matlab failed")
     return cfg
 
 

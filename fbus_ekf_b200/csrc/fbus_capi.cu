@@ -165,7 +165,11 @@ int launch_window(fbus_handle* h, WinParams& prm) {
     prm.stagger_cycles = (prm.mode & M_FUSED) ? h->stagger_cycles : 0u;
     const unsigned grid = (unsigned)((h->B + WIN_BS - 1) / WIN_BS);
     const bool jo = (h->k.flags & FBUS_FLAG_JOSEPH) != 0, f32 = prm.imu32 != nullptr;
-    if (h->lane_batch) {
+    if (h->k.flags & FBUS_FLAG_MATLAB) {  // MATLAB-semantics mode: the lanes-per-filter kernel at any batch size
+        const unsigned g32 = (unsigned)((h->B + 31) / 32);
+        if (f32) ekf_window_lane_kernel<false, true, true><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
+        else ekf_window_lane_kernel<false, false, true><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
+    } else if (h->lane_batch) {
         const unsigned g32 = (unsigned)((h->B + 31) / 32);
         if (f32) {
             if (jo) ekf_window_lane_kernel<true, true><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
@@ -226,6 +230,11 @@ int fbus_config_default(fbus_config* cfg) {
     config_default(cfg);
     return FBUS_OK;
 }
+int fbus_config_matlab(fbus_config* cfg) {
+    if (!cfg) return FBUS_E_BADARG;
+    config_matlab(cfg);
+    return FBUS_OK;
+}
 
 void fbus_quat_from_rotmat(const double R[9], double q[4]) { R2q(R, q); }
 
@@ -243,6 +252,10 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
     h->device = device;
     h->B = batch;
     h->cfg = *cfg;
+    if ((cfg->flags & FBUS_FLAG_MATLAB) && (cfg->flags & FBUS_FLAG_JOSEPH)) {
+        delete h;
+        return fail(nullptr, FBUS_E_BADARG, "fbus_create: FBUS_FLAG_MATLAB and FBUS_FLAG_JOSEPH cannot be combined");
+    }
     if (make_dev_consts(cfg, &h->k, &h->tab) != FBUS_OK) {
         delete h;
         return fail(nullptr, FBUS_E_BADARG, "fbus_create: bad config (n_markers)");
@@ -301,6 +314,8 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
         if (e != cudaSuccess) return bail("cudaFuncSetAttribute(lane)", e);
         const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
         e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);

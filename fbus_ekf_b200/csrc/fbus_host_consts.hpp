@@ -25,6 +25,70 @@ inline void host_quat_right(const double* q, double* m) {  // matrix_math.hpp:64
     memcpy(m, t, sizeof t);
 }
 
+// matlab/rotmat_to_quaternion.m:23-43: the unit eigenvector of the largest eigenvalue of the symmetric 4x4 matrix K(R^T)
+// (the best-fit unit quaternion of a not exactly orthonormal R), by cyclic Jacobi rotations.  MATLAB leaves the sign to
+// LAPACK; no filter output except the sign of the state quaternion depends on it (see oracle/fbus_oracle_matlab.py): here the
+// first component that is not ~0 is made positive.
+inline void rotmat_to_quat_eig(const double* Rin, double* q) {
+    double R[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = Rin[j * 3 + i];  // R = R'
+    double K[16];
+    K[0] = R[0] - R[4] - R[8];
+    K[1] = K[4] = R[3] + R[1];
+    K[2] = K[8] = R[6] + R[2];
+    K[3] = K[12] = R[5] - R[7];
+    K[5] = R[4] - R[0] - R[8];
+    K[6] = K[9] = R[7] + R[5];
+    K[7] = K[13] = R[6] - R[2];
+    K[10] = R[8] - R[0] - R[4];
+    K[11] = K[14] = R[1] - R[3];
+    K[15] = R[0] + R[4] + R[8];
+    for (int i = 0; i < 16; ++i) K[i] /= 3.0;
+    double V[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 4; ++p)
+            for (int r = p + 1; r < 4; ++r) off += K[p * 4 + r] * K[p * 4 + r];
+        if (off < 1e-34) break;
+        for (int p = 0; p < 4; ++p)
+            for (int r = p + 1; r < 4; ++r) {
+                const double apq = K[p * 4 + r];
+                if (apq == 0.0) continue;
+                const double th = (K[r * 4 + r] - K[p * 4 + p]) / (2.0 * apq);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                for (int x = 0; x < 4; ++x) {  // K <- K J
+                    const double kp = K[x * 4 + p], kr = K[x * 4 + r];
+                    K[x * 4 + p] = cs * kp - sn * kr;
+                    K[x * 4 + r] = sn * kp + cs * kr;
+                }
+                for (int x = 0; x < 4; ++x) {  // K <- J^T K
+                    const double kp = K[p * 4 + x], kr = K[r * 4 + x];
+                    K[p * 4 + x] = cs * kp - sn * kr;
+                    K[r * 4 + x] = sn * kp + cs * kr;
+                }
+                for (int x = 0; x < 4; ++x) {  // V <- V J
+                    const double vp = V[x * 4 + p], vr = V[x * 4 + r];
+                    V[x * 4 + p] = cs * vp - sn * vr;
+                    V[x * 4 + r] = sn * vp + cs * vr;
+                }
+            }
+    }
+    int best = 0;
+    for (int i = 1; i < 4; ++i)
+        if (K[i * 4 + i] > K[best * 4 + best]) best = i;
+    const double v[4] = {V[0 * 4 + best], V[1 * 4 + best], V[2 * 4 + best], V[3 * 4 + best]};
+    double nrm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+    q[0] = v[3] / nrm; q[1] = v[0] / nrm; q[2] = v[1] / nrm; q[3] = v[2] / nrm;  // q = [V(4); V(1); V(2); V(3)]
+    for (int i = 0; i < 4; ++i)
+        if (fabs(q[i]) > 1e-12) {
+            if (q[i] < 0)
+                for (int j = 0; j < 4; ++j) q[j] = -q[j];
+            break;
+        }
+}
+
 inline int make_dev_consts(const fbus_config* c, DevConsts* k, MarkerTable* tab) {
     if (c->n_markers < 0 || c->n_markers > MAXM) return FBUS_E_BADARG;
     memset(k, 0, sizeof *k);
@@ -35,7 +99,9 @@ inline int make_dev_consts(const fbus_config* c, DevConsts* k, MarkerTable* tab)
         for (int j = 0; j < 3; ++j) k->R_IL[i * 3 + j] = flip[i] * c->tsc_left[i * 4 + j];
         P_LI[i] = flip[i] * c->tsc_left[i * 4 + 3];
     }
-    R2q(k->R_IL, k->Q_IL);  // Quaterniond(R_I_L), NOT normalised (filter.cpp:370)
+    const bool matlab = (c->flags & FBUS_FLAG_MATLAB) != 0;
+    if (matlab) rotmat_to_quat_eig(k->R_IL, k->Q_IL);  // rotmat_to_quaternion.m (unit quaternion)
+    else R2q(k->R_IL, k->Q_IL);  // Quaterniond(R_I_L), NOT normalised (filter.cpp:370)
     for (int i = 0; i < 3; ++i)  // P_I_L = -R_I_L^T * P_L_I (filter.cpp:372)
         k->P_IL[i] = -(k->R_IL[i] * P_LI[0] + k->R_IL[3 + i] * P_LI[1] + k->R_IL[6 + i] * P_LI[2]);
     k->Qd[0] = c->accel_n_cov; k->Qd[1] = c->gyro_n_cov; k->Qd[2] = c->accel_b_cov; k->Qd[3] = c->gyro_b_cov;
@@ -84,7 +150,8 @@ inline int make_dev_consts(const fbus_config* c, DevConsts* k, MarkerTable* tab)
         MarkerConst& mk = tab->mk[m];
         mk.id = c->marker_id[m];
         for (int i = 0; i < 3; ++i) mk.p[i] = c->marker_pos[m * 3 + i];
-        R2q(&c->marker_rot[m * 9], mk.q);  // main.cpp:201
+        if (matlab) rotmat_to_quat_eig(&c->marker_rot[m * 9], mk.q);
+        else R2q(&c->marker_rot[m * 9], mk.q);  // main.cpp:201
         double Rq[16], A1[16];
         host_quat_right(mk.q, Rq);
         for (int i = 0; i < 4; ++i)
@@ -158,6 +225,17 @@ inline void config_default(fbus_config* c) {
     }
     c->flags = 0;
     c->imu_g = 9.802;  // camerainfo1.yml "g" (IMUInfo.g, common.hpp:148)
+}
+
+// the constants of matlab/FBUS_EKF.m:28-41,83-112 on top of the defaults: P0, measurement noise, FBUS_FLAG_MATLAB
+inline void config_matlab(fbus_config* c) {
+    config_default(c);
+    const double p0[6] = {0.0001, 0.1, 0.0001, 0.001, 0.001, 100.0};  // FBUS_EKF.m:86-98
+    memcpy(c->p0_diag, p0, sizeof p0);
+    c->pos_n_cov = 0.01; c->quat_n_cov = 0.01;                        // FBUS_EKF.m:32-33
+    // FBUS_EKF.m:36-39 and 101-105: systemNoise = diag(1e-3 I, 1e-4 I, 1e-3 I, 1e-4 I) on the v, theta, b_a, b_g rows -- the
+    // values of paramconfig.yml, i.e. the defaults
+    c->flags = FBUS_FLAG_MATLAB;
 }
 
 }  // namespace fbus

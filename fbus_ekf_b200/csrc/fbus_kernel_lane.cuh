@@ -40,8 +40,9 @@ constexpr int LANE_TS = 19;               // row stride of the per-filter transp
 constexpr int LANE_T = 9 * LANE_TS;       // doubles of transpose scratch per filter
 constexpr size_t LANE_SMEM = (size_t)(LX_TOTAL * 32 + LANE_T * 32) * sizeof(double);
 
-// y = F x on one column (rows 0..8 change):  filter.cpp:598-604 with A = -R[a]x dt, B = -R dt, Wm = -[w]x dt
-__device__ __forceinline__ void lane_apply_F(double* x, const double* A, const double* Bm, double u0, double u1, double u2, double dt) {
+// y = F x on one column (rows 0..8 change):  filter.cpp:598-604 with A = -R[a]x dt, B = -R dt and W = F[theta,theta] - I in
+// full (-[w]x dt for the C++ semantics, expm(-[w]x dt) - I for the MATLAB ones: the nominal warp decides, the lanes just apply it)
+__device__ __forceinline__ void lane_apply_F(double* x, const double* A, const double* Bm, const double* W, double dt) {
     double y[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -57,13 +58,13 @@ __device__ __forceinline__ void lane_apply_F(double* x, const double* A, const d
         }
         y[3 + i] = t;
     }
-    {
-        double t0 = x[6], t1 = x[7], t2 = x[8];
-        t0 -= dt * x[12]; t1 -= dt * x[13]; t2 -= dt * x[14];
-        t0 += u2 * x[7]; t0 -= u1 * x[8];
-        t1 += u0 * x[8]; t1 -= u2 * x[6];
-        t2 += u1 * x[6]; t2 -= u0 * x[7];
-        y[6] = t0; y[7] = t1; y[8] = t2;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double t = x[6 + i];
+        t -= dt * x[12 + i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t += W[i * 3 + c] * x[6 + c];
+        y[6 + i] = t;
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) x[i] = y[i];
@@ -106,15 +107,14 @@ __device__ __forceinline__ void lane_cov_role(const WinParams& prm, const DevCon
             cta_bar<NT>();  // record (i) is complete; the nominal warp moves on to sample i+1
             const int slot = (int)((i - lo) & 1u);
             const bool valid = act && sflag[slot][f] != 0;
-            const double* rec = X + (size_t)slot * 22 * 32;
-            double A[9], Bm[9];
+            const double* rec = X + (size_t)slot * LX_REC * 32;
+            double A[9], Bm[9], Wm[9];
 #pragma unroll
-            for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * 32]; Bm[e] = rec[(size_t)(9 + e) * 32]; }
-            const double u0 = rec[(size_t)18 * 32], u1 = rec[(size_t)19 * 32], u2 = rec[(size_t)20 * 32];
-            const double dt = rec[(size_t)21 * 32];
+            for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * 32]; Bm[e] = rec[(size_t)(9 + e) * 32]; Wm[e] = rec[(size_t)(18 + e) * 32]; }
+            const double dt = rec[(size_t)27 * 32];
             if (valid) {  // A: M = F P on both columns
-                lane_apply_F(c0, A, Bm, u0, u1, u2, dt);
-                lane_apply_F(c1, A, Bm, u0, u1, u2, dt);
+                lane_apply_F(c0, A, Bm, Wm, dt);
+                lane_apply_F(c1, A, Bm, Wm, dt);
 #pragma unroll
                 for (int r = 0; r < 9; ++r) {  // T: publish the rows of M that change
                     T[r * LANE_TS + l] = c0[r];
@@ -125,7 +125,7 @@ __device__ __forceinline__ void lane_cov_role(const WinParams& prm, const DevCon
             if (valid) {  // B: column l of F P F^T = F (row l of M)^T
 #pragma unroll
                 for (int c = 0; c < 18; ++c) c0[c] = T[l * LANE_TS + c];
-                lane_apply_F(c0, A, Bm, u0, u1, u2, dt);
+                lane_apply_F(c0, A, Bm, Wm, dt);
 #pragma unroll
                 for (int r = 3; r < 9; ++r) c0[r] += (r == l) ? q0 : 0.0;
 #pragma unroll
@@ -233,7 +233,7 @@ __device__ __forceinline__ void lane_cov_role(const WinParams& prm, const DevCon
     }
 }
 
-template <bool JOSEPH, bool IMU32>
+template <bool JOSEPH, bool IMU32, bool MATLAB = false>
 __global__ void __launch_bounds__(LANE_NT, 1) ekf_window_lane_kernel(const __grid_constant__ WinParams prm, const __grid_constant__ DevConsts k) {
     extern __shared__ double smem[];
     __shared__ SplitShared sh;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(LANE_NT, 1) ekf_window_lane_kernel(const __gri
     } else {
         const size_t b0 = (size_t)blockIdx.x * 32 + lane;
         const bool live = b0 < prm.B;
-        nominal_role<32, false, IMU32, true, JOSEPH>(prm, k, smem, sh, sflag, lane, live ? b0 : prm.B - 1, live);
+        nominal_role<32, false, IMU32, true, JOSEPH, MATLAB>(prm, k, smem, sh, sflag, lane, live ? b0 : prm.B - 1, live);
     }
 }
 

@@ -242,6 +242,11 @@ struct FramePlan {
     double t_det, t_end;
     double y[7];             // measurement of the update (p, q of the chosen detection)
     double qv[4], pv[3];     // vision-only pose for init / reset
+    // MATLAB-semantics mode only (dead in the other instantiations)
+    double Rv[9];            // quaternion_to_rotmat of the un-normalised Q_IG (State.rotateMat after init / reset)
+    double t_init;           // time of the last IMU sample not later than the initialising frame (preImuTime, FBUS_EKF.m:175)
+    double t_img_new;        // preImgTime after this frame
+    bool set_t_img;
 };
 
 template <int BSF>
@@ -372,10 +377,117 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
     }
 }
 
+// MATLAB-semantics mode (FBUS_FLAG_MATLAB): what a frame does in matlab/FBUS_EKF.m:151-197.  Differences from plan_frame:
+// nearest marker without hysteresis or range gate (MeasureUpdate.m:51-60); a gap between two IMAGE times resets and skips
+// propagation and update (FBUS_EKF.m:168-171, ResetState.m); the initialising frame is processed by the main loop as well
+// (FBUS_EKF.m:116-151: the loop starts again at the first image row); the vision-only pose of every frame is that of
+// ComputeVisionOnlyResults.m (normalised Q_IG).  An unknown marker id, on which the MATLAB script would stop with an index error,
+// skips the frame for that filter with a status bit, like the C++ path.
+template <int BSF>
+__device__ __forceinline__ void plan_frame_matlab(const WinParams& prm, const DevConsts& k, uint32_t w, size_t b, bool live, uint32_t cursor,
+                                                  double t_img, int inited, int& prev_id, int& status, FramePlan& pl) {
+    const size_t B = prm.B;
+    const int mode = prm.mode;
+    const bool fused = (mode & M_FUSED) != 0;
+    pl.do_prop = pl.apply_init = pl.apply_reset = pl.set_t_img = false;
+    pl.req = 0;
+    pl.p_first = pl.p_end = 0;
+    pl.n_init_erase = 0;
+    pl.t_det = pl.t_end = pl.t_init = pl.t_img_new = 0.0;
+    if (!(mode & (M_INIT | M_RESET | M_UPDATE | M_FUSED))) {  // un-fused propagate
+        pl.do_prop = true;
+        pl.p_first = prm.prop_first;
+        pl.p_end = prm.prop_first + prm.prop_count;
+        pl.t_end = prm.prop_t_end;
+        return;
+    }
+    pl.t_det = prm.det_t[w];
+    int n_det = 0, idx_near = 0;
+    double md = 10.0;
+    for (int s = 0; s < prm.m; ++s) {
+        const size_t slot = (size_t)w * prm.m + s;
+        if (prm.det_id[slot * B + b] < 0) continue;
+        const double* pp = prm.det_pose + slot * 7 * B + b;
+        const double px = pp[0], py = pp[B], pz = pp[2 * B];
+        const double dist = sqrt_d(px * px + py * py + pz * pz);
+        if (n_det == 0) idx_near = s;
+        if (dist < md) { md = dist; idx_near = s; }
+        ++n_det;
+    }
+    if (n_det == 0) { status |= FBUS_ST_NO_DETECTION; return; }
+    const size_t slot = (size_t)w * prm.m + idx_near;
+    const int did = prm.det_id[slot * B + b];
+    const int mk = find_marker(k, prm.tab, did);
+    if (mk < 0) {
+        status |= inited ? (FBUS_ST_UPDATE_SKIPPED | FBUS_ST_RESET_SKIPPED) : FBUS_ST_INIT_FAILED;
+        return;
+    }
+    const MarkerConst mkc = prm.tab->mk[mk];
+    const double* pp = prm.det_pose + slot * 7 * B + b;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) pl.y[c] = pp[(size_t)c * B];
+    vision_pose<true>(k, mkc, pl.y, pl.y + 3, pl.qv, pl.Rv, pl.pv);  // InitPositionAndQuaternion.m / ResetState.m
+    if (live) {  // ComputeVisionOnlyResults.m: the same with Q_IG normalised first
+        double qn[4] = {pl.qv[0], pl.qv[1], pl.qv[2], pl.qv[3]}, Rn[9], u[3], r1[3], r2[3];
+        qnormalize(qn);
+        q2R_matlab(qn, Rn);
+        mat3t_vec(k.R_IL, pl.y, u);
+        mat3_vec(Rn, k.P_IL, r1);
+        mat3_vec(Rn, u, r2);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) prm.nom[(size_t)(F_PV + i) * B + b] = (mkc.p[i] - r1[i]) - r2[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) prm.nom[(size_t)(F_QV + i) * B + b] = qn[i];
+    }
+    bool run_frame = false;  // propagate + update
+    if (fused) {
+        if (!inited) {
+            uint32_t n_before = 0;
+            const uint32_t hi = prm.win_off[w + 1];
+            for (uint32_t i = cursor; i < hi; ++i) {
+                if (prm.imu_t[i] > pl.t_det) break;
+                pl.t_init = prm.imu_t[i];
+                ++n_before;
+            }
+            if (n_before == 0) { status |= FBUS_ST_INIT_FAILED; return; }
+            pl.apply_init = true;
+            pl.n_init_erase = n_before;
+            cursor += n_before;
+            run_frame = true;  // preImgTime is still 0: no reset, the (empty) IMU loop, then MeasureUpdate
+        } else if (t_img != 0.0 && pl.t_det - t_img > k.reset_gap) {
+            pl.apply_reset = true;
+            status |= FBUS_ST_RESET_DONE;
+        } else {
+            run_frame = true;
+        }
+        pl.set_t_img = true;
+        pl.t_img_new = pl.t_det;
+        if (run_frame) {
+            pl.do_prop = true;
+            pl.p_first = cursor;
+            pl.p_end = prm.win_off[w + 1];
+            pl.t_end = pl.t_det;
+        }
+    } else {
+        if (mode & M_INIT) {
+            if (prm.n_imu_before == 0) { status |= FBUS_ST_INIT_FAILED; return; }
+            pl.apply_init = true;
+            pl.t_init = pl.t_det;  // the un-fused call has no IMU buffer to take preImuTime from
+        }
+        if (mode & M_RESET) { pl.apply_reset = true; status |= FBUS_ST_RESET_DONE; }  // ResetState.m is unconditional
+        run_frame = (mode & M_UPDATE) != 0;
+    }
+    if (run_frame) {
+        prev_id = did;
+        pl.req = mk + 1;
+    }
+}
+
 // exchange area of the lanes-per-filter kernel (fbus_kernel_lane.cuh), doubles per filter laid out [entry][32 filters]:
 // ring 2 x 22 | P6 (6x6 of the p/theta rows and columns) | Lc (21, Joseph form only) | y (6) or z (7) | dx (18) |
 // X = L^-1 Hs (42: scratch of the update prologue, and the 7-row factor the lanes read in the default form)
-constexpr int LX_P6 = 44, LX_CM = 80, LX_Y = 101, LX_DX = 108, LX_SCR = 126, LX_TOTAL = 168;
+// (a ring slot has 28 doubles here: A 9, B 9, W = F[theta,theta] - I 9, dt -- the MATLAB-semantics mode needs the full W)
+constexpr int LX_REC = 28, LX_P6 = 56, LX_CM = 92, LX_Y = 113, LX_DX = 120, LX_SCR = 138, LX_TOTAL = 180;
 constexpr int LANE_NT = 384;  // 11 covariance warps (3 filters each, 9 lanes per filter) + the nominal warp
 
 // the p/theta sub-matrix P6 = P[{0,1,2,6,7,8}, {0,1,2,6,7,8}] as the covariance lanes publish it: the only part of P the
@@ -407,11 +519,13 @@ struct P6View {
 // records need no neutral content, and the update is split differently -- this warp (one lane per filter) runs the
 // state-only prologue (predicted measurement, Hs, S, the gain factors) from the published P6 and the error-state
 // injection, the covariance lanes run the sweep P -= Z^T Z and dx = Z^T y.
-template <int BSF, bool TM, bool IMU32 = false, bool LANE = false, bool JOSEPH = false>
+template <int BSF, bool TM, bool IMU32 = false, bool LANE = false, bool JOSEPH = false, bool MATLAB = false>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
                                              int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
     constexpr int NT = LANE ? LANE_NT : 2 * BSF, NW = BSF / 32;
     static_assert(!LANE || BSF == 32, "the lanes-per-filter kernel has 32 filters per CTA");
+    static_assert(!MATLAB || (LANE && !JOSEPH), "the MATLAB-semantics mode runs on the lanes-per-filter kernel, reference update form");
+    constexpr int REC = LANE ? LX_REC : 22;  // doubles per ring slot
     const size_t B = prm.B;
     double* const X = smem + (size_t)((TM || LANE) ? 0 : NPK) * BSF + fl;
     auto sbar = [&](int pair) {
@@ -442,16 +556,26 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     uint32_t pf_i = 0xffffffffu;
     double pf_st = 0.0, pf_sd[6];
 
+    double t_img = MATLAB ? prm.nom[(size_t)F_TIMG * B + b] : 0.0;  // preImgTime (FBUS_EKF.m:144)
+    auto plan = [&](uint32_t wf, FramePlan& out) {
+        if constexpr (MATLAB) plan_frame_matlab<BSF>(prm, k, wf, b, live, cursor, t_img, inited, prev_id, status, out);
+        else plan_frame<BSF>(prm, k, wf, b, live, cursor, n.t, inited, prev_id, status, out);
+    };
     FramePlan pl;
-    if (prm.w0 < prm.w1) plan_frame<BSF>(prm, k, prm.w0, b, live, cursor, n.t, inited, prev_id, status, pl);
+    if (prm.w0 < prm.w1) plan(prm.w0, pl);
 
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
         // ---- apply the planned F6b InitializePose / F5 ResetSystemState --------------------------------------
         if (pl.apply_init) {
-            n.t = pl.t_det;
+            n.t = MATLAB ? pl.t_init : pl.t_det;
 #pragma unroll
             for (int i = 0; i < 4; ++i) n.q[i] = pl.qv[i];
-            q2R(pl.qv, n.R);
+            if constexpr (MATLAB) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) n.R[i] = pl.Rv[i];
+            } else {
+                q2R(pl.qv, n.R);
+            }
 #pragma unroll
             for (int i = 0; i < 3; ++i) n.p[i] = pl.pv[i];
             n.g[0] = 9.8; n.g[1] = 0.0; n.g[2] = 0.0;  // filter.cpp:387
@@ -459,12 +583,23 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             if (fused) cursor += pl.n_init_erase;  // only the samples not later than the frame are erased (filter.cpp:299-305,390)
         }
         if (pl.apply_reset) {
-            n.t = pl.t_det;
+            if constexpr (MATLAB) {  // ResetState.m:70-79: rotateMat refreshed, b_g and the IMU time base kept
 #pragma unroll
-            for (int i = 0; i < 4; ++i) n.q[i] = pl.qv[i];
+                for (int i = 0; i < 4; ++i) n.q[i] = pl.qv[i];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { n.p[i] = pl.pv[i]; n.v[i] = 0.0; n.ba[i] = 0.0; n.bg[i] = 0.0; }
+                for (int i = 0; i < 9; ++i) n.R[i] = pl.Rv[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { n.p[i] = pl.pv[i]; n.v[i] = 0.0; n.ba[i] = 0.0; }
+            } else {
+                n.t = pl.t_det;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) n.q[i] = pl.qv[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { n.p[i] = pl.pv[i]; n.v[i] = 0.0; n.ba[i] = 0.0; n.bg[i] = 0.0; }
+            }
         }
+        const double t_img_frame = t_img;  // samples older than the PREVIOUS image time are skipped (FBUS_EKF.m:180-183)
+        if (MATLAB && pl.set_t_img) t_img = pl.t_img_new;
         const bool do_prop = pl.do_prop;
         const uint32_t p_first = pl.p_first, p_end = pl.p_end;
         const double t_end = pl.t_end;
@@ -484,7 +619,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         int fs = 0;
         if (lo < hi) {
             fs = (int)((hi - lo) & 1u);
-            const double start = n.t;
+            const double start = MATLAB ? t_img_frame : n.t;
             bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
             uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
             const bool pfi = (pf_i == lo);
@@ -506,6 +641,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                 if (open && i >= p_first && i < p_end) {
                     if (ti < start) {
                         consumed = i + 1;
+                        if (MATLAB) n.t = ti;  // preImuTime moves on (FBUS_EKF.m:181)
                     } else if (ti > t_end) {
                         open = false;  // this sample stays buffered
                     } else {
@@ -516,17 +652,32 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                         for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
                         cov_coeffs(n.R, av, wv, dt, A, Bm, u);  // F1 uses the CARRIED rotmatI2G (A.3-2,3)
-                        double* rec = X + (size_t)slot * 22 * BSF;
+                        double* rec = X + (size_t)slot * REC * BSF;
 #pragma unroll
                         for (int e = 0; e < 9; ++e) { rec[(size_t)e * BSF] = A[e]; rec[(size_t)(9 + e) * BSF] = Bm[e]; }
-                        rec[(size_t)18 * BSF] = u[0]; rec[(size_t)19 * BSF] = u[1]; rec[(size_t)20 * BSF] = u[2];
-                        rec[(size_t)21 * BSF] = dt;
-                        propagate_nominal(n, dt, d, d + 3);  // F2 after F1's coefficients were taken (filter.cpp:509-513)
+                        if constexpr (LANE) {  // W = F[theta,theta] - I in full
+                            double Wm[9];
+                            if constexpr (MATLAB) {
+                                expm_rot_minus_I(wv, dt, Wm);  // ImuUpdate.m:68
+                            } else {                            // -[w]x dt, filter.cpp:603
+                                Wm[0] = 0.0; Wm[1] = u[2]; Wm[2] = -u[1];
+                                Wm[3] = -u[2]; Wm[4] = 0.0; Wm[5] = u[0];
+                                Wm[6] = u[1]; Wm[7] = -u[0]; Wm[8] = 0.0;
+                            }
+#pragma unroll
+                            for (int e = 0; e < 9; ++e) rec[(size_t)(18 + e) * BSF] = Wm[e];
+                            rec[(size_t)27 * BSF] = dt;
+                        } else {
+                            rec[(size_t)18 * BSF] = u[0]; rec[(size_t)19 * BSF] = u[1]; rec[(size_t)20 * BSF] = u[2];
+                            rec[(size_t)21 * BSF] = dt;
+                        }
+                        if constexpr (MATLAB) propagate_nominal_matlab(n, dt, d, d + 3);
+                        else propagate_nominal(n, dt, d, d + 3);  // F2 after F1's coefficients were taken (filter.cpp:509-513)
                         n.t = ti;
                     }
                 }
                 if (TM && !LANE && !valid) {  // tensor-memory mode: the covariance warp runs every lane, invalid ones with F = I
-                    double* rec = X + (size_t)slot * 22 * BSF;
+                    double* rec = X + (size_t)slot * REC * BSF;
 #pragma unroll
                     for (int e = 0; e < 22; ++e) rec[(size_t)e * BSF] = 0.0;
                 }
@@ -573,7 +724,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                         // across the wait spill at this kernel's 168 registers)
                         double L[28], Li[7], zv[7];
                         UpdHs hh;
-                        update_hs(n, k, mkc, pl.y, pl.y + 3, hh);
+                        update_hs<MATLAB>(n, k, mkc, pl.y, pl.y + 3, hh);
                         update_prologue_sx<BSF, BSF, P6View>(P6View{X + (size_t)LX_P6 * BSF}, k, hh, L, Li, zv, X + (size_t)LX_SCR * BSF);
 #pragma unroll
                         for (int c = 0; c < 7; ++c) X[(size_t)(LX_Y + c) * BSF] = zv[c];
@@ -593,7 +744,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                 for (int c = 0; c < 6; ++c) pf_sd[c] = imu_sample_t<IMU32>(prm, k.imu_g, cursor, c, B, b);
             }
-            plan_frame<BSF>(prm, k, w + 1, b, live, cursor, n.t, inited, prev_id, status, nx);
+            plan(w + 1, nx);
         }
         if (any) {
             sbar(wq);  // (d) results posted
@@ -658,6 +809,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     prm.init[b] = inited;
     if (fused) prm.cursor_io[b] = cursor;
     prm.status[b] = status;
+    if (MATLAB) prm.nom[(size_t)F_TIMG * B + b] = t_img;
 }
 
 // Two CTAs can share an SM when BSF = 64 (2 x 110 KB of shared memory, 2 x 128 threads x 255 registers).  Warp w of

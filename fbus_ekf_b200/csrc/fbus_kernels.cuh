@@ -18,8 +18,8 @@
 
 namespace fbus {
 
-constexpr int NOM_FIELDS = 36;  // t q4 R9 p3 v3 ba3 bg3 g3 pv3 qv4
-enum NomField { F_T = 0, F_Q = 1, F_R = 5, F_P = 14, F_V = 17, F_BA = 20, F_BG = 23, F_G = 26, F_PV = 29, F_QV = 32 };
+constexpr int NOM_FIELDS = 37;  // t q4 R9 p3 v3 ba3 bg3 g3 pv3 qv4 + t_img (MATLAB-semantics mode: time of the previous image frame)
+enum NomField { F_T = 0, F_Q = 1, F_R = 5, F_P = 14, F_V = 17, F_BA = 20, F_BG = 23, F_G = 26, F_PV = 29, F_QV = 32, F_TIMG = 36 };
 
 enum WinMode { M_INIT = 1, M_RESET = 2, M_PROP = 4, M_UPDATE = 8, M_FUSED = 16 };
 

@@ -725,6 +725,83 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// MATLAB-semantics mode (FBUS_FLAG_MATLAB): the numerics of matlab/*.m where they differ from filter.cpp
+// ------------------------------------------------------------------------------------------------
+// quaternion_to_rotmat.m:24-32: the w^2+x^2-y^2-z^2 form (equal to Eigen's toRotationMatrix only for a unit quaternion; the
+// MATLAB filter applies it to un-normalised products)
+FBUS_HD void q2R_matlab(const double* q, double* R) {
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z);           R[2] = 2 * (x * z + w * y);
+    R[3] = 2 * (x * y + w * z);           R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+    R[6] = 2 * (x * z - w * y);           R[7] = 2 * (y * z + w * x);           R[8] = w * w - x * x - y * y + z * z;
+}
+// ImuUpdate.m:37-60,76-79: always the axis-angle increment (axis = w/|w|: NaN for w = 0, as MATLAB), rotation matrices of
+// the UN-normalised products, R0 = the carried State.rotateMat, State.rotateMat <- R(qT), State.quaternion <- qT/|qT|
+FBUS_HD void propagate_nominal_matlab(Nominal& n, double dt, const double* accel, const double* gyro) {
+    double w[3];
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) w[i] = gyro[i] - n.bg[i];
+    const double wn2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    const double inv = rsqrt_d(wn2);
+    const double wn = wn2 * inv;
+    const double ax[3] = {w[0] * inv, w[1] * inv, w[2] * inv};
+    const double dth = wn * (dt < 0 ? -dt : dt);  // norm(w*dt)
+    double sh, ch;
+    sincos_d(dth * 0.25, &sh, &ch);               // qHalfT: axisangle(w, dtheta/2) -> half angle dtheta/4
+    const double sf = 2.0 * sh * ch, cf = 1.0 - 2.0 * sh * sh;
+    const double dqh[4] = {ch, sh * ax[0], sh * ax[1], sh * ax[2]};
+    const double dq[4] = {cf, sf * ax[0], sf * ax[1], sf * ax[2]};
+    double qh[4], qn[4], R0[9], Rh[9];
+    qmul(n.q, dqh, qh);
+    qmul(n.q, dq, qn);
+    FBUS_UNROLL
+    for (int i = 0; i < 9; ++i) R0[i] = n.R[i];
+    q2R_matlab(qh, Rh);
+    q2R_matlab(qn, n.R);
+    qnormalize(qn);
+    FBUS_UNROLL
+    for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
+    double a[3], k1[3], k2[3], k4[3];
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) a[i] = accel[i] - n.ba[i];
+    mat3_vec(R0, a, k1);
+    mat3_vec(Rh, a, k2);
+    mat3_vec(n.R, a, k4);
+    const double dt6 = dt * (1.0 / 6.0), dt2 = dt * 0.5;
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const double kv1 = k1[i] + n.g[i], kv2 = k2[i] + n.g[i], kv4 = k4[i] + n.g[i];
+        const double v0 = n.v[i];
+        n.v[i] = v0 + dt6 * (kv1 + 2 * kv2 + 2 * kv2 + kv4);
+        const double kp2 = v0 + kv1 * dt2, kp3 = v0 + kv2 * dt2;
+        n.p[i] = n.p[i] + dt6 * (v0 + 2 * kp2 + 2 * kp3 + kp3);
+    }
+}
+// ImuUpdate.m:68: Fx(7:9,7:9) = expm(-[w]x dt), returned as W = expm(-[w]x dt) - I (the kernels add the identity themselves).
+// Rodrigues: expm(-K) = I - (sin t / t) K + ((1 - cos t) / t^2) K^2 with K = [w dt]x, t = |w dt|.
+FBUS_HD void expm_rot_minus_I(const double* w, double dt, double* W) {
+    const double v[3] = {w[0] * dt, w[1] * dt, w[2] * dt};
+    const double t2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    double s1 = 1.0, c1 = 0.5;  // limits for t -> 0
+    if (t2 > 1e-16) {
+        const double it = rsqrt_d(t2), t = t2 * it;
+        double sh, ch;
+        sincos_d(0.5 * t, &sh, &ch);
+        s1 = 2.0 * sh * ch * it;         // sin t / t
+        c1 = 2.0 * sh * sh * (it * it);  // (1 - cos t) / t^2
+    }
+    // K = [v]x ; K^2 = v v^T - t^2 I
+    const double K[9] = {0.0, -v[2], v[1], v[2], 0.0, -v[0], -v[1], v[0], 0.0};
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i)
+        FBUS_UNROLL
+        for (int j = 0; j < 3; ++j) {
+            const double k2 = v[i] * v[j] - ((i == j) ? t2 : 0.0);
+            W[i * 3 + j] = c1 * k2 - s1 * K[i * 3 + j];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
 // marker-map lookup (std::map::find on markerPoseServer_, filter.cpp:353,442,671)
 // ------------------------------------------------------------------------------------------------
 FBUS_HD int find_marker(const DevConsts& k, const MarkerTable* tab, int id) {
@@ -736,12 +813,14 @@ FBUS_HD int find_marker(const DevConsts& k, const MarkerTable* tab, int id) {
 
 // vision-only pose (shared by InitializePose filter.cpp:379-384 and ResetSystemState :454-459):
 //   q = Q_M * conj(Q_ML) * Q_IL ;  Rq = R(q) ;  p = P_M - Rq*P_IL - Rq*R_IL^T*P_ML
+template <bool MATLAB = false>
 FBUS_HD void vision_pose(const DevConsts& k, const MarkerConst& mk, const double* pml, const double* qml, double* q,
                          double* Rq, double* p) {
     double t1[4];
     qmul_conjb(mk.q, qml, t1);
     qmul(t1, k.Q_IL, q);
-    q2R(q, Rq);
+    if (MATLAB) q2R_matlab(q, Rq);  // InitPositionAndQuaternion.m / ResetState.m: quaternion_to_rotmat of the un-normalised Q_IG
+    else q2R(q, Rq);
     double u[3], r1[3], r2[3];
     mat3t_vec(k.R_IL, pml, u);  // R_IL^T * P_ML
     mat3_vec(Rq, k.P_IL, r1);
@@ -799,6 +878,7 @@ struct CholStep<N, N> {
 struct UpdHs {
     double Hp0[9], Hp2[9], Hq[12], r[7];
 };
+template <bool MATLAB = false>
 FBUS_HD void update_hs(const Nominal& n, const DevConsts& k, const MarkerConst& mk, const double* yP, const double* yQ, UpdHs& hh) {
     double* const Hp0 = hh.Hp0;
     double* const Hp2 = hh.Hp2;
@@ -857,7 +937,7 @@ FBUS_HD void update_hs(const Nominal& n, const DevConsts& k, const MarkerConst& 
                 Hq[i * 3 + j] = s;
             }
         FBUS_UNROLL
-        for (int i = 0; i < 4; ++i) r[3 + i] = yQ[i] - sg * hQ[i];
+        for (int i = 0; i < 4; ++i) r[3 + i] = MATLAB ? 0.0 : (yQ[i] - sg * hQ[i]);  // MeasureUpdate.m:88 zeroes the quaternion rows
     }
 }
 template <int S, int XS, class CV = Cov<S>>

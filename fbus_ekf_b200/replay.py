@@ -80,6 +80,32 @@ def solve_image_rows(corner_rows: np.ndarray, cfg=None, device: int = 0, gn_iter
     return rows[np.asarray(valid).astype(bool)]
 
 
+def recorded_frames(t_imu: np.ndarray, t_frames: np.ndarray, groups, cfg, start: int) -> np.ndarray:
+    """Which detection frames the reference writes a data/fusion.txt row for: FILTER::FilterThreadFunction records only after
+    ResetSystemState / BatchImuProcessing / ObservationUpdate ran (filter.cpp:229-248); the frame that initialises the pose and
+    every frame before it `continue` past the recording block (filter.cpp:207-226).  Decided from the inputs alone, with the
+    conditions of InitializePose (filter.cpp:295-358): a buffered IMU sample not later than the frame, the nearest marker
+    within marker_max_dist, its id in the marker map."""
+    known = {int(cfg.marker_id[i]) for i in range(cfg.n_markers)}
+    rec = np.zeros(len(t_frames), dtype=bool)
+    initialised = False
+    for w, g in enumerate(groups):
+        if len(g) == 0:
+            continue  # the filter thread is not woken (vision.cpp:136-140)
+        if initialised:
+            rec[w] = True
+            continue
+        n_before = int(np.searchsorted(t_imu, t_frames[w], side="right")) - start
+        dist = np.sqrt((g[:, 1:4] ** 2).sum(axis=1))
+        near, md = 0, 10.0
+        for c, d in enumerate(dist):  # first strict minimum below 10 (filter.cpp:331-341)
+            if d < md:
+                md, near = d, c
+        if n_before > 0 and not md > cfg.marker_max_dist and int(g[near, 0]) in known:
+            initialised = True
+    return rec
+
+
 IMU_BUFFER_MAX_SIZE = 2000  # filter.hpp:25
 IMU_BUFFER_DROP = 500        # filter.cpp:52
 
@@ -132,7 +158,8 @@ def replay_log(imu: np.ndarray, image_rows: np.ndarray, cfg=None, n_init: int = 
         w1 = min(W, w0 + chunk)
         traces.append(f.StepWindows(stream, det, off, w0, w1, trace=True))
     trace = np.concatenate(traces, axis=0)
-    return {"rows": trace[:, :, 0].copy(), "trace": trace, "state": f.GetState(), "filter": f, "win_off": off}
+    return {"rows": trace[:, :, 0].copy(), "trace": trace, "state": f.GetState(), "filter": f, "win_off": off,
+            "recorded": recorded_frames(t_imu, t_frames, groups, f.cfg, n_init)}
 
 
 def main(argv=None) -> int:
@@ -166,10 +193,11 @@ def main(argv=None) -> int:
             ap.error(f"{a.dataset}: no image.txt")
         image = logs["image"]
     res = replay_log(logs["imu"], image, None, n_init=a.n_init, use_iir=a.iir, device=a.device, buffer_cap=a.buffer_cap or None)
-    rows = res["rows"]
+    # one row per frame the reference records: not the frame that initialises the pose, nor the ones before it (filter.cpp:207-248)
+    rows = res["rows"][res["recorded"]]
     st = res["filter"].GetState(with_cov=False)
     logio.write_fusion_log(a.out, rows, newline="\r\n" if a.crlf else "\n")
-    print(f"{len(rows)} frames -> {a.out}; final t = {rows[-1, 0]:.6g} s, p = ({rows[-1, 1]:.6g}, {rows[-1, 2]:.6g}, {rows[-1, 3]:.6g}) m, "
+    print(f"{len(res['rows'])} frames, {len(rows)} recorded -> {a.out}; final t = {rows[-1, 0]:.6g} s, p = ({rows[-1, 1]:.6g}, {rows[-1, 2]:.6g}, {rows[-1, 3]:.6g}) m, "
           f"status bits seen: 0x{int(np.bitwise_or.reduce(st['status'])) if 'status' in st else 0:x}")
     return 0
 

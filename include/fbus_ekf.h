@@ -76,6 +76,21 @@ extern "C" {
 /* flags in fbus_config.flags */
 #define FBUS_FLAG_JOSEPH 0x1 /* opt-in Joseph-form covariance update (north_star); default is the
                                 reference's (I-KH)P form, filter.cpp:735 */
+#define FBUS_FLAG_MATLAB 0x2 /* MATLAB-semantics mode: the numerics of the matlab/ .m files where they differ from filter.cpp:
+                                  ImuUpdate.m       always the axis-angle quaternion increment; rotation matrices of the
+                                                    UN-normalised products (quaternion_to_rotmat.m form); R0 of the Runge-Kutta
+                                                    step = the carried State.rotateMat; Fx(7:9,7:9) = expm(-[w]x dt);
+                                  MeasureUpdate.m   position-only residual (quaternion rows zeroed, :88); nearest marker, no
+                                                    hysteresis, no range gate;
+                                  rotmat_to_quaternion.m  unit eigen-quaternions for Q_IL and the marker map;
+                                  FBUS_EKF.m        dt between consecutive IMU samples; a gap > reset_gap between two IMAGE
+                                                    times resets (ResetState.m: p, q, rotateMat from vision, v = b_a = 0, b_g kept)
+                                                    and SKIPS propagation and update for that frame (:168-171); the frame that
+                                                    initialises the pose also gets a measurement update (:116-151).
+                                fbus_config_matlab() also sets the script's P0 and measurement noise.  Runs on the
+                                lanes-per-filter window kernel at any batch size; not combinable with FBUS_FLAG_JOSEPH.
+                                Checked against oracle/fbus_oracle_matlab.py (a NumPy restatement of the .m files; "parity
+                                unpinned": no MATLAB here). */
 
 /*
  * Per-run constants.  Mirrors EkfParam / RefractInfo / CameraInfo.T_SC / MarkerPoseServer
@@ -123,6 +138,8 @@ typedef struct fbus_config {
 /* Fill *cfg with the values the bundled logs were recorded with: C++/config/camerainfo1.yml,
    paramconfig.yml, markersetup.yml, filter.hpp:29-34. */
 int fbus_config_default(fbus_config* cfg);
+/* The same with the constants of matlab/FBUS_EKF.m:28-41,83-112 (P0, measurement noise) and FBUS_FLAG_MATLAB set. */
+int fbus_config_matlab(fbus_config* cfg);
 
 /*
  * IMU stream (IMUData, common.hpp:176-193).  Timestamps are shared by the batch (one time base,

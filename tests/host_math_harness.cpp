@@ -130,3 +130,15 @@ extern "C" int hm_inair(const fbus_config* cfg, const float* c16, double* c3d, d
     marker_pose(c3d, k.rod_s, k.rod_c, pose, pose + 3);
     return ok;
 }
+
+// MATLAB-semantics mode pieces (FBUS_FLAG_MATLAB): the host build of the same inlines the kernels use
+extern "C" {
+void hm_rotmat_to_quat_eig(const double* R, double* q) { rotmat_to_quat_eig(R, q); }
+void hm_expm_rot_minus_I(const double* w, double dt, double* W) { expm_rot_minus_I(w, dt, W); }
+void hm_propagate_nominal_matlab(double* nom, const double* accel, const double* gyro, double dt) {
+    Nominal n;
+    nom_from(nom, n);
+    propagate_nominal_matlab(n, dt, accel, gyro);
+    nom_to(n, nom);
+}
+}

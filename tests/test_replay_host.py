@@ -54,3 +54,34 @@ def test_periodic_truth_is_periodic(cfg):
     a2 = synth.truth_trajectory(cfg, 1.0, periodic=True)
     assert np.array_equal(a["base_imu"], a2["base_imu"])
     assert np.abs(a["base_imu"][:, 0:3]).max() < 14 and np.abs(a["base_imu"][:, 3:6]).max() < 0.5
+
+
+def test_recorded_frames_match_the_reference(cfg, golden):
+    """replay.recorded_frames (host logic of the replay CLI: which frames get a data/fusion.txt row) against the reference's
+    own FilterThreadFunction body run frame by frame (oracle/_ref): a row is recorded iff the pose was initialised BEFORE the
+    frame (filter.cpp:207-248).  Includes frames whose initialisation fails (marker out of range / unknown id)."""
+    import orc
+    from fbus_ekf_b200 import capi, replay
+    if not orc.ref_available():
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    imu = golden["land_imu"][:4000]
+    img = golden["land_image"].copy()
+    img = img[img[:, 0] <= imu[-1, 0]][:40]
+    img[0, 1] = 99        # unknown id on the first frame: initialisation fails
+    img[1, 4] = 7.0       # marker farther than marker_max_dist on the second
+    t_imu = np.ascontiguousarray(imu[:, 0])
+    t_frames, groups = replay.group_frames(img)
+    rec = replay.recorded_frames(t_imu, t_frames, groups, cfg, 500)
+    assert not rec[:3].any() and rec[3:].all()
+    stream = capi.make_imu_stream(t_imu, np.ascontiguousarray(imu[:, 1:7, None]), 1)
+    ids, pose = replay.frames_to_soa(t_frames, groups, 1)
+    det = capi.make_det_frames(t_frames, ids, pose, 1, ids.shape[1])
+    off = replay.window_offsets(t_imu, t_frames, 500)
+    r = orc.Ref(cfg, 1)
+    r.init_gravity_gyrobias(stream, 0, 500)
+    got = []
+    for w in range(len(t_frames)):
+        got.append(bool(r.get_state(with_cov=False)["initialised"][0]))
+        r.step_windows(stream, det, off, w, w + 1)
+    assert np.array_equal(rec, np.array(got))
