@@ -42,6 +42,45 @@ def test_million_filters_properties(cfg):
         assert np.abs(sg[k][:, sel] - so[k]).max() <= 1e-9, k
 
 
+def test_strong_scaling_shard_with_covariance(cfg):
+    """131,072 filters = the shard of BASELINE configs[4] on 8 GPUs (1,024 CTAs of the tensor-memory kernel, 6.9 waves):
+    state AND covariance of filters sampled across the grid -- first / last lanes of CTAs, the partial last wave -- against the
+    oracle and, where oracle/_ref travelled, against the reference's own filter.cpp"""
+    import torch
+    import orc
+    from fbus_ekf_b200 import BatchFilter, capi, synth
+    from helpers import cov_close
+    B = 131072
+    traj = synth.truth_trajectory(cfg, 1.0)
+    N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
+    f = BatchFilter(cfg, batch=B)
+    imu_d = torch.empty((N, 6, B), dtype=torch.float64, device="cuda")
+    id_d = torch.empty((W, 1, B), dtype=torch.int32, device="cuda")
+    pose_d = torch.empty((W, 1, 7, B), dtype=torch.float64, device="cuda")
+    f.SynthStreams(synth.make_synth_spec(traj, seed=78), imu_d.data_ptr(), id_d.data_ptr(), pose_d.data_ptr())
+    imu = capi.make_imu_stream(traj["t_imu"], imu_d.data_ptr(), B, capi.FBUS_MEM_DEVICE)
+    det = capi.make_det_frames(traj["t_frames"], id_d.data_ptr(), pose_d.data_ptr(), B, 1, capi.FBUS_MEM_DEVICE)
+    f.StepWindows(imu, det, traj["win_off"], 0, W)
+    sg = f.GetState(with_cov=True)
+    rng = np.random.default_rng(5)
+    sel = np.unique(np.concatenate([[0, 31, 32, 127, 128, B - 129, B - 128, B - 1], 128 * rng.integers(0, B // 128, 40) + rng.integers(0, 128, 40),
+                                    np.arange(148 * 128 * 6, 148 * 128 * 6 + 128 * 8, 61)]))
+    n = len(sel)
+    idx = torch.from_numpy(sel).cuda()
+    s = capi.make_imu_stream(traj["t_imu"], np.ascontiguousarray(imu_d[:, :, idx].cpu().numpy()), n)
+    d = capi.make_det_frames(traj["t_frames"], np.ascontiguousarray(id_d[:, :, idx].cpu().numpy()),
+                             np.ascontiguousarray(pose_d[:, :, :, idx].cpu().numpy()), n, 1)
+    checkers = [orc.Oracle] + ([orc.Ref] if orc.ref_available() else [])
+    for cls in checkers:
+        o = cls(cfg, n)
+        o.step_windows(s, d, traj["win_off"], 0, W, None, 8)
+        so = o.get_state(with_cov=True)
+        for k in ("t", "q", "R", "p", "v", "ba", "bg", "g"):
+            assert np.abs(sg[k][..., sel] - so[k]).max() <= 1e-9, (cls.__name__, k)
+        ok, worst = cov_close(sg["P"][:, sel], so["P"], 1e-9)
+        assert ok, (cls.__name__, worst)
+
+
 def test_half_million_refractive_solves(cfg):
     """configs[3]: 65,536 filters x 8 markers per frame"""
     import orc

@@ -9,13 +9,13 @@ from helpers import cov_close
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_replay(cfg, imu, image_rows, n_init=500, use_iir=False):
+def _oracle_replay(cfg, imu, image_rows, n_init=500, use_iir=False, cls=None):
     import orc
     from fbus_ekf_b200 import capi, replay
     if use_iir:
         import fbus_oracle_np
         imu = fbus_oracle_np.iir_prefilter(imu, restart_at=(n_init,))
-    o = orc.Oracle(cfg, 1)
+    o = (cls or orc.Oracle)(cfg, 1)
     t_imu = np.ascontiguousarray(imu[:, 0])
     data = np.ascontiguousarray(imu[:, 1:7, None])
     stream = capi.make_imu_stream(t_imu, data, 1)
@@ -47,6 +47,27 @@ def test_log_replay(cfg, golden, name, use_iir):
     assert ok, f"final covariance off by {w}"
     assert int(st["status"][0]) == int(ref_state["status"][0])
     assert int(st["status"][0]) & 0x4                                      # both logs contain vision gaps -> resets
+
+
+@pytest.mark.parametrize("name", ["land", "water"])
+def test_log_replay_against_the_reference_itself(cfg, golden, name):
+    """the same replay against oracle/_ref -- the reference's own filter.cpp, compiled unmodified and executed (prebuilt
+    library travelling with the snapshot) -- at north_star's tolerances, without the oracle in between"""
+    import orc
+    from fbus_ekf_b200 import replay
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref did not travel")
+    imu, img = golden[f"{name}_imu"], golden[f"{name}_image"]
+    ref_rows, ref_state = _oracle_replay(cfg, imu, img, cls=orc.Ref)
+    out = replay.replay_log(imu, img, cfg, chunk=400)
+    rows, st = out["rows"], out["state"]
+    assert np.array_equal(rows[:, 0], ref_rows[:, 0])
+    assert np.abs(rows[:, 1:4] - ref_rows[:, 1:4]).max() <= 1e-6
+    assert np.abs(rows[:, 4:17] - ref_rows[:, 4:17]).max() <= 1e-9
+    ok, w = cov_close(st["P"], ref_state["P"], 1e-9)
+    assert ok, f"final covariance off by {w}"
+    for k in ("t", "q", "R", "p", "v", "ba", "bg", "g", "pv", "qv"):
+        assert np.abs(st[k] - ref_state[k]).max() <= 1e-9, k
 
 
 def test_water_refraction_feeds_update(cfg, golden):
