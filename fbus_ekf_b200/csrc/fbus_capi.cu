@@ -74,6 +74,8 @@ struct fbus_handle {
     size_t pipeline_min_bytes = (size_t)64 << 20;  // host streams smaller than this are staged and processed in one go
     bool small_batch = false;
     bool lane_batch = false;  // batches that leave SMs idle even with 32-filter CTAs: nine lanes per filter (fbus_kernel_lane.cuh)
+    int lane_gen = 2;         // generation of the lanes-per-filter kernel (FBUS_LANE_GEN=1: the first one, kept for the MATLAB-semantics mode)
+    uint32_t lane_fpc = 32;   // second generation: filters per CTA (the batch is spread over all SMs)
     double* d_nom = nullptr;
     double* d_P = nullptr;
     int32_t* d_prev = nullptr;
@@ -169,6 +171,14 @@ int launch_window(fbus_handle* h, WinParams& prm) {
         const unsigned g32 = (unsigned)((h->B + 31) / 32);
         if (f32) ekf_window_lane_kernel<false, true, true><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
         else ekf_window_lane_kernel<false, false, true><<<g32, LANE_NT, LANE_SMEM, h->stream>>>(prm, h->k);
+    } else if (h->lane_batch && h->lane_gen == 2) {
+        prm.lane_fpc = h->lane_fpc;
+        const unsigned g32 = (unsigned)((h->B + h->lane_fpc - 1) / h->lane_fpc);
+        if (f32) {
+            if (jo) ekf_window_lane2_kernel<true, true><<<g32, LANE_NT, LANE2_SMEM, h->stream>>>(prm, h->k);
+            else ekf_window_lane2_kernel<false, true><<<g32, LANE_NT, LANE2_SMEM, h->stream>>>(prm, h->k);
+        } else if (jo) ekf_window_lane2_kernel<true, false><<<g32, LANE_NT, LANE2_SMEM, h->stream>>>(prm, h->k);
+        else ekf_window_lane2_kernel<false, false><<<g32, LANE_NT, LANE2_SMEM, h->stream>>>(prm, h->k);
     } else if (h->lane_batch) {
         const unsigned g32 = (unsigned)((h->B + 31) / 32);
         if (f32) {
@@ -224,6 +234,20 @@ int stage_det(fbus_handle* h, const fbus_det_frames* det, size_t w0, size_t w1, 
 extern "C" {
 
 int fbus_abi_version(void) { return FBUS_ABI_VERSION; }
+
+#ifdef FBUS_L2_TRACE
+// experiment builds only (profiles/probes/lane2_trace.py): (tag, clock) pairs of one role, resets the counters
+int fbus_debug_l2_trace(long long* out, int role, int max_pairs) {
+    int n[2];
+    if (cudaMemcpyFromSymbol(n, g_l2_trace_n, sizeof(n)) != cudaSuccess) return -1;
+    int cnt = n[role] < max_pairs ? n[role] : max_pairs;
+    if (cnt > 8192) cnt = 8192;
+    if (cudaMemcpyFromSymbol(out, g_l2_trace, sizeof(long long) * 2 * cnt, sizeof(long long) * 16384 * role) != cudaSuccess) return -1;
+    int z[2] = {0, 0};
+    if (role == 1) cudaMemcpyToSymbol(g_l2_trace_n, z, sizeof(z));
+    return cnt;
+}
+#endif
 
 int fbus_config_default(fbus_config* cfg) {
     if (!cfg) return FBUS_E_BADARG;
@@ -308,8 +332,19 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         if (const char* sb = getenv("FBUS_SMALL_BATCH")) h->small_batch = atoi(sb) != 0;
         // one 32-filter lanes-per-filter CTA per SM at most: below that the batch is latency-bound and nine lanes per filter
         // cut the latency of a filter-step ~3x; an explicit FBUS_SMALL_BATCH choice keeps the thread-per-filter kernels
-        h->lane_batch = !getenv("FBUS_SMALL_BATCH") && (batch + 31) / 32 <= (size_t)prop.multiProcessorCount;
+        // Measured (profiles/probes/lane_gen_sweep.py): with a full 32-filter CTA the lanes-per-filter kernels are no faster per
+        // frame than the 32-filter thread-per-filter CTAs (the CTA's one nominal warp, its schedulers and its shared-memory
+        // bandwidth are shared by 32 filters); with at most 16 filters per CTA the second generation is 13-24 % faster.  So the
+        // lane kernel takes the batches that can be spread at <= 16 filters per SM, as thin as the SM count allows.
+        const size_t nsm = (size_t)prop.multiProcessorCount;
+        h->lane_fpc = (uint32_t)((batch + nsm - 1) / nsm);
+        h->lane_batch = !getenv("FBUS_SMALL_BATCH") && h->lane_fpc <= 16;
         if (const char* lb = getenv("FBUS_LANE")) h->lane_batch = atoi(lb) != 0;
+        if (h->lane_fpc > 32) h->lane_fpc = 32;
+        if (const char* fp = getenv("FBUS_LANE_FPC")) {
+            const int v = atoi(fp);
+            if (v >= 1 && v <= 32) h->lane_fpc = (uint32_t)v;
+        }
         e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
@@ -317,6 +352,12 @@ int fbus_create(fbus_handle** out, const fbus_config* cfg, int device, size_t ba
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM);
         if (e != cudaSuccess) return bail("cudaFuncSetAttribute(lane)", e);
+        if (const char* lg = getenv("FBUS_LANE_GEN")) h->lane_gen = atoi(lg);
+        e = cudaFuncSetAttribute(ekf_window_lane2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE2_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE2_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE2_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_lane2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE2_SMEM);
+        if (e != cudaSuccess) return bail("cudaFuncSetAttribute(lane2)", e);
         const int smem32 = (int)((NPK + XCH) * 32 * sizeof(double));
         e = cudaFuncSetAttribute(ekf_window_split_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_window_split_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);

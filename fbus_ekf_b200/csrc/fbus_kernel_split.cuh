@@ -30,6 +30,25 @@
 
 namespace fbus {
 
+// -DFBUS_L2_TRACE: phase time stamps of CTA 0 of the second-generation lane kernel (nominal lane 0 = role 0, covariance warp 0 =
+// role 1) for profiles/probes/lane2_trace.py; compiled out of the library
+#ifdef FBUS_L2_TRACE
+__device__ long long g_l2_trace[2][16384];
+__device__ int g_l2_trace_n[2];
+#define L2T(cond, role, tag)                                                    \
+    do {                                                                        \
+        if (blockIdx.x == 0 && (cond)) {                                        \
+            const int i_ = g_l2_trace_n[role]++;                                \
+            if (i_ < 8192) {                                                    \
+                g_l2_trace[role][2 * i_] = (tag);                               \
+                g_l2_trace[role][2 * i_ + 1] = clock64();                       \
+            }                                                                   \
+        }                                                                       \
+    } while (0)
+#else
+#define L2T(cond, role, tag) ((void)0)
+#endif
+
 constexpr int XCH = 54;  // doubles of exchange area per filter: ring 2 x 22 (+ request, results); the update parks 54 doubles of Z here
 
 // CTA-wide named barrier used by both roles (the two roles run different code, so the barrier is issued from
@@ -489,6 +508,28 @@ __device__ __forceinline__ void plan_frame_matlab(const WinParams& prm, const De
 // (a ring slot has 28 doubles here: A 9, B 9, W = F[theta,theta] - I 9, dt -- the MATLAB-semantics mode needs the full W)
 constexpr int LX_REC = 28, LX_P6 = 56, LX_CM = 92, LX_Y = 113, LX_DX = 120, LX_SCR = 138, LX_TOTAL = 180;
 constexpr int LANE_NT = 384;  // 11 covariance warps (3 filters each, 9 lanes per filter) + the nominal warp
+// Second generation of the lanes-per-filter kernel (ekf_window_lane2_kernel): the ring holds a whole CHUNK of L2_CH samples, the
+// sample-only half of F2 (nominal_increment) is evaluated for all samples of the chunk in parallel by the covariance warps (warp =
+// sample slot, lane = filter) before the nominal lane walks its now short chain, and each ring record is handed over through its own
+// mbarrier instead of a CTA-wide barrier per sample.  Exchange area: ring L2_CH x 28 | the sections of the first generation, shifted |
+// increments [L2_CH][L2_NE] | ba, bg of the frame.
+constexpr int L2_CH = 8;
+constexpr int L2_SHIFT = (L2_CH - 2) * LX_REC;
+constexpr int L2_NE = 16;  // dt, t, dqh (4), dq (4), a = accel - b_a (3), u = (gyro - b_g) dt (3)
+constexpr int L2_INC = LX_TOTAL + L2_SHIFT;
+constexpr int L2_BIAS = L2_INC + L2_CH * L2_NE;
+constexpr int L2_TOTAL = L2_BIAS + 6;
+struct Lane2Shared {
+    int32_t sval[2][L2_CH][32];      // sample (slot) is processed by filter (lane); double-buffered by chunk parity: the nominal
+                                     // lane posts chunk c+1 while the covariance lanes may still be working through chunk c
+};
+// hand-over of ring slot s: named barrier 2 + s, 32 producer threads (the nominal lanes) arrive without waiting, the 352 covariance
+// threads wait.  A hardware barrier, not a polled flag: the waiting warps sleep and leave the issue slots to the nominal warp
+// (a first version polled an mbarrier, and the eleven spinning warps slowed the nominal chain ~4x).
+// (bar.arrive / bar.sync order the producer's earlier shared-memory writes before the consumers' later reads, as every barrier does;
+// the arrive is executed by the whole, converged warp: the aligned form counts warps, not threads)
+__device__ __forceinline__ void slot_arrive(int slot) { asm volatile("bar.arrive %0, %1;" ::"r"(slot + 2), "n"(LANE_NT) : "memory"); }
+__device__ __forceinline__ void slot_wait(int slot) { asm volatile("bar.sync %0, %1;" ::"r"(slot + 2), "n"(LANE_NT) : "memory"); }
 
 // the p/theta sub-matrix P6 = P[{0,1,2,6,7,8}, {0,1,2,6,7,8}] as the covariance lanes publish it: the only part of P the
 // update prologue reads (accessor interface of update_prologue)
@@ -519,13 +560,15 @@ struct P6View {
 // records need no neutral content, and the update is split differently -- this warp (one lane per filter) runs the
 // state-only prologue (predicted measurement, Hs, S, the gain factors) from the published P6 and the error-state
 // injection, the covariance lanes run the sweep P -= Z^T Z and dx = Z^T y.
-template <int BSF, bool TM, bool IMU32 = false, bool LANE = false, bool JOSEPH = false, bool MATLAB = false>
+template <int BSF, bool TM, bool IMU32 = false, bool LANE = false, bool JOSEPH = false, bool MATLAB = false, bool LANE2 = false>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
-                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live) {
+                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live, Lane2Shared* l2 = nullptr) {
     constexpr int NT = LANE ? LANE_NT : 2 * BSF, NW = BSF / 32;
     static_assert(!LANE || BSF == 32, "the lanes-per-filter kernel has 32 filters per CTA");
     static_assert(!MATLAB || (LANE && !JOSEPH), "the MATLAB-semantics mode runs on the lanes-per-filter kernel, reference update form");
+    static_assert(!LANE2 || (LANE && !MATLAB), "the second-generation lanes-per-filter kernel has the C++ semantics only");
     constexpr int REC = LANE ? LX_REC : 22;  // doubles per ring slot
+    constexpr int LXS = LANE2 ? L2_SHIFT : 0;  // shift of the exchange sections behind the ring
     const size_t B = prm.B;
     double* const X = smem + (size_t)((TM || LANE) ? 0 : NPK) * BSF + fl;
     auto sbar = [&](int pair) {
@@ -560,11 +603,20 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     auto plan = [&](uint32_t wf, FramePlan& out) {
         if constexpr (MATLAB) plan_frame_matlab<BSF>(prm, k, wf, b, live, cursor, t_img, inited, prev_id, status, out);
         else plan_frame<BSF>(prm, k, wf, b, live, cursor, n.t, inited, prev_id, status, out);
+        if constexpr (LANE2) {
+            // lanes past the batch mirror the last filter for their reads; in this kernel they neither propagate nor update, so
+            // that a small batch (the live single-filter case) leaves the covariance warps of the unused slots asleep
+            if (!live) {
+                out.do_prop = out.apply_init = out.apply_reset = false;
+                out.req = 0;
+            }
+        }
     };
     FramePlan pl;
     if (prm.w0 < prm.w1) plan(prm.w0, pl);
 
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
+        L2T(LANE2 && fl == 0, 0, 1);
         // ---- apply the planned F6b InitializePose / F5 ResetSystemState --------------------------------------
         if (pl.apply_init) {
             n.t = MATLAB ? pl.t_init : pl.t_det;
@@ -613,10 +665,119 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             if ((fl & 31) == 0) { sh.lo_hi[fp][0][wq] = vlo; sh.lo_hi[fp][1][wq] = vhi; }
         }
         cta_bar<NT>();  // (a)
+        L2T(LANE2 && fl == 0, 0, 2);
         uint32_t lo = sh.lo_hi[fp][0][0], hi = sh.lo_hi[fp][1][0];
 #pragma unroll
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[fp][0][q]); hi = max(hi, sh.lo_hi[fp][1][q]); }
         int fs = 0;
+        if constexpr (LANE2) {
+            if (lo < hi) {
+                const double start = n.t;
+                bool open = do_prop;          // false once this filter hit a sample later than t_end (the reference's break)
+                uint32_t consumed = p_first;  // samples erased afterwards (filter.cpp:492-503,520)
+                double tprev = n.t;           // sysNominalState_.timeStamp as the sample loop sees it
+                uint32_t cpar = 0;            // chunk parity (restarts with every frame, as in the covariance role)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {  // the biases are constant over the window: posted once for the increment pass
+                    X[(size_t)(L2_BIAS + c) * BSF] = n.ba[c];
+                    X[(size_t)(L2_BIAS + 3 + c) * BSF] = n.bg[c];
+                }
+                // R(q) of the current quaternion = rotmatI2GBeginTime of the next sample (filter.cpp:543).  It is the carried
+                // rotmatI2G except right after an update or a reset, which change q and leave rotmatI2G alone (A.3-2).
+                double Rq[9];
+                q2R(n.q, Rq);
+                // The velocity / position half of F2 runs ONE SAMPLE BEHIND the quaternion half: it is not part of the chain
+                // through q, and in the same instruction stream it fills the latency gaps of that chain.  Pending operands
+                // (dt = 0, a = 0: a no-op until the first processed sample).
+                double pq[4] = {n.q[0], n.q[1], n.q[2], n.q[3]}, pdqh[4] = {1.0, 0.0, 0.0, 0.0}, pa[3] = {0.0, 0.0, 0.0}, pR0[9], pdt = 0.0;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) pR0[c] = Rq[c];
+                // the time stamps are shared by all filters: lane j loads the chunk's j-th, the loop below reads them by shuffle;
+                // the next chunk's are in flight while this chunk is processed
+                const int tl = fl & 31;
+                double ts = (tl < L2_CH && lo + tl < hi) ? prm.imu_t[lo + tl] : 0.0;
+                for (uint32_t c0 = lo; c0 < hi; c0 += L2_CH) {
+                    const uint32_t c1 = min(c0 + (uint32_t)L2_CH, hi);
+                    const double ts_next = (tl < L2_CH && c1 + tl < hi) ? prm.imu_t[c1 + tl] : 0.0;
+                    // which samples of the chunk this filter processes, and their dt (the only part of the window logic that is a
+                    // chain through the time stamps, filter.cpp:492-516).  Unrolled and branch-free: the shuffles and comparisons of
+                    // all slots are independent, only open / tprev / consumed chain from slot to slot.
+#pragma unroll
+                    for (int j = 0; j < L2_CH; ++j) {
+                        const uint32_t i = c0 + (uint32_t)j;
+                        const double ti = __shfl_sync(0xffffffffu, ts, j);
+                        const bool in = open && i < c1 && i >= p_first && i < p_end;
+                        const bool early = ti < start, late = ti > t_end;
+                        const bool valid = in && !early && !late;
+                        if (in && !early && late) open = false;  // this sample stays buffered (the reference's break)
+                        if (in && (early || !late)) consumed = i + 1;
+                        const double dt = valid ? ti - tprev : 0.0;
+                        if (valid) tprev = ti;
+                        double* ic = X + (size_t)(L2_INC + j * L2_NE) * BSF;
+                        ic[0] = dt;
+                        ic[(size_t)BSF] = ti;
+                        l2->sval[cpar][j][fl] = valid ? 1 : 0;
+                    }
+                    L2T(fl == 0, 0, 3);
+                    cta_bar<NT>();  // (I) validity, dt and the biases are posted: the covariance warps evaluate the increments
+                    cta_bar<NT>();  // (J) increments posted
+                    L2T(fl == 0, 0, 4);
+                    for (uint32_t i = c0; i < c1; ++i) {
+                        const int slot = (int)(i - c0);
+                        const bool valid = l2->sval[cpar][slot][fl] != 0;
+                        const double* ic = X + (size_t)(L2_INC + slot * L2_NE) * BSF;
+                        double dt = 0.0, dqh[4], dq[4], av[3];
+                        if (valid) {
+                            dt = ic[0];
+                            double u[3];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) { dqh[c] = ic[(size_t)(2 + c) * BSF]; dq[c] = ic[(size_t)(6 + c) * BSF]; }
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) { av[c] = ic[(size_t)(10 + c) * BSF]; u[c] = ic[(size_t)(13 + c) * BSF]; }
+                            // coefficients of F from the CARRIED rotmatI2G (A.3-2,3), as cov_coeffs forms them
+                            const double ndt = -dt;
+                            const double s0 = av[0] * ndt, s1 = av[1] * ndt, s2 = av[2] * ndt;
+                            double* rec = X + (size_t)slot * REC * BSF;
+#pragma unroll
+                            for (int r = 0; r < 3; ++r) {
+                                rec[(size_t)(r * 3 + 0) * BSF] = n.R[r * 3 + 1] * s2 - n.R[r * 3 + 2] * s1;
+                                rec[(size_t)(r * 3 + 1) * BSF] = n.R[r * 3 + 2] * s0 - n.R[r * 3 + 0] * s2;
+                                rec[(size_t)(r * 3 + 2) * BSF] = n.R[r * 3 + 0] * s1 - n.R[r * 3 + 1] * s0;
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) rec[(size_t)(9 + r * 3 + c) * BSF] = n.R[r * 3 + c] * ndt;
+                            }
+                            rec[(size_t)18 * BSF] = u[0]; rec[(size_t)19 * BSF] = u[1]; rec[(size_t)20 * BSF] = u[2];  // -[w]x dt by its three numbers
+                            rec[(size_t)21 * BSF] = dt;
+                        }
+                        __syncwarp();
+                        slot_arrive(slot);  // record (slot) is complete
+                        if (valid) {
+                            // F2 after F1's coefficients were taken (filter.cpp:509-513): q of this sample side by side with v, p of
+                            // the previous one
+                            double q0[4], R0[9];  // quaternion and R(q) before this sample's step: operands of its own v, p half
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) q0[c] = n.q[c];
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) R0[c] = Rq[c];
+                            nominal_apply_dual(n, Rq, pdt, pq, pdqh, pa, pR0, dq);
+                            pdt = dt;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) { pq[c] = q0[c]; pdqh[c] = dqh[c]; }
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) pa[c] = av[c];
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) pR0[c] = R0[c];
+                            n.t = ic[(size_t)BSF];
+                            L2T(fl == 0, 0, 10 + slot);
+                        }
+                    }
+                    cpar ^= 1u;
+                    ts = ts_next;
+                }
+                nominal_apply_vp(n, pdt, pq, pdqh, pa, pR0, Rq);  // the last sample's v, p
+                if (fused && do_prop) cursor = consumed;
+            }
+        } else
         if (lo < hi) {
             fs = (int)((hi - lo) & 1u);
             const double start = MATLAB ? t_img_frame : n.t;
@@ -704,32 +865,36 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             const int wany = __any_sync(0xffffffffu, req != 0);
             if ((fl & 31) == 0) sh.any_upd[wq] = wany;
         }
+        L2T(LANE2 && fl == 0, 0, 5);
         sbar(wq);  // (r)
+        L2T(LANE2 && fl == 0, 0, 6);
         const int any = pair_any(sh, wq);
         if constexpr (LANE) {
             if (any) {
                 sbar(wq);  // (p) the covariance lanes have published P6
+                L2T(LANE2 && fl == 0, 0, 7);
                 if (req) {
                     const MarkerConst mkc = prm.tab->mk[req - 1];
                     if constexpr (JOSEPH) {  // 6-row factor Lc of the Joseph-form C_J and y = Lc^-1 u
                         double Cm[21], yv[6];
-                        update_prologue<BSF, BSF, true, P6View>(P6View{X + (size_t)LX_P6 * BSF}, n, k, mkc, pl.y, pl.y + 3, Cm, yv,
-                                                                X + (size_t)LX_SCR * BSF);
+                        update_prologue<BSF, BSF, true, P6View>(P6View{X + (size_t)(LXS + LX_P6) * BSF}, n, k, mkc, pl.y, pl.y + 3, Cm, yv,
+                                                                X + (size_t)(LXS + LX_SCR) * BSF);
 #pragma unroll
-                        for (int c = 0; c < 21; ++c) X[(size_t)(LX_CM + c) * BSF] = Cm[c];
+                        for (int c = 0; c < 21; ++c) X[(size_t)(LXS + LX_CM + c) * BSF] = Cm[c];
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) X[(size_t)(LX_Y + c) * BSF] = yv[c];
+                        for (int c = 0; c < 6; ++c) X[(size_t)(LXS + LX_Y + c) * BSF] = yv[c];
                     } else {  // 7-row factor X = L^-1 Hs (left in the scratch entries) and z = L^-1 r: no second factorisation
                         // (computing Hs and r before the barrier, while the lanes finish, measured slower: the 37 doubles held
                         // across the wait spill at this kernel's 168 registers)
                         double L[28], Li[7], zv[7];
                         UpdHs hh;
                         update_hs<MATLAB>(n, k, mkc, pl.y, pl.y + 3, hh);
-                        update_prologue_sx<BSF, BSF, P6View>(P6View{X + (size_t)LX_P6 * BSF}, k, hh, L, Li, zv, X + (size_t)LX_SCR * BSF);
+                        update_prologue_sx<BSF, BSF, P6View>(P6View{X + (size_t)(LXS + LX_P6) * BSF}, k, hh, L, Li, zv, X + (size_t)(LXS + LX_SCR) * BSF);
 #pragma unroll
-                        for (int c = 0; c < 7; ++c) X[(size_t)(LX_Y + c) * BSF] = zv[c];
+                        for (int c = 0; c < 7; ++c) X[(size_t)(LXS + LX_Y + c) * BSF] = zv[c];
                     }
                 }
+                L2T(LANE2 && fl == 0, 0, 8);
                 sbar(wq);  // (c) gain factors posted
             }
         }
@@ -738,7 +903,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
         nx.do_prop = nx.apply_init = nx.apply_reset = false;
         nx.req = 0;
         if (w + 1 < prm.w1) {
-            if (fused && cursor < prm.win_off[prm.w1]) {
+            if (!LANE2 && fused && cursor < prm.win_off[prm.w1]) {  // (the second-generation lane kernel loads the samples in its covariance warps)
                 pf_i = cursor;
                 pf_st = prm.imu_t[cursor];
 #pragma unroll
@@ -746,13 +911,15 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             }
             plan(w + 1, nx);
         }
+        L2T(LANE2 && fl == 0, 0, 9);
         if (any) {
             sbar(wq);  // (d) results posted
+            L2T(LANE2 && fl == 0, 0, 20);
             if (req) {
                 if constexpr (LANE) {
                     double dx[18];
 #pragma unroll
-                    for (int c = 0; c < 18; ++c) dx[c] = X[(size_t)(LX_DX + c) * BSF];
+                    for (int c = 0; c < 18; ++c) dx[c] = X[(size_t)(LXS + LX_DX + c) * BSF];
                     inject_error_state(n, dx);  // rotmatI2G deliberately NOT refreshed (A.3-2)
                 } else {
 #pragma unroll
@@ -784,6 +951,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             }
         }
         pl = nx;
+        L2T(LANE2 && fl == 0, 0, 21);
     }
     if (!live) return;
     bool fin = isfinite(n.t);

@@ -50,6 +50,7 @@ struct WinParams {
     int32_t cursor_resume;    // fused mode: start from cursor_io (continuation of the same stream) instead of win_off[w0]
     uint32_t stagger_cycles;  // split kernel, 2 CTAs per SM: start delay of odd-ticket CTAs
     uint32_t* sm_ticket;      // split kernel: per-SM arrival counters [256] (device), or nullptr
+    uint32_t lane_fpc;        // second-generation lane kernel: filters per CTA (1..32); the other slots of a CTA stay idle
 };
 
 // One IMU component (c = 0..2 accel, 3..5 gyro).  Float32 sensor samples are converted exactly as the reference's IMU callback

@@ -668,51 +668,43 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
 // ------------------------------------------------------------------------------------------------
 // F2: nominal state propagation (FILTER::UpdateNominalState, filter.cpp:533-582)
 // ------------------------------------------------------------------------------------------------
-FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const double* gyro) {
-    double w[3];
-    FBUS_UNROLL
-    for (int i = 0; i < 3; ++i) w[i] = gyro[i] - n.bg[i];
+// The step in two halves.  nominal_increment: everything that depends on the sample, the biases and dt only (bias-corrected rate,
+// the half- and full-interval increment quaternions): independent from sample to sample, so the lanes-per-filter kernel evaluates
+// it for all samples of a window in parallel lanes.  nominal_apply: the part that is a chain through q, v, p.
+FBUS_HD void nominal_increment(const double* w, double dt, double* dqh, double* dq) {
     const double wn2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
     const double inv = rsqrt_d(wn2);  // 1/|w| (inf for w = 0: only used in the branch below)
     const double wn = wn2 * inv;      // |w|
-    double R0[9], qh[4], qn[4];
-    q2R(n.q, R0);
-    {
-        // Both forms of the increment are evaluated and the one the reference's branch takes (filter.cpp:544-561) is selected:
-        // straight-line code instead of a divergent region, so that the scheduler can overlap the sincos chain with the rest
-        // of the step.  The values selected are exactly those the branch would have produced (a zero rate gives inf / NaN in
-        // the unused axis-angle form, which the select discards).
-        const bool big = wn > 10e-5;
-        const double ax[3] = {w[0] * inv, w[1] * inv, w[2] * inv};
-        // one sincos: the half-interval quaternion needs angle/2 = wn*dt/4, the full one twice that
-        // (double-angle identities; ~1 ulp from evaluating sin/cos of wn*dt/2 directly)
-        double sh, ch;
-        sincos_d(big ? wn * dt * 0.25 : 0.0, &sh, &ch);
-        const double sf = 2.0 * sh * ch, cf = 1.0 - 2.0 * sh * sh;
-        double dqh[4], dq[4];
-        dqh[0] = big ? ch : 1.0;
-        dq[0] = big ? cf : 1.0;
-        FBUS_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            dqh[1 + i] = big ? sh * ax[i] : 0.25 * dt * w[i];
-            dq[1 + i] = big ? sf * ax[i] : 0.5 * dt * w[i];
-        }
-        qmul(n.q, dqh, qh);
-        qmul(n.q, dq, qn);
+    // Both forms of the increment are evaluated and the one the reference's branch takes (filter.cpp:544-561) is selected:
+    // straight-line code instead of a divergent region, so that the scheduler can overlap the sincos chain with the rest
+    // of the step.  The values selected are exactly those the branch would have produced (a zero rate gives inf / NaN in
+    // the unused axis-angle form, which the select discards).
+    const bool big = wn > 10e-5;
+    const double ax[3] = {w[0] * inv, w[1] * inv, w[2] * inv};
+    // one sincos: the half-interval quaternion needs angle/2 = wn*dt/4, the full one twice that
+    // (double-angle identities; ~1 ulp from evaluating sin/cos of wn*dt/2 directly)
+    double sh, ch;
+    sincos_d(big ? wn * dt * 0.25 : 0.0, &sh, &ch);
+    const double sf = 2.0 * sh * ch, cf = 1.0 - 2.0 * sh * sh;
+    dqh[0] = big ? ch : 1.0;
+    dq[0] = big ? cf : 1.0;
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        dqh[1 + i] = big ? sh * ax[i] : 0.25 * dt * w[i];
+        dq[1 + i] = big ? sf * ax[i] : 0.5 * dt * w[i];
     }
+}
+// the velocity / position half of nominal_apply: q0, R0 = quaternion and rotation matrix before the step, Rn = after it.  Not part of
+// the chain through q, so the lanes-per-filter kernel runs it one sample behind (dt = 0 and a = 0 leave v and p as they are).
+FBUS_HD void nominal_apply_vp(Nominal& n, double dt, const double* q0, const double* dqh, const double* a, const double* R0, const double* Rn) {
+    double qh[4], Rh[9];
+    qmul(q0, dqh, qh);
     qnormalize(qh);
-    qnormalize(qn);
-    FBUS_UNROLL
-    for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
-    double Rh[9];
     q2R(qh, Rh);
-    q2R(n.q, n.R);
-    double a[3], k1[3], k2[3], k4[3];
-    FBUS_UNROLL
-    for (int i = 0; i < 3; ++i) a[i] = accel[i] - n.ba[i];
+    double k1[3], k2[3], k4[3];
     mat3_vec(R0, a, k1);
     mat3_vec(Rh, a, k2);
-    mat3_vec(n.R, a, k4);
+    mat3_vec(Rn, a, k4);
     const double dt6 = dt * (1.0 / 6.0), dt2 = dt * 0.5;
     FBUS_UNROLL
     for (int i = 0; i < 3; ++i) {
@@ -722,6 +714,117 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
         const double kp2 = v0 + kv1 * dt2, kp3 = v0 + kv2 * dt2;
         n.p[i] = n.p[i] + dt6 * (v0 + 2 * kp2 + 2 * kp3 + kp3);
     }
+}
+// the quaternion half: q <- normalised q * dq, rotmatI2G <- R(q)
+FBUS_HD void nominal_apply_q(Nominal& n, const double* dq) {
+    double qn[4];
+    qmul(n.q, dq, qn);
+    qnormalize(qn);
+    FBUS_UNROLL
+    for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
+    q2R(n.q, n.R);
+}
+// ---- the same arithmetic written for a LONE warp ------------------------------------------------------------------------------
+// A warp that has its scheduler to itself (the nominal lane of the lanes-per-filter kernel) pays the full 8-clock latency of every
+// dependent FP64 instruction, and ptxas keeps independent chains that are far apart in the source far apart in the code: F2 written
+// as above ran at ~8 clk per instruction.  These versions evaluate TWO independent chains statement by statement next to each other
+// (value for value the expressions of qmul / qnormalize / q2R, so the results are bit-identical).
+FBUS_HD void qmul2(const double* a, const double* b, double* o, const double* c, const double* d, double* p) {
+    const double w1 = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    const double w2 = c[0] * d[0] - c[1] * d[1] - c[2] * d[2] - c[3] * d[3];
+    const double x1 = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    const double x2 = c[0] * d[1] + c[1] * d[0] + c[2] * d[3] - c[3] * d[2];
+    const double y1 = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+    const double y2 = c[0] * d[2] + c[2] * d[0] + c[3] * d[1] - c[1] * d[3];
+    const double z1 = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+    const double z2 = c[0] * d[3] + c[3] * d[0] + c[1] * d[2] - c[2] * d[1];
+    o[0] = w1; o[1] = x1; o[2] = y1; o[3] = z1;
+    p[0] = w2; p[1] = x2; p[2] = y2; p[3] = z2;
+}
+FBUS_HD void qnormalize2(double* q, double* r) {
+    const double s1 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const double s2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+#ifdef __CUDA_ARCH__
+    double y1, y2;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y1) : "d"(s1));
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y2) : "d"(s2));
+    const double h1 = 0.5 * s1, h2 = 0.5 * s2;
+    double e1 = fma(-h1 * y1, y1, 0.5), e2 = fma(-h2 * y2, y2, 0.5);
+    y1 = fma(y1, e1, y1);
+    y2 = fma(y2, e2, y2);
+    e1 = fma(-h1 * y1, y1, 0.5);
+    e2 = fma(-h2 * y2, y2, 0.5);
+    y1 = fma(y1, e1, y1);
+    y2 = fma(y2, e2, y2);
+#else
+    const double y1 = 1.0 / sqrt(s1), y2 = 1.0 / sqrt(s2);
+#endif
+    q[0] *= y1; r[0] *= y2; q[1] *= y1; r[1] *= y2; q[2] *= y1; r[2] *= y2; q[3] *= y1; r[3] *= y2;
+}
+FBUS_HD void q2R2(const double* q, double* R, const double* p, double* S) {
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double a = p[0], b = p[1], c = p[2], d = p[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double tb = 2 * b, tc = 2 * c, td = 2 * d;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double tab = tb * a, tac = tc * a, tad = td * a;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tbb = tb * b, tbc = tc * b, tbd = td * b;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    const double tcc = tc * c, tcd = td * c, tdd = td * d;
+    R[0] = 1 - (tyy + tzz); S[0] = 1 - (tcc + tdd);
+    R[1] = txy - twz;       S[1] = tbc - tad;
+    R[2] = txz + twy;       S[2] = tbd + tac;
+    R[3] = txy + twz;       S[3] = tbc + tad;
+    R[4] = 1 - (txx + tzz); S[4] = 1 - (tbb + tdd);
+    R[5] = tyz - twx;       S[5] = tcd - tab;
+    R[6] = txz - twy;       S[6] = tbd - tac;
+    R[7] = tyz + twx;       S[7] = tcd + tab;
+    R[8] = 1 - (txx + tyy); S[8] = 1 - (tbb + tcc);
+}
+// One sample of the pipelined F2: the quaternion half of THIS sample (q <- normalised q * dq, rotmatI2G <- R(q)) side by side with
+// the velocity / position half of the PREVIOUS one (nominal_apply_vp with its operands pq, pdqh, pa, pR0, pdt; its R-after-the-step is
+// the current R(q), Rq).  On return Rq = R of the new quaternion.
+FBUS_HD void nominal_apply_dual(Nominal& n, double* Rq, double pdt, const double* pq, const double* pdqh, const double* pa, const double* pR0,
+                                const double* dq) {
+    double qn[4], qh[4], Rh[9], k1[3], k2[3], k4[3];
+    qmul2(n.q, dq, qn, pq, pdqh, qh);
+    mat3_vec(pR0, pa, k1);
+    mat3_vec(Rq, pa, k4);
+    qnormalize2(qn, qh);
+    FBUS_UNROLL
+    for (int i = 0; i < 4; ++i) n.q[i] = qn[i];
+    q2R2(n.q, n.R, qh, Rh);
+    mat3_vec(Rh, pa, k2);
+    const double dt6 = pdt * (1.0 / 6.0), dt2 = pdt * 0.5;
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const double kv1 = k1[i] + n.g[i], kv2 = k2[i] + n.g[i], kv4 = k4[i] + n.g[i];
+        const double v0 = n.v[i];
+        n.v[i] = v0 + dt6 * (kv1 + 2 * kv2 + 2 * kv2 + kv4);
+        const double kp2 = v0 + kv1 * dt2, kp3 = v0 + kv2 * dt2;
+        n.p[i] = n.p[i] + dt6 * (v0 + 2 * kp2 + 2 * kp3 + kp3);
+    }
+    FBUS_UNROLL
+    for (int i = 0; i < 9; ++i) Rq[i] = n.R[i];
+}
+FBUS_HD void nominal_apply(Nominal& n, double dt, const double* dqh, const double* dq, const double* a) {
+    double R0[9], q0[4];
+    q2R(n.q, R0);
+    FBUS_UNROLL
+    for (int i = 0; i < 4; ++i) q0[i] = n.q[i];
+    nominal_apply_q(n, dq);
+    nominal_apply_vp(n, dt, q0, dqh, a, R0, n.R);
+}
+FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const double* gyro) {
+    double w[3], a[3], dqh[4], dq[4];
+    FBUS_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        w[i] = gyro[i] - n.bg[i];
+        a[i] = accel[i] - n.ba[i];
+    }
+    nominal_increment(w, dt, dqh, dq);
+    nominal_apply(n, dt, dqh, dq, a);
 }
 
 // ------------------------------------------------------------------------------------------------

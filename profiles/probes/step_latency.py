@@ -14,12 +14,12 @@ cfg = capi.config_default()
 traj = synth.truth_trajectory(cfg, 1.0, 200.0, 25.0, periodic=True)
 N, W = traj["base_imu"].shape[0], traj["base_pose"].shape[0]
 dev = torch.device("cuda:0")
-FORMS = {"lane9": {"FBUS_LANE": "1"}, "smem32": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"}, "tmem128": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}}
+FORMS = {"lane9": {"FBUS_LANE": "1"}, "lane9-gen1": {"FBUS_LANE": "1", "FBUS_LANE_GEN": "1"}, "smem32": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"}, "tmem128": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}}
 print("| kernel | filters | us per IMU sample (propagate only) | us per frame (8 samples + update) | => us per update |")
 print("|---|---|---|---|---|")
 for B in (1, 32, 128):
     for name, env in FORMS.items():
-        for k in ("FBUS_LANE", "FBUS_SMALL_BATCH"):
+        for k in ("FBUS_LANE", "FBUS_LANE_GEN", "FBUS_SMALL_BATCH"):
             os.environ.pop(k, None)
         os.environ.update(env)
         f = BatchFilter(cfg, batch=B, device=0)

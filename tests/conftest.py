@@ -51,24 +51,25 @@ def cfg(built):
 
 
 # The window kernel exists in three forms: nine lanes per filter with the covariance in registers (small batches,
-# fbus_kernel_lane.cuh), one thread per filter with the covariance in shared memory (32-filter CTAs) and one thread per filter
+# fbus_kernel_lane.cuh; two generations, "lane" = the current one with the batch spread thin over the SMs as fbus_create does, "lane32" = the same with full 32-filter CTAs, "lane1" = the first, which the MATLAB-semantics mode still uses), one thread per filter with the covariance in shared memory (32-filter CTAs) and one thread per filter
 # with the covariance in tensor memory (128-filter CTAs, batches that fill the GPU).  The parity tests work on small batches,
-# so the modules listed here run three times, forcing each kernel in turn.
+# so the modules listed here run once per form, forcing each kernel in turn.
 _ALL_PATHS = ("test_gpu_step_parity", "test_gpu_replay_parity", "test_gpu_synth_batch", "test_gpu_init_overshoot")
-_PATH_ENV = {"auto": {}, "lane": {"FBUS_LANE": "1"}, "smem": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"},
-             "tmem": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}}
+_PATH_ENV = {"auto": {}, "lane": {"FBUS_LANE": "1"}, "lane32": {"FBUS_LANE": "1", "FBUS_LANE_FPC": "32"},
+             "lane1": {"FBUS_LANE": "1", "FBUS_LANE_GEN": "1"},
+             "smem": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"}, "tmem": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}}
 
 
 def pytest_generate_tests(metafunc):
     if metafunc.module.__name__.split(".")[-1] in _ALL_PATHS and "cov_store" in metafunc.fixturenames:
-        metafunc.parametrize("cov_store", ["lane", "smem", "tmem"], indirect=True)
+        metafunc.parametrize("cov_store", ["lane", "lane32", "lane1", "smem", "tmem"], indirect=True)
 
 
 @pytest.fixture(autouse=True)
 def cov_store(request):
     mode = getattr(request, "param", "auto")
     want = _PATH_ENV[mode]
-    old = {k: os.environ.get(k) for k in ("FBUS_LANE", "FBUS_SMALL_BATCH")}
+    old = {k: os.environ.get(k) for k in ("FBUS_LANE", "FBUS_LANE_GEN", "FBUS_LANE_FPC", "FBUS_SMALL_BATCH")}
     for k in old:
         os.environ.pop(k, None)
     os.environ.update(want)
