@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(LANE_NT, 1) ekf_window_lane_kernel(const __gri
 //     covariance lanes of a filter follow their nominal lane at their own pace.
 // Results are bit-identical to the first generation (the same expressions in the same order, split at values that are not contracted).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr size_t LANE2_SMEM = (size_t)(L2_TOTAL * 32 + LANE_T * 32) * sizeof(double);
+constexpr size_t LANE2_SMEM = (size_t)(L2_TOTAL * 32 + L2_RING + LANE_T * 32) * sizeof(double);
 
 template <bool JOSEPH, bool IMU32>
 __device__ __forceinline__ void lane2_cov_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh, int32_t (*sflag)[32],
@@ -372,7 +372,8 @@ __device__ __forceinline__ void lane2_cov_role(const WinParams& prm, const DevCo
     const bool live = act && f < (int)prm.lane_fpc && b0 < B;
     const size_t b = (b0 < B) ? b0 : B - 1;
     double* const X = smem + f;                                   // exchange area, entry stride 32
-    double* const T = smem + (size_t)L2_TOTAL * 32 + (size_t)f * LANE_T;  // transpose scratch of this filter
+    const double* const ring = smem + (size_t)L2_TOTAL * 32;                                  // [slot][filter][L2_RS]
+    double* const T = smem + (size_t)L2_TOTAL * 32 + L2_RING + (size_t)f * LANE_T;            // transpose scratch of this filter
     // increment pass: this warp is sample slot cw of the chunk, this lane is filter `lane` of the CTA
     double* const XI = smem + lane;
     const size_t bi0 = (size_t)blockIdx.x * prm.lane_fpc + lane;
@@ -437,11 +438,20 @@ __device__ __forceinline__ void lane2_cov_role(const WinParams& prm, const DevCo
                 const int slot = (int)(i - cb);
                 slot_wait(slot);  // record (slot) is complete
                 const bool valid = act && l2.sval[cpar][slot][f] != 0;
-                const double* rec = X + (size_t)slot * LX_REC * 32;
-                double A[9], Bm[9];
+                const double2* rec2 = reinterpret_cast<const double2*>(ring + ((size_t)slot * 32 + (size_t)f) * L2_RS);
+                double A[9], Bm[9], u0, u1, u2, dt;
+                {
+                    double rv[22];
 #pragma unroll
-                for (int e = 0; e < 9; ++e) { A[e] = rec[(size_t)e * 32]; Bm[e] = rec[(size_t)(9 + e) * 32]; }
-                const double u0 = rec[(size_t)18 * 32], u1 = rec[(size_t)19 * 32], u2 = rec[(size_t)20 * 32], dt = rec[(size_t)21 * 32];
+                    for (int e = 0; e < 11; ++e) {
+                        const double2 v = rec2[e];
+                        rv[2 * e] = v.x;
+                        rv[2 * e + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) { A[e] = rv[e]; Bm[e] = rv[9 + e]; }
+                    u0 = rv[18]; u1 = rv[19]; u2 = rv[20]; dt = rv[21];
+                }
                 if (valid) {  // A: M = F P on both columns
                     lane_apply_Fu2(c0, c1, A, Bm, u0, u1, u2, dt);
 #pragma unroll
@@ -568,7 +578,15 @@ __global__ void __launch_bounds__(LANE_NT, 1) ekf_window_lane2_kernel(const __gr
     __shared__ SplitShared sh;
     __shared__ int32_t sflag[3][32];
     __shared__ Lane2Shared l2;
+    __shared__ MarkerTable s_tab;  // the marker map is read by every frame's plan and update: one copy per CTA in shared memory
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        static_assert(sizeof(MarkerTable) % sizeof(double) == 0, "MarkerTable is copied as doubles");
+        const double* src = reinterpret_cast<const double*>(prm.tab);
+        double* dst = reinterpret_cast<double*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(MarkerTable) / sizeof(double)); i += LANE_NT) dst[i] = src[i];
+        __syncthreads();
+    }
     if (wi < 11) {
         lane2_cov_role<JOSEPH, IMU32>(prm, k, smem, sh, sflag, l2, wi, lane);
     } else {
@@ -576,7 +594,8 @@ __global__ void __launch_bounds__(LANE_NT, 1) ekf_window_lane2_kernel(const __gr
         // faster the fewer filters share the CTA's nominal warp, schedulers and shared-memory bandwidth
         const size_t b0 = (size_t)blockIdx.x * prm.lane_fpc + lane;
         const bool live = lane < (int)prm.lane_fpc && b0 < prm.B;
-        nominal_role<32, false, IMU32, true, JOSEPH, false, true>(prm, k, smem, sh, sflag, lane, live ? b0 : prm.B - 1, live, &l2);
+        nominal_role<32, false, IMU32, true, JOSEPH, false, true>(prm, k, smem, sh, sflag, lane, live ? b0 : prm.B - 1, live, &l2, &s_tab,
+                                                                  smem + (size_t)L2_TOTAL * 32);
     }
 }
 

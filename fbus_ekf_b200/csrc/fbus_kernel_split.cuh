@@ -269,8 +269,8 @@ struct FramePlan {
 };
 
 template <int BSF>
-__device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts& k, uint32_t w, size_t b, bool live, uint32_t cursor,
-                                           double n_t, int inited, int& prev_id, int& status, FramePlan& pl) {
+__device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts& k, const MarkerTable* tab, uint32_t w, size_t b, bool live,
+                                           uint32_t cursor, double n_t, int inited, int& prev_id, int& status, FramePlan& pl) {
     const size_t B = prm.B;
     const int mode = prm.mode;
     const bool fused = (mode & M_FUSED) != 0;
@@ -350,12 +350,12 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
             for (int c = 0; c < 3; ++c) dp[c] = pp[(size_t)c * B];
 #pragma unroll
             for (int c = 0; c < 4; ++c) dq[c] = pp[(size_t)(3 + c) * B];
-            mk = find_marker(k, prm.tab, did);
+            mk = find_marker(k, tab, did);
             ok = mk >= 0;
         }
         if (ok) {
             double Rv[9];
-            const MarkerConst mkc = prm.tab->mk[mk];
+            const MarkerConst mkc = tab->mk[mk];
             vision_pose(k, mkc, dp, dq, pl.qv, Rv, pl.pv);
             double t_now = n_t;
             int inited_now = inited;
@@ -383,7 +383,7 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
     if (do_update && n_det > 0) {
         const size_t slot = (size_t)w * prm.m + idx_upd;
         const int did = prm.det_id[slot * B + b];
-        const int mk = find_marker(k, prm.tab, did);
+        const int mk = find_marker(k, tab, did);
         if (mk >= 0) {
             prev_id = did;
             pl.req = mk + 1;
@@ -403,8 +403,8 @@ __device__ __forceinline__ void plan_frame(const WinParams& prm, const DevConsts
 // ComputeVisionOnlyResults.m (normalised Q_IG).  An unknown marker id, on which the MATLAB script would stop with an index error,
 // skips the frame for that filter with a status bit, like the C++ path.
 template <int BSF>
-__device__ __forceinline__ void plan_frame_matlab(const WinParams& prm, const DevConsts& k, uint32_t w, size_t b, bool live, uint32_t cursor,
-                                                  double t_img, int inited, int& prev_id, int& status, FramePlan& pl) {
+__device__ __forceinline__ void plan_frame_matlab(const WinParams& prm, const DevConsts& k, const MarkerTable* tab, uint32_t w, size_t b, bool live,
+                                                  uint32_t cursor, double t_img, int inited, int& prev_id, int& status, FramePlan& pl) {
     const size_t B = prm.B;
     const int mode = prm.mode;
     const bool fused = (mode & M_FUSED) != 0;
@@ -436,12 +436,12 @@ __device__ __forceinline__ void plan_frame_matlab(const WinParams& prm, const De
     if (n_det == 0) { status |= FBUS_ST_NO_DETECTION; return; }
     const size_t slot = (size_t)w * prm.m + idx_near;
     const int did = prm.det_id[slot * B + b];
-    const int mk = find_marker(k, prm.tab, did);
+    const int mk = find_marker(k, tab, did);
     if (mk < 0) {
         status |= inited ? (FBUS_ST_UPDATE_SKIPPED | FBUS_ST_RESET_SKIPPED) : FBUS_ST_INIT_FAILED;
         return;
     }
-    const MarkerConst mkc = prm.tab->mk[mk];
+    const MarkerConst mkc = tab->mk[mk];
     const double* pp = prm.det_pose + slot * 7 * B + b;
 #pragma unroll
     for (int c = 0; c < 7; ++c) pl.y[c] = pp[(size_t)c * B];
@@ -514,11 +514,17 @@ constexpr int LANE_NT = 384;  // 11 covariance warps (3 filters each, 9 lanes pe
 // mbarrier instead of a CTA-wide barrier per sample.  Exchange area: ring L2_CH x 28 | the sections of the first generation, shifted |
 // increments [L2_CH][L2_NE] | ba, bg of the frame.
 constexpr int L2_CH = 8;
-constexpr int L2_SHIFT = (L2_CH - 2) * LX_REC;
-constexpr int L2_NE = 16;  // dt, t, dqh (4), dq (4), a = accel - b_a (3), u = (gyro - b_g) dt (3)
+constexpr int L2_SHIFT = -LX_P6;  // the exchange sections of the first generation start at entry 0 (its two-slot ring is not used)
+constexpr int L2_NE = 16;         // dt, t, dqh (4), dq (4), a = accel - b_a (3), u = (gyro - b_g) dt (3)
 constexpr int L2_INC = LX_TOTAL + L2_SHIFT;
 constexpr int L2_BIAS = L2_INC + L2_CH * L2_NE;
 constexpr int L2_TOTAL = L2_BIAS + 6;
+// ring of the second generation: [slot][filter][L2_RS doubles], a filter's record (A 9, B 9, u 3, dt = 22 doubles) contiguous so that
+// it moves as eleven 16-byte accesses on both sides.  L2_RS = 30: the 32 nominal lanes' 16-byte stores at a stride of 240 bytes
+// fall on eight distinct bank groups (four wavefronts for 512 bytes, the minimum), the three filters a covariance warp reads are
+// conflict-free, and 240 is a multiple of 16.
+constexpr int L2_RS = 30;
+constexpr int L2_RING = L2_CH * 32 * L2_RS;  // doubles
 struct Lane2Shared {
     int32_t sval[2][L2_CH][32];      // sample (slot) is processed by filter (lane); double-buffered by chunk parity: the nominal
                                      // lane posts chunk c+1 while the covariance lanes may still be working through chunk c
@@ -562,7 +568,9 @@ struct P6View {
 // injection, the covariance lanes run the sweep P -= Z^T Z and dx = Z^T y.
 template <int BSF, bool TM, bool IMU32 = false, bool LANE = false, bool JOSEPH = false, bool MATLAB = false, bool LANE2 = false>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
-                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live, Lane2Shared* l2 = nullptr) {
+                                             int32_t (*sflag)[BSF], int fl, size_t b, bool live, Lane2Shared* l2 = nullptr,
+                                             const MarkerTable* tab_smem = nullptr, double* ring2 = nullptr) {
+    const MarkerTable* const tab = tab_smem ? tab_smem : prm.tab;  // the second-generation lane kernel keeps a copy in shared memory
     constexpr int NT = LANE ? LANE_NT : 2 * BSF, NW = BSF / 32;
     static_assert(!LANE || BSF == 32, "the lanes-per-filter kernel has 32 filters per CTA");
     static_assert(!MATLAB || (LANE && !JOSEPH), "the MATLAB-semantics mode runs on the lanes-per-filter kernel, reference update form");
@@ -601,8 +609,8 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 
     double t_img = MATLAB ? prm.nom[(size_t)F_TIMG * B + b] : 0.0;  // preImgTime (FBUS_EKF.m:144)
     auto plan = [&](uint32_t wf, FramePlan& out) {
-        if constexpr (MATLAB) plan_frame_matlab<BSF>(prm, k, wf, b, live, cursor, t_img, inited, prev_id, status, out);
-        else plan_frame<BSF>(prm, k, wf, b, live, cursor, n.t, inited, prev_id, status, out);
+        if constexpr (MATLAB) plan_frame_matlab<BSF>(prm, k, tab, wf, b, live, cursor, t_img, inited, prev_id, status, out);
+        else plan_frame<BSF>(prm, k, tab, wf, b, live, cursor, n.t, inited, prev_id, status, out);
         if constexpr (LANE2) {
             // lanes past the batch mirror the last filter for their reads; in this kernel they neither propagate nor update, so
             // that a small batch (the live single-filter case) leaves the covariance warps of the unused slots asleep
@@ -737,17 +745,20 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                             // coefficients of F from the CARRIED rotmatI2G (A.3-2,3), as cov_coeffs forms them
                             const double ndt = -dt;
                             const double s0 = av[0] * ndt, s1 = av[1] * ndt, s2 = av[2] * ndt;
-                            double* rec = X + (size_t)slot * REC * BSF;
+                            double rv[22];
 #pragma unroll
                             for (int r = 0; r < 3; ++r) {
-                                rec[(size_t)(r * 3 + 0) * BSF] = n.R[r * 3 + 1] * s2 - n.R[r * 3 + 2] * s1;
-                                rec[(size_t)(r * 3 + 1) * BSF] = n.R[r * 3 + 2] * s0 - n.R[r * 3 + 0] * s2;
-                                rec[(size_t)(r * 3 + 2) * BSF] = n.R[r * 3 + 0] * s1 - n.R[r * 3 + 1] * s0;
+                                rv[r * 3 + 0] = fma(n.R[r * 3 + 1], s2, -FBUS_PROD(n.R[r * 3 + 2], s1));
+                                rv[r * 3 + 1] = fma(n.R[r * 3 + 2], s0, -FBUS_PROD(n.R[r * 3 + 0], s2));
+                                rv[r * 3 + 2] = fma(n.R[r * 3 + 0], s1, -FBUS_PROD(n.R[r * 3 + 1], s0));
 #pragma unroll
-                                for (int c = 0; c < 3; ++c) rec[(size_t)(9 + r * 3 + c) * BSF] = n.R[r * 3 + c] * ndt;
+                                for (int c = 0; c < 3; ++c) rv[9 + r * 3 + c] = n.R[r * 3 + c] * ndt;
                             }
-                            rec[(size_t)18 * BSF] = u[0]; rec[(size_t)19 * BSF] = u[1]; rec[(size_t)20 * BSF] = u[2];  // -[w]x dt by its three numbers
-                            rec[(size_t)21 * BSF] = dt;
+                            rv[18] = u[0]; rv[19] = u[1]; rv[20] = u[2];  // -[w]x dt by its three numbers
+                            rv[21] = dt;
+                            double2* rec2 = reinterpret_cast<double2*>(ring2 + ((size_t)slot * 32 + (size_t)fl) * L2_RS);
+#pragma unroll
+                            for (int e = 0; e < 11; ++e) rec2[e] = make_double2(rv[2 * e], rv[2 * e + 1]);
                         }
                         __syncwarp();
                         slot_arrive(slot);  // record (slot) is complete
@@ -874,7 +885,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                 sbar(wq);  // (p) the covariance lanes have published P6
                 L2T(LANE2 && fl == 0, 0, 7);
                 if (req) {
-                    const MarkerConst mkc = prm.tab->mk[req - 1];
+                    const MarkerConst mkc = tab->mk[req - 1];
                     if constexpr (JOSEPH) {  // 6-row factor Lc of the Joseph-form C_J and y = Lc^-1 u
                         double Cm[21], yv[6];
                         update_prologue<BSF, BSF, true, P6View>(P6View{X + (size_t)(LXS + LX_P6) * BSF}, n, k, mkc, pl.y, pl.y + 3, Cm, yv,

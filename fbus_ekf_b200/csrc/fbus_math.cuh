@@ -189,15 +189,23 @@ FBUS_HD void qnormalize(double* q) {
     const double inv = rsqrt_d(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
 }
+// An expression like  t1*x - t2*w  has two products, and the compiler may contract either into the FMA: which one it picks can differ
+// between two instantiations of the same kernel (it did: the float32-sensor and the double instantiation of the lane kernel rounded
+// R(q) differently in the last bit, and the bitwise tests between the two element formats caught it).  Where a sum has more than one
+// product the pairing is therefore written out: FBUS_PROD is a product rounded on its own, the other one goes into an explicit fma.
+#ifdef __CUDA_ARCH__
+#define FBUS_PROD(a, b) __dmul_rn((a), (b))
+#else
+#define FBUS_PROD(a, b) ((a) * (b))
+#endif
 FBUS_HD void q2R(const double* q, double* R) {  // Eigen toRotationMatrix, literal also for non-unit q
     const double w = q[0], x = q[1], y = q[2], z = q[3];
     const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
-    const double twx = tx * w, twy = ty * w, twz = tz * w;
-    const double txx = tx * x, txy = ty * x, txz = tz * x;
-    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
-    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
-    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+    const double twx = FBUS_PROD(tx, w), twy = FBUS_PROD(ty, w), twz = FBUS_PROD(tz, w);
+    const double tyy = FBUS_PROD(ty, y), tzz = FBUS_PROD(tz, z);
+    R[0] = 1 - fma(ty, y, tzz);  R[1] = fma(ty, x, -twz);     R[2] = fma(tz, x, twy);
+    R[3] = fma(ty, x, twz);      R[4] = 1 - fma(tx, x, tzz);  R[5] = fma(tz, y, -twx);
+    R[6] = fma(tz, x, -twy);     R[7] = fma(tz, y, twx);      R[8] = 1 - fma(tx, x, tyy);
 }
 FBUS_HD void R2q(const double* m, double* q) {  // Eigen Quaterniond(Matrix3d), not normalised
     double t = m[0] + m[4] + m[8];
@@ -336,9 +344,9 @@ FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, dou
     FBUS_UNROLL
     for (int i = 0; i < 3; ++i) {
         // (R * [v]x)[i][:] = (R[i][1]v2 - R[i][2]v1, R[i][2]v0 - R[i][0]v2, R[i][0]v1 - R[i][1]v0)
-        A[i * 3 + 0] = R[i * 3 + 1] * s2 - R[i * 3 + 2] * s1;
-        A[i * 3 + 1] = R[i * 3 + 2] * s0 - R[i * 3 + 0] * s2;
-        A[i * 3 + 2] = R[i * 3 + 0] * s1 - R[i * 3 + 1] * s0;
+        A[i * 3 + 0] = fma(R[i * 3 + 1], s2, -FBUS_PROD(R[i * 3 + 2], s1));
+        A[i * 3 + 1] = fma(R[i * 3 + 2], s0, -FBUS_PROD(R[i * 3 + 0], s2));
+        A[i * 3 + 2] = fma(R[i * 3 + 0], s1, -FBUS_PROD(R[i * 3 + 1], s0));
         FBUS_UNROLL
         for (int j = 0; j < 3; ++j) B[i * 3 + j] = R[i * 3 + j] * ndt;
     }
@@ -766,21 +774,19 @@ FBUS_HD void q2R2(const double* q, double* R, const double* p, double* S) {
     const double a = p[0], b = p[1], c = p[2], d = p[3];
     const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
     const double tb = 2 * b, tc = 2 * c, td = 2 * d;
-    const double twx = tx * w, twy = ty * w, twz = tz * w;
-    const double tab = tb * a, tac = tc * a, tad = td * a;
-    const double txx = tx * x, txy = ty * x, txz = tz * x;
-    const double tbb = tb * b, tbc = tc * b, tbd = td * b;
-    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    const double tcc = tc * c, tcd = td * c, tdd = td * d;
-    R[0] = 1 - (tyy + tzz); S[0] = 1 - (tcc + tdd);
-    R[1] = txy - twz;       S[1] = tbc - tad;
-    R[2] = txz + twy;       S[2] = tbd + tac;
-    R[3] = txy + twz;       S[3] = tbc + tad;
-    R[4] = 1 - (txx + tzz); S[4] = 1 - (tbb + tdd);
-    R[5] = tyz - twx;       S[5] = tcd - tab;
-    R[6] = txz - twy;       S[6] = tbd - tac;
-    R[7] = tyz + twx;       S[7] = tcd + tab;
-    R[8] = 1 - (txx + tyy); S[8] = 1 - (tbb + tcc);
+    const double twx = FBUS_PROD(tx, w), twy = FBUS_PROD(ty, w), twz = FBUS_PROD(tz, w);
+    const double tab = FBUS_PROD(tb, a), tac = FBUS_PROD(tc, a), tad = FBUS_PROD(td, a);
+    const double tyy = FBUS_PROD(ty, y), tzz = FBUS_PROD(tz, z);
+    const double tcc = FBUS_PROD(tc, c), tdd = FBUS_PROD(td, d);
+    R[0] = 1 - fma(ty, y, tzz);  S[0] = 1 - fma(tc, c, tdd);
+    R[1] = fma(ty, x, -twz);     S[1] = fma(tc, b, -tad);
+    R[2] = fma(tz, x, twy);      S[2] = fma(td, b, tac);
+    R[3] = fma(ty, x, twz);      S[3] = fma(tc, b, tad);
+    R[4] = 1 - fma(tx, x, tzz);  S[4] = 1 - fma(tb, b, tdd);
+    R[5] = fma(tz, y, -twx);     S[5] = fma(td, c, -tab);
+    R[6] = fma(tz, x, -twy);     S[6] = fma(td, b, -tac);
+    R[7] = fma(tz, y, twx);      S[7] = fma(td, c, tab);
+    R[8] = 1 - fma(tx, x, tyy);  S[8] = 1 - fma(tb, b, tcc);
 }
 // One sample of the pipelined F2: the quaternion half of THIS sample (q <- normalised q * dq, rotmatI2G <- R(q)) side by side with
 // the velocity / position half of the PREVIOUS one (nominal_apply_vp with its operands pq, pdqh, pa, pR0, pdt; its R-after-the-step is
@@ -834,9 +840,10 @@ FBUS_HD void propagate_nominal(Nominal& n, double dt, const double* accel, const
 // MATLAB filter applies it to un-normalised products)
 FBUS_HD void q2R_matlab(const double* q, double* R) {
     const double w = q[0], x = q[1], y = q[2], z = q[3];
-    R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z);           R[2] = 2 * (x * z + w * y);
-    R[3] = 2 * (x * y + w * z);           R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
-    R[6] = 2 * (x * z - w * y);           R[7] = 2 * (y * z + w * x);           R[8] = w * w - x * x - y * y + z * z;
+    const double ww = FBUS_PROD(w, w), wx = FBUS_PROD(w, x), wy = FBUS_PROD(w, y), wz = FBUS_PROD(w, z);  // (pairing written out: see q2R)
+    R[0] = fma(-z, z, fma(-y, y, fma(x, x, ww)));  R[1] = 2 * fma(x, y, -wz);                     R[2] = 2 * fma(x, z, wy);
+    R[3] = 2 * fma(x, y, wz);                      R[4] = fma(-z, z, fma(y, y, fma(-x, x, ww)));  R[5] = 2 * fma(y, z, -wx);
+    R[6] = 2 * fma(x, z, -wy);                     R[7] = 2 * fma(y, z, wx);                      R[8] = fma(z, z, fma(-y, y, fma(-x, x, ww)));
 }
 // ImuUpdate.m:37-60,76-79: always the axis-angle increment (axis = w/|w|: NaN for w = 0, as MATLAB), rotation matrices of
 // the UN-normalised products, R0 = the carried State.rotateMat, State.rotateMat <- R(qT), State.quaternion <- qT/|qT|
