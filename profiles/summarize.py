@@ -2,6 +2,7 @@
 
     python profiles/summarize.py full  gpurun_out/prof_window_r1_final.ncu-rep  profiles/r1_window_kernel_ncu_full.md
     python profiles/summarize.py list  gpurun_out/launches_r1_final.csv         profiles/r1_launches.md
+    python profiles/summarize.py inputs gpurun_out/prof_window_r2.ncu-rep       profiles/roofline_inputs.json
 """
 import collections
 import csv
@@ -87,5 +88,59 @@ def launch_list(path, out):
     open(out, "w").write("\n".join(lines) + "\n")
 
 
+def roofline_inputs(rep, out):
+    """profiles/roofline_inputs.json from an `ncu --set full` capture of ekf_window_split_kernel<128> (one launch of the bench workload:
+    200 IMU steps + 25 updates per filter).  Stamped with the source hash of the library in the tree, which must be the one profiled:
+    bench.py reports the profiler-derived fields only while the loaded library has the same hash."""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def val(k, scale=None):
+        v = float(vals[col[k]].replace(",", ""))
+        u = units[col[k]].lower()
+        if scale == "bytes":
+            v *= {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+        return v
+    assert "ekf_window_split_kernel<128" in vals[col["Kernel Name"]].replace("(int)", ""), vals[col["Kernel Name"]]
+    filters = int(val("launch__grid_size")) * 128
+    rd, wr = val("dram__bytes_read.sum", "bytes"), val("dram__bytes_write.sum", "bytes")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(src.splitlines()))
+    shdr, data = srows[1], srows[2:]
+    ix = {h: i for i, h in enumerate(shdr)}
+    flop = 0.0
+    for r in data:
+        toks = r[ix["Source"]].split()
+        if not toks:
+            continue
+        op = (toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]).split(".")[0]
+        if op in ("DFMA", "DMUL", "DADD"):
+            flop += (2.0 if op == "DFMA" else 1.0) * float(r[ix["Predicated-On Thread Instructions Executed"]])
+    here = os.path.dirname(os.path.abspath(__file__))
+    try:
+        old = json.load(open(out))
+    except Exception:
+        old = {}
+    new = {"kernel": "ekf_window_split_kernel<128>",
+           "source": f"{os.path.basename(rep)} (ncu --set full --clock-control none, one launch: 200 IMU steps + 25 updates per filter); summary in "
+                     "profiles/r2_window_kernel_ncu_full.md",
+           "srchash": open(os.path.join(here, "..", "fbus_ekf_b200", "libfbus_ekf.so.srchash")).read().strip(),
+           "measured_at_filters": filters,
+           "dram__bytes_read.sum": rd, "dram__bytes_write.sum": wr,
+           "ekf_window_dram_bytes_per_filter_per_launch": (rd + wr) / filters,
+           "fp64_flop_executed_per_filter_per_launch": flop / filters,
+           "fp64_pipe_busy_pct_ncu": val("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+           "issue_active_pct_ncu": val("smsp__issue_active.avg.pct_of_peak_sustained_active")}
+    for k in ("refract_kernel", "solve_to_det_kernel"):
+        if k in old:
+            new[k] = old[k]
+    json.dump(new, open(out, "w"), indent=1)
+    print(json.dumps(new, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"full": full, "list": launch_list, "inputs": roofline_inputs}[sys.argv[1]](sys.argv[2], sys.argv[3])
