@@ -1,6 +1,6 @@
 """Randomised GPU-vs-oracle soak of the window kernel (not collected by pytest; run on a B200: python tests/soak_gpu.py [iterations]).
 Every iteration draws a batch size (ragged), a stream length, a pattern of dropped detections / unknown marker ids / far markers
-and a kernel path (32-filter shared-memory CTAs, 128-filter tensor-memory CTAs) and an IMU element format, runs the fused windows on the
+and a kernel path (both generations of the lanes-per-filter kernel, the second one also with full 32-filter CTAs; 32-filter shared-memory CTAs; 128-filter tensor-memory CTAs) and an IMU element format, runs the fused windows on the
 GPU and in the CPU oracle and compares status words bit for bit, trace rows and covariance to 1e-9."""
 import os
 import sys
@@ -15,12 +15,14 @@ import orc  # noqa: E402
 from fbus_ekf_b200 import BatchFilter, capi, synth  # noqa: E402
 from helpers import cov_close  # noqa: E402
 
-PATHS = {"lane9": {"FBUS_LANE": "1"}, "smem32": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"}, "tmem128": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}}
+PATHS = {"lane9": {"FBUS_LANE": "1"}, "lane9-full-cta": {"FBUS_LANE": "1", "FBUS_LANE_FPC": "32"}, "lane9-gen1": {"FBUS_LANE": "1", "FBUS_LANE_GEN": "1"},
+         "smem32": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "1"}, "tmem128": {"FBUS_LANE": "0", "FBUS_SMALL_BATCH": "0"}}
+_ENV_KEYS = ("FBUS_SMALL_BATCH", "FBUS_LANE", "FBUS_LANE_GEN", "FBUS_LANE_FPC")
 
 
 def one(it, rng, cfg):
     path = list(PATHS)[it % len(PATHS)]
-    for k in ("FBUS_SMALL_BATCH", "FBUS_LANE"):
+    for k in _ENV_KEYS:
         os.environ.pop(k, None)
     os.environ.update(PATHS[path])
     B = int(rng.integers(1, 400))
@@ -80,7 +82,7 @@ def board(it, rng, cfg):
     """multi-marker frames (8 board markers, refractive solve on the GPU -> detections), random subsets of the markers
     detected per filter and frame, occasional unknown ids: marker selection / hysteresis / prev-id logic across all paths"""
     path = list(PATHS)[it % len(PATHS)]
-    for k in ("FBUS_SMALL_BATCH", "FBUS_LANE"):
+    for k in _ENV_KEYS:
         os.environ.pop(k, None)
     os.environ.update(PATHS[path])
     B, m = int(rng.integers(1, 200)), 8
