@@ -70,37 +70,8 @@ __device__ __forceinline__ void lane_apply_F(double* x, const double* A, const d
     for (int i = 0; i < 9; ++i) x[i] = y[i];
 }
 
-// the same with F[theta,theta] - I = -[w]x dt given by u = w dt (C++ semantics only): 30 FMA, same products in the same order
-__device__ __forceinline__ void lane_apply_Fu(double* x, const double* A, const double* Bm, double u0, double u1, double u2, double dt) {
-    double y[9];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        double s = x[i];
-        s += dt * x[3 + i];
-        y[i] = s;
-        double t = x[3 + i];
-        t += dt * x[15 + i];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            t += A[i * 3 + c] * x[6 + c];
-            t += Bm[i * 3 + c] * x[9 + c];
-        }
-        y[3 + i] = t;
-    }
-    {
-        double t0 = x[6], t1 = x[7], t2 = x[8];
-        t0 -= dt * x[12]; t1 -= dt * x[13]; t2 -= dt * x[14];
-        t0 += u2 * x[7]; t0 -= u1 * x[8];
-        t1 -= u2 * x[6]; t1 += u0 * x[8];
-        t2 += u1 * x[6]; t2 -= u0 * x[7];
-        y[6] = t0; y[7] = t1; y[8] = t2;
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) x[i] = y[i];
-}
-
-// y = F x on TWO columns at once, written term by term across all eighteen results (the same products in the same order per result
-// as lane_apply_Fu): with few warps per scheduler every dependent FP64 instruction costs its full 8-clock latency, and ptxas keeps the
+// y = F x on TWO columns at once with F[theta,theta] - I = -[w]x dt given by u = w dt (C++ semantics only: 30 FMA per column), written
+// term by term across all eighteen results (the same products in the same order per result as lane_apply_F): with few warps per scheduler every dependent FP64 instruction costs its full 8-clock latency, and ptxas keeps the
 // source order of independent chains, so the independent results are advanced together instead of one after the other
 __device__ __forceinline__ void lane_apply_Fu2(double* x, double* z, const double* A, const double* Bm, double u0, double u1, double u2, double dt) {
     double px[3], pz[3], vx[3], vz[3], tx[3], tz[3];
