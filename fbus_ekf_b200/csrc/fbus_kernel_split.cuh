@@ -27,13 +27,6 @@
 #ifndef FBUS_TMEM
 #define FBUS_TMEM 1
 #endif
-// 1: in the tensor-memory kernel the NOMINAL warp advances block column 5 (the gravity columns) of the covariance cross blocks
-// (column_job5, ~17 % of the covariance warp's step) in the ~1 000 clocks per step it otherwise waits at the pair barrier.  The three
-// blocks ping-pong between their home columns and a second copy in the spare tensor-memory columns, so that the covariance warp's
-// reads of the old blocks never meet the nominal warp's stores of the new ones; the existing per-sample pair barrier orders the rest.
-#ifndef FBUS_K5
-#define FBUS_K5 0
-#endif
 
 namespace fbus {
 
@@ -171,37 +164,12 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #pragma unroll
         for (int q = 1; q < NW; ++q) { lo = min(lo, sh.lo_hi[fp][0][q]); hi = max(hi, sh.lo_hi[fp][1][q]); }
         int fs = 0;  // ring slot that carries the update request
-        constexpr bool K5 = TM && (FBUS_K5 != 0);
-        double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
-        // K5: which copy holds the current blocks (0,5), (1,5), (2,5) (0 = home); a*M05, a*M15 of the last step still to be folded in
-        uint32_t par5 = 0;
-        bool pend5 = false;
-        double a5 = 0.0;
-        auto fold5 = [&]() {  // P'01 += a*M05 ; P'11 += a*M15 (upper) with the blocks the nominal warp has just written
-            double M05[9], M15[9];
-            P.ldblk_nw(0, 5, M05);
-            P.ldtr_nw(1, 5, M15, false);
-            P.wait_ld();
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    double t = TL[tlidx(i, 3 + j)];
-                    t += a5 * M05[i * 3 + j];
-                    TL[tlidx(i, 3 + j)] = t;
-                    if (j >= i) {
-                        double t1 = TL[tlidx(3 + i, 3 + j)];
-                        t1 += a5 * M15[i * 3 + j];
-                        TL[tlidx(3 + i, 3 + j)] = t1;
-                    }
-                }
-        };
         if (lo < hi) {
             fs = (int)((hi - lo) & 1u);
+            double TL[NTL];  // top-left 9x9 of P lives in registers for the whole window
             tl_load_any<TM>(P, TL);
             for (uint32_t i = lo; i < hi; ++i) {
                 step_bar(wq);  // record (i) is complete; the nominal warp moves on to sample i+1
-                if constexpr (K5) tm_fence_after_sync();
                 const int slot = (int)((i - lo) & 1u);
                 const int valid = sflag[slot][fl];
                 // tensor-memory accesses are warp-wide: a warp with any valid lane runs the step on all lanes, the
@@ -216,45 +184,12 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
                     double Qv[4] = {k.Qd[0], k.Qd[1], k.Qd[2], k.Qd[3]};
                     if (TM && !valid) Qv[0] = Qv[1] = Qv[2] = Qv[3] = 0.0;  // the record of an invalid sample is all zeros
                     P.fence_st();  // the previous step's stores
-                    if constexpr (K5) {
-                        // copy par5 holds column 5 after the previous step (the nominal warp finished it before the barrier above):
-                        // fold its new blocks into the top-left block, then read them as this step's OLD blocks; the nominal warp
-                        // meanwhile writes this step's new blocks into the other copy
-                        P.off5 = par5 ? TM_K5_OFF : 0u;
-                        if (pend5) fold5();
-                        propagate_cov_core<BSF, true, CV, true>(P, A, Bm, u0, u1, u2, dt, Qv, TL);
-                        a5 = dt;
-                        pend5 = true;
-                        par5 ^= 1u;
-                    } else {
-                        propagate_cov_core<BSF, true>(P, A, Bm, u0, u1, u2, dt, Qv, TL);
-                    }
+                    propagate_cov_core<BSF, true>(P, A, Bm, u0, u1, u2, dt, Qv, TL);
                 }
             }
-            if constexpr (!K5) tl_store_any<TM>(P, TL);
+            tl_store_any<TM>(P, TL);
         }
-        if constexpr (K5) { P.fence_st(); tm_fence_before_sync(); }
         step_bar(wq);  // (r) update request posted (normally long before this warp gets here)
-        if constexpr (K5) {
-            tm_fence_after_sync();
-            if (lo < hi) {  // the nominal warp has finished the last column job: fold it, bring column 5 home, park the top-left block
-                P.off5 = par5 ? TM_K5_OFF : 0u;
-                if (pend5) fold5();
-                if (par5) {
-                    double C0[9], C1[9], C2[9];
-                    P.ldblk_nw(0, 5, C0);
-                    P.ldtr_nw(1, 5, C1, false);
-                    P.ldtr_nw(2, 5, C2, false);
-                    P.wait_ld();
-                    P.off5 = 0u;
-                    P.stblk(0, 5, C0);
-                    P.sttr(1, 5, C1);
-                    P.sttr(2, 5, C2);
-                }
-                P.off5 = 0u;
-                tl_store_any<TM>(P, TL);
-            }
-        }
         if (pair_any(sh, wq)) {
             const int req = sflag[2][fl];
             if (TM ? true : (req != 0)) {  // tensor memory: all lanes, the ones without a request with zero gain
@@ -287,7 +222,6 @@ __device__ __forceinline__ void cov_role(const WinParams& prm, const DevConsts& 
 #pragma unroll
                 for (int c = 0; c < 4; ++c) X[(size_t)(26 + c) * BSF] = t.q[c];
             }
-            if constexpr (K5) tm_fence_before_sync();
             step_bar(wq);  // (d) results posted
         }
     }
@@ -635,7 +569,7 @@ struct P6View {
 template <int BSF, bool TM, bool IMU32 = false, bool LANE = false, bool JOSEPH = false, bool MATLAB = false, bool LANE2 = false>
 __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevConsts& k, double* smem, SplitShared& sh,
                                              int32_t (*sflag)[BSF], int fl, size_t b, bool live, Lane2Shared* l2 = nullptr,
-                                             const MarkerTable* tab_smem = nullptr, double* ring2 = nullptr, uint32_t tm_base = 0) {
+                                             const MarkerTable* tab_smem = nullptr, double* ring2 = nullptr) {
     const MarkerTable* const tab = tab_smem ? tab_smem : prm.tab;  // the second-generation lane kernel keeps a copy in shared memory
     constexpr int NT = LANE ? LANE_NT : 2 * BSF, NW = BSF / 32;
     static_assert(!LANE || BSF == 32, "the lanes-per-filter kernel has 32 filters per CTA");
@@ -688,13 +622,6 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
     };
     FramePlan pl;
     if (prm.w0 < prm.w1) plan(prm.w0, pl);
-    // FBUS_K5: this warp advances block column 5 of the covariance cross blocks (see the macro); same lane partition of tensor memory
-    // as the covariance warp of the pair
-    constexpr bool K5 = TM && !LANE && (FBUS_K5 != 0);
-    CovTM<false> P5in, P5out;
-    if constexpr (K5) {
-        P5in.base = P5out.base = __shfl_sync(0xffffffffu, tm_base + ((uint32_t)((threadIdx.x >> 5) & 3) << 21), 0);
-    }
 
     for (uint32_t w = prm.w0; w < prm.w1; ++w) {
         L2T(LANE2 && fl == 0, 0, 1);
@@ -871,24 +798,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
             double s_t = pfi ? pf_st : prm.imu_t[lo], s_d[6];
 #pragma unroll
             for (int c = 0; c < 6; ++c) s_d[c] = pfi ? pf_sd[c] : imu_sample_t<IMU32>(prm, k.imu_g, lo, c, B, b);
-            // K5: coefficients of the last published sample, whose column job runs after that sample's barrier
-            double kA[9], kB[9], ku[3] = {0.0, 0.0, 0.0}, kdt = 0.0;
-            bool k_have = false, k_any = false;
-            uint32_t par5 = 0;  // copy that holds the current column-5 blocks (0 = home), as the covariance warp counts it
-            auto job5 = [&]() {
-                if (k_have && k_any) {
-                    P5in.off5 = par5 ? TM_K5_OFF : 0u;
-                    P5out.off5 = par5 ? 0u : TM_K5_OFF;
-                    column_job5(P5in, P5out, kA, kB, ku[0], ku[1], ku[2], kdt);
-                    par5 ^= 1u;
-                }
-            };
-            if constexpr (K5) {
-#pragma unroll
-                for (int e = 0; e < 9; ++e) kA[e] = kB[e] = 0.0;
-            }
             for (uint32_t i = lo; i < hi; ++i) {
-                if constexpr (K5) job5();  // column 5 of sample i-1 (its barrier is behind us: the covariance warp has read the old blocks)
                 const double ti = s_t;
                 double d[6];
 #pragma unroll
@@ -914,12 +824,6 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
 #pragma unroll
                         for (int c = 0; c < 3; ++c) { av[c] = d[c] - n.ba[c]; wv[c] = d[3 + c] - n.bg[c]; }
                         cov_coeffs(n.R, av, wv, dt, A, Bm, u);  // F1 uses the CARRIED rotmatI2G (A.3-2,3)
-                        if constexpr (K5) {
-#pragma unroll
-                            for (int e = 0; e < 9; ++e) { kA[e] = A[e]; kB[e] = Bm[e]; }
-                            ku[0] = u[0]; ku[1] = u[1]; ku[2] = u[2];
-                            kdt = dt;
-                        }
                         double* rec = X + (size_t)slot * REC * BSF;
 #pragma unroll
                         for (int e = 0; e < 9; ++e) { rec[(size_t)e * BSF] = A[e]; rec[(size_t)(9 + e) * BSF] = Bm[e]; }
@@ -950,25 +854,7 @@ __device__ __forceinline__ void nominal_role(const WinParams& prm, const DevCons
                     for (int e = 0; e < 22; ++e) rec[(size_t)e * BSF] = 0.0;
                 }
                 sflag[slot][fl] = valid;
-                if constexpr (K5) {
-                    if (!valid) {  // neutral step for this lane: F = I
-#pragma unroll
-                        for (int e = 0; e < 9; ++e) kA[e] = kB[e] = 0.0;
-                        ku[0] = ku[1] = ku[2] = 0.0;
-                        kdt = 0.0;
-                    }
-                    k_have = true;
-                    k_any = __any_sync(0xffffffffu, valid) != 0;
-                    tm_wait_st();
-                    tm_fence_before_sync();
-                }
                 sbar(wq);  // publish record (i); also: the covariance warp has finished sample i-1
-                if constexpr (K5) tm_fence_after_sync();
-            }
-            if constexpr (K5) {
-                job5();  // the window's last sample
-                tm_wait_st();
-                tm_fence_before_sync();
             }
             if (fused && do_prop) cursor = consumed;
         }
@@ -1146,7 +1032,7 @@ __global__ void __launch_bounds__(2 * BSF) ekf_window_split_kernel(const __grid_
         tm_base = tm_alloc_cta(&tm_slot);
     }
     if (is_cov) cov_role<BSF, JOSEPH, TM>(prm, k, smem, sh, sflag, fl, b, live, tm_base);
-    else nominal_role<BSF, TM, IMU32>(prm, k, smem, sh, sflag, fl, b, live, nullptr, nullptr, nullptr, tm_base);
+    else nominal_role<BSF, TM, IMU32>(prm, k, smem, sh, sflag, fl, b, live);
     if constexpr (TM) tm_free_cta(tm_base);
 }
 

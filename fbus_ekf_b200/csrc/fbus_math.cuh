@@ -356,10 +356,7 @@ FBUS_HD void cov_coeffs(const double* R, const double* acc, const double* w, dou
 
 // TLR = true: the top-left 9x9 (p, v, theta covariance: read AND written by every step) is held in the caller's
 // registers TL[45] across the IMU samples of a window instead of making a round trip through shared memory per step.
-// SKIP5 (FBUS_K5, fbus_kernel_split.cuh): block column 5 of rows 0..2 is advanced by ANOTHER warp (column_job5 below); this warp adds the
-// d01 / d11 terms here and folds a*M05, a*M15 of the new blocks into the top-left block at the start of its next step -- the same
-// additions in the same order as the k == 5 branch below.
-template <int S, bool TLR = false, class CV = Cov<S>, bool SKIP5 = false>
+template <int S, bool TLR = false, class CV = Cov<S>>
 FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, double u0, double u1, double u2, double dt,
                                 const double* Qd, double* TL = nullptr) {
 // element (r, c) of block (bi, bj) loaded with ldblk_nw: a blocked accessor delivers the stored block (min, max), i.e. the
@@ -529,7 +526,7 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
     // the new cross blocks are computed and folded into the top-left block
     double d01[9], d11[9];
     FBUS_UNROLL
-    for (int kk = 0; kk < (SKIP5 ? 2 : 3); ++kk) {
+    for (int kk = 0; kk < 3; ++kk) {
         const int k = (kk == 0) ? 4 : (kk == 1) ? 3 : 5;
         double X1[9], X2[9], M0[9], M2[9];
         {
@@ -660,15 +657,6 @@ FBUS_HD void propagate_cov_core(const CV P, const double* A, const double* B, do
         }
         FBUS_FENCE_B;
     }
-    if (SKIP5) {  // P'01 += d01 ; P'11 += d11 (upper): the a*M05 / a*M15 halves follow when the other warp's blocks are there
-        FBUS_UNROLL
-        for (int i = 0; i < 3; ++i)
-            FBUS_UNROLL
-            for (int j = 0; j < 3; ++j) {
-                FBUS_TLST(i, 3 + j, FBUS_TLLD(i, 3 + j) + d01[i * 3 + j]);
-                if (j >= i) FBUS_TLST(3 + i, 3 + j, FBUS_TLLD(3 + i, 3 + j) + d11[i * 3 + j]);
-            }
-    }
 #undef FBUS_WX_ACC
 #undef FBUS_XWT_ACC
 #undef FBUS_BLK
@@ -683,50 +671,6 @@ FBUS_HD void propagate_cov(const Cov<S> P, const double* R, const double* acc, c
     double A[9], B[9], u[3];
     cov_coeffs(R, acc, w, dt, A, B, u);
     propagate_cov_core<S, false>(P, A, B, u[0], u[1], u[2], dt, Qd, nullptr);
-}
-
-// Block column 5 (the gravity columns) of rows 0..2 for one step, the k == 5 iteration of phase 2 above on its own: reads the
-// blocks of the copy `Pin` selects (and the bottom-right blocks (3,5), (4,5), (5,5), which propagation never changes), writes the
-// new (0,5), (1,5), (2,5) through `Pout`.  No process noise lands in this column.
-template <class CV>
-FBUS_HD void column_job5(const CV Pin, const CV Pout, const double* A, const double* B, double u0, double u1, double u2, double a) {
-    double X1[9], X2[9], M0[9], M2[9], X3[9], X4[9], X5[9];
-    Pin.ldtr_nw(1, 5, X1, false);
-    Pin.ldblk_nw(0, 5, M0);
-    Pin.ldtr_nw(2, 5, X2, false);
-    Pin.ldblk_nw(3, 5, X3);
-    Pin.ldblk_nw(5, 5, X5);
-    Pin.ldblk_nw(4, 5, X4);
-    Pin.wait_ld();
-    FBUS_UNROLL
-    for (int e = 0; e < 9; ++e) M0[e] += a * X1[e];
-    Pout.stblk(0, 5, M0);
-    FBUS_UNROLL
-    for (int i = 0; i < 3; ++i)
-        FBUS_UNROLL
-        for (int j = 0; j < 3; ++j) {
-            double t = X2[i * 3 + j];
-            t -= a * X4[i * 3 + j];
-            if (i == 0) { t += u2 * X2[3 + j]; t -= u1 * X2[6 + j]; }
-            else if (i == 1) { t += u0 * X2[6 + j]; t -= u2 * X2[j]; }
-            else { t += u1 * X2[j]; t -= u0 * X2[3 + j]; }
-            M2[i * 3 + j] = t;
-        }
-    FBUS_UNROLL
-    for (int i = 0; i < 3; ++i)
-        FBUS_UNROLL
-        for (int j = 0; j < 3; ++j) {
-            double s = X1[i * 3 + j];
-            s += a * X5[i * 3 + j];
-            FBUS_UNROLL
-            for (int c = 0; c < 3; ++c) {
-                s += A[i * 3 + c] * X2[c * 3 + j];
-                s += B[i * 3 + c] * X3[c * 3 + j];
-            }
-            M0[i * 3 + j] = s;  // M1 (M0 is stored already)
-        }
-    Pout.sttr(1, 5, M0);
-    Pout.sttr(2, 5, M2);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -66,10 +66,6 @@ __device__ __forceinline__ void tm_free_cta(uint32_t addr) {
 }
 
 __device__ constexpr uint32_t tm_blk_col(int bi, int bj) { return 18u * (uint32_t)(bj * (bj + 1) / 2 + bi); }  // bi <= bj
-constexpr uint32_t TM_K5_ALT = 378u;  // second copy of the blocks (0,5), (1,5), (2,5): columns 378..431 of the 512
-constexpr uint32_t TM_K5_OFF = TM_K5_ALT - 18u * 15u;
-__device__ __forceinline__ void tm_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tm_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // Same interface as CovX (fbus_math.cuh).  Every call must be made by all 32 lanes of the warp (tcgen05 .sync.aligned);
 // lanes that have nothing to do run the same code with neutral operands.
@@ -79,12 +75,6 @@ struct CovTM {
     static constexpr bool kBlocked = true;  // block access is the cheap unit
     uint32_t base;         // TMEM address: lane partition of this warp, column 0 of the covariance
     double* TL = nullptr;  // TLR: the top-left 9x9 lives in the caller's registers
-    // FBUS_K5 (fbus_kernel_split.cuh): the cross blocks (0,5), (1,5), (2,5) ping-pong between their home columns and a second copy in
-    // the spare columns (TM_K5_ALT); off5 = 0 or TM_K5_ALT - tm_blk_col(0,5) selects the copy the accessor reads and writes
-    uint32_t off5 = 0;
-    __device__ __forceinline__ uint32_t blk_addr(int bi, int bj) const {  // bi <= bj
-        return base + tm_blk_col(bi, bj) + ((bj == 5 && bi < 3) ? off5 : 0u);
-    }
     __device__ __forceinline__ void fence_st() const { tm_wait_st(); }
     __device__ __forceinline__ double ld(int i, int j) const {
         if (TLR && i < 9 && j < 9) return TL[tlidx(i, j)];
@@ -104,12 +94,12 @@ struct CovTM {
     }
     // raw block as stored (bi <= bj), no wait
     __device__ __forceinline__ void ldraw(int bi, int bj, double* X) const {
-        const uint32_t a = blk_addr(bi, bj);
+        const uint32_t a = base + tm_blk_col(bi, bj);
         tm_ld8(a, X);
         tm_ld1(a + 16u, X[8]);
     }
     __device__ __forceinline__ void straw(int bi, int bj, const double* X) const {
-        const uint32_t a = blk_addr(bi, bj);
+        const uint32_t a = base + tm_blk_col(bi, bj);
 #if FBUS_TMEM_WIDE_ST
         tm_st8(a, X);  // one 16-column store: needs the eight values in consecutive registers (ptxas adds moves)
         tm_st1(a + 16u, X[8]);
