@@ -348,34 +348,40 @@ def run_ours(args):
 
     # ---- BASELINE configs[2]: 4 096 Monte-Carlo filters on one B200 (latency / occupancy case, 32-filter CTAs) ---------
     small = None
+    small_1k = None
     if not args.no_solves:
-        Bs = 4096
-        fs = BatchFilter(cfg, batch=Bs, device=local)
-        s_stream = torch.cuda.ExternalStream(fs.stream, device=dev)
-        imu_s = torch.empty((N, 6, Bs), dtype=torch.float64, device=dev)
-        id_s = torch.empty((W, 1, Bs), dtype=torch.int32, device=dev)
-        pose_s = torch.empty((W, 1, 7, Bs), dtype=torch.float64, device=dev)
-        fs.SynthStreams(synth.make_synth_spec(traj, seed=20260117 + 3, filter_offset=rank * Bs), imu_s.data_ptr(), id_s.data_ptr(),
-                        pose_s.data_ptr())
+        def small_run(Bs):
+            fs = BatchFilter(cfg, batch=Bs, device=local)
+            s_stream = torch.cuda.ExternalStream(fs.stream, device=dev)
+            imu_s = torch.empty((N, 6, Bs), dtype=torch.float64, device=dev)
+            id_s = torch.empty((W, 1, Bs), dtype=torch.int32, device=dev)
+            pose_s = torch.empty((W, 1, 7, Bs), dtype=torch.float64, device=dev)
+            fs.SynthStreams(synth.make_synth_spec(traj, seed=20260117 + 3, filter_offset=rank * Bs), imu_s.data_ptr(), id_s.data_ptr(),
+                            pose_s.data_ptr())
 
-        def small_step(kk):
-            ti, tf = shifted(traj, kk)
-            fs.StepWindows(capi.make_imu_stream(ti, imu_s.data_ptr(), Bs, capi.FBUS_MEM_DEVICE),
-                           capi.make_det_frames(tf, id_s.data_ptr(), pose_s.data_ptr(), Bs, 1, capi.FBUS_MEM_DEVICE), traj["win_off"], 0, W)
-        reps = max(K, 5) * 4
-        for kk in range(3):
-            small_step(kk)
-        fs.Synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(s_stream)
-        for kk in range(reps):
-            small_step(3 + kk)
-        s1.record(s_stream)
-        fs.Synchronize()
+            def small_step(kk):
+                ti, tf = shifted(traj, kk)
+                fs.StepWindows(capi.make_imu_stream(ti, imu_s.data_ptr(), Bs, capi.FBUS_MEM_DEVICE),
+                               capi.make_det_frames(tf, id_s.data_ptr(), pose_s.data_ptr(), Bs, 1, capi.FBUS_MEM_DEVICE), traj["win_off"], 0, W)
+            reps = max(K, 5) * 4
+            for kk in range(3):
+                small_step(kk)
+            fs.Synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(s_stream)
+            for kk in range(reps):
+                small_step(3 + kk)
+            s1.record(s_stream)
+            fs.Synchronize()
+            fs.close()
+            return world * Bs * steps_per_filter * reps / (s0.elapsed_time(s1) * 1e-3), s0.elapsed_time(s1) / reps
+        v, ms = small_run(4096)
         small = {"workload": "BASELINE configs[2]: 4,096 Monte-Carlo filters, 1 s of 200 Hz IMU + 25 Hz marker poses per launch",
-                 "value": world * Bs * steps_per_filter * reps / (s0.elapsed_time(s1) * 1e-3), "unit": UNIT,
-                 "ms_per_launch": s0.elapsed_time(s1) / reps}
-        fs.close()
+                 "value": v, "unit": UNIT, "ms_per_launch": ms,
+                 "kernel": "ekf_window_split_kernel<32> (one thread per filter, 32-filter CTAs): 28 filters per SM, latency-bound"}
+        v, ms = small_run(1024)
+        small_1k = {"workload": "1,024 Monte-Carlo filters, same streams", "value": v, "unit": UNIT, "ms_per_launch": ms,
+                    "kernel": "ekf_window_lane2_kernel (nine lanes per filter, 7 filters per CTA)"}
 
     # ---- the live use of the reference: ONE filter, one detection frame per call with host arrays (what the C++ shim does
     #      in SetDetectionResultUpdated): latency of a frame, H2D of its ~8 IMU samples and the synchronisation included ----
@@ -430,7 +436,7 @@ def run_ours(args):
                 "dtype": "f64", "data": "synthetic", "config": workload_config(B, world), "e2e": e2e, "e2e_f64_si": e2e_f64,
                 "e2e_montecarlo": e2e_mc, "strong_scaling": strong, "gpu_launches": K, "library_build": library_build_info(),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "stats": stats, "solves": solves,
-                "small_batch": small, "single_filter": single, "config4": config4, "config4_gn_tol": config4_tol,
+                "small_batch": small, "small_batch_1024": small_1k, "single_filter": single, "config4": config4, "config4_gn_tol": config4_tol,
                 "timing": "CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks"}
         print(json.dumps(line), file=JSON_OUT or sys.stdout, flush=True)
     if world > 1:
